@@ -1,0 +1,75 @@
+// Library-wide pieces of the C ABI: version, thread-local error string, device attribute cache,
+// lazy resolution of cuTensorMapEncodeTiled (so dlopen works without libcuda / without a GPU).
+#include "common.cuh"
+#include "../../include/ctclip_b200.h"
+#include <mutex>
+
+namespace ctb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                   uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
+                   uint32_t box_outer, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return CTCLIP_ERR_DRIVER;
+  }
+  (void)elem_bytes;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult=%d (inner=%llu outer=%llu pitch=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes, box_inner,
+              box_outer);
+    return CTCLIP_ERR_DRIVER;
+  }
+  return CTCLIP_OK;
+}
+
+}  // namespace ctb
+
+extern "C" int ctclip_version(void) { return CTCLIP_B200_VERSION; }
+extern "C" const char* ctclip_last_error(void) { return ctb::g_err; }

@@ -1,0 +1,417 @@
+// Persistent warp-specialised GEMM for sm_100a: TMA (SWIZZLE_128B) -> shared memory ring ->
+// tcgen05.mma (cta_group::1, M=128, N=BN, K=16, bf16 in / fp32 accumulate in TMEM, two
+// accumulator stages) -> tcgen05.ld epilogue fused with bias / residual / GEGLU / split-K
+// reduction / argmax.
+//
+// Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane),
+// warps 2..5 = epilogue (warp 2 also owns the TMEM allocation). Epilogue warp w reads TMEM lanes
+// [32*(w%4), 32*(w%4)+32), i.e. one output row per thread.
+//
+// Reference ops replaced: see include/ctclip_b200.h (ctclip_gemm_bf16).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/ctclip_b200.h"
+
+namespace ctb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5 };
+
+struct GemmKParams {
+  int M, N, K;
+  int m_blks, n_blks, k_blks;
+  int splits, k_blks_per_split;
+  int n_per_unit;  // 1, or n_blks (argmax: one CTA sweeps all N tiles of its M tile)
+  int n_groups;    // n_blks / n_per_unit
+  int num_units;
+  int epi;
+  void* C;
+  long long ldc;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+  void* C2;
+  long long ldc2;
+  int* arg_out;
+  float* argval_out;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+
+template <int BN, int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const int ng = unit % p.n_groups;
+        const int rest = unit / p.n_groups;
+        const int m_blk = rest % p.m_blks;
+        const int split = rest / p.m_blks;
+        const int kb0 = split * p.k_blks_per_split;
+        const int kb1 = min(p.k_blks, kb0 + p.k_blks_per_split);
+        for (int j = 0; j < p.n_per_unit; j++) {
+          const int n_blk = ng * p.n_per_unit + j;
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
+            uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
+            if (AMAJ == 0) {
+              tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; i++)
+                tma_load_2d(a_dst + i * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + i * 64,
+                            kb * BK);
+            }
+            if (BMAJ == 0) {
+              tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; i++)
+                tma_load_2d(b_dst + i * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + i * 64,
+                            kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(/*bf16*/ 1, AMAJ, BMAJ, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const int rest = unit / p.n_groups;
+        const int split = rest / p.m_blks;
+        const int kb0 = split * p.k_blks_per_split;
+        const int kb1 = min(p.k_blks, kb0 + p.k_blks_per_split);
+        for (int j = 0; j < p.n_per_unit; j++, it++) {
+          const uint32_t acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t adesc = (AMAJ == 0) ? umma_smem_desc(a_addr + k * 32, 16, 1024)
+                                                 : umma_smem_desc(a_addr + k * 2048, BK * 128, 1024);
+              const uint64_t bdesc = (BMAJ == 0) ? umma_smem_desc(b_addr + k * 32, 16, 1024)
+                                                 : umma_smem_desc(b_addr + k * 2048, BK * 128, 1024);
+              umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int ng = unit % p.n_groups;
+      const int rest = unit / p.n_groups;
+      const int m_blk = rest % p.m_blks;
+      const long long row = (long long)m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float best_v = -INFINITY;
+      int best_i = 0;
+      for (int j = 0; j < p.n_per_unit; j++, it++) {
+        const int n_blk = ng * p.n_per_unit + j;
+        const uint32_t acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+          const int col0 = n_blk * BN + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + c * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
+          const int ncols = min(32, p.N - col0);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (i < ncols) v[i] += __ldg(p.bias + col0 + i);
+          }
+          if (p.epi == EPI_ARGMAX) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (i < ncols && v[i] > best_v) { best_v = v[i]; best_i = col0 + i; }
+            continue;
+          }
+          if (!row_ok) continue;
+          if (p.epi == EPI_BF16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              store_bf16x32(dst, v);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (i < ncols) dst[i] = __float2bfloat16(v[i]);
+            }
+          } else if (p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+            float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+            const float* rs = (p.epi == EPI_RESID_F32) ? (p.resid + row * p.ldr + col0) : nullptr;
+            const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                             (rs == nullptr || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (rs != nullptr) {
+                  const float4 r = *reinterpret_cast<const float4*>(rs + 4 * i);
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(dst + 4 * i) = o;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (i < ncols) dst[i] = v[i] + (rs != nullptr ? rs[i] : 0.f);
+            }
+          } else if (p.epi == EPI_GEGLU) {
+            if (p.C != nullptr) {
+              __nv_bfloat16* hdst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(hdst) & 15) == 0)) {
+                store_bf16x32(hdst, v);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                  if (i < ncols) hdst[i] = __float2bfloat16(v[i]);
+              }
+            }
+            __nv_bfloat16* gdst = reinterpret_cast<__nv_bfloat16*>(p.C2) + row * p.ldc2 + (col0 >> 1);
+            float g[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) g[i] = gelu_erf(v[2 * i + 1]) * v[2 * i];
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0)) {
+              uint4* d4 = reinterpret_cast<uint4*>(gdst);
+#pragma unroll
+              for (int i = 0; i < 2; i++) {
+                uint4 u;
+                u.x = pack_bf16x2(g[8 * i + 0], g[8 * i + 1]);
+                u.y = pack_bf16x2(g[8 * i + 2], g[8 * i + 3]);
+                u.z = pack_bf16x2(g[8 * i + 4], g[8 * i + 5]);
+                u.w = pack_bf16x2(g[8 * i + 6], g[8 * i + 7]);
+                d4[i] = u;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i++)
+                if (2 * i < ncols) gdst[i] = __float2bfloat16(g[i]);
+            }
+          } else if (p.epi == EPI_ATOMIC_F32) {
+            float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i),
+                             "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                             : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (i < ncols) atomicAdd(dst + i, v[i]);
+            }
+          }
+        }
+        // release this accumulator stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (p.epi == EPI_ARGMAX && row_ok) {
+        p.arg_out[row] = best_i;
+        if (p.argval_out != nullptr) p.argval_out[row] = best_v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int AMAJ, int BMAJ>
+static int launch_gemm(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (AMAJ == 0)
+    rc = encode_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->K, (uint64_t)a->M,
+                        (uint64_t)a->lda * 2, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = encode_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->A, (uint64_t)a->M, (uint64_t)a->K,
+                        (uint64_t)a->lda * 2, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (BMAJ == 0)
+    rc = encode_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->K, (uint64_t)a->N,
+                        (uint64_t)a->ldb * 2, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = encode_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->B, (uint64_t)a->N, (uint64_t)a->K,
+                        (uint64_t)a->ldb * 2, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+
+  p.n_blks = ceil_div(a->N, BN);
+  p.n_per_unit = (p.epi == EPI_ARGMAX) ? p.n_blks : 1;
+  p.n_groups = p.n_blks / p.n_per_unit;
+  p.num_units = p.m_blks * p.n_groups * p.splits;
+
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(a != nullptr, "gemm: null args");
+  CTB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  CTB_CHECK_ARG(a->A && a->B, "gemm: null operand");
+  CTB_CHECK_ARG((a->lda * 2) % 16 == 0 && (a->ldb * 2) % 16 == 0,
+                "gemm: operand pitch must be a multiple of 16 bytes (lda=%lld ldb=%lld)",
+                (long long)a->lda, (long long)a->ldb);
+  CTB_CHECK_ARG(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: operands must be 16B aligned");
+  CTB_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 5, "gemm: bad epilogue %d", a->epilogue);
+  CTB_CHECK_ARG(a->splits >= 1, "gemm: splits must be >= 1");
+  CTB_CHECK_ARG(a->splits == 1 || a->epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the ATOMIC_F32 epilogue");
+  if (a->epilogue == EPI_ARGMAX) CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
+  else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU, "gemm: null C");
+  if (a->epilogue == EPI_GEGLU) CTB_CHECK_ARG(a->C2 != nullptr && (a->N % 2) == 0, "gemm: GEGLU needs C2 and even N");
+  if (a->epilogue == EPI_RESID_F32) CTB_CHECK_ARG(a->resid != nullptr, "gemm: RESID_F32 needs resid");
+
+  GemmKParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.m_blks = ceil_div(a->M, BM);
+  p.k_blks = ceil_div(a->K, BK);
+  p.splits = a->splits > p.k_blks ? p.k_blks : a->splits;
+  p.k_blks_per_split = ceil_div(p.k_blks, p.splits);
+  p.splits = ceil_div(p.k_blks, p.k_blks_per_split);  // no empty splits
+  p.epi = a->epilogue;
+  p.C = a->C; p.ldc = a->ldc;
+  p.bias = a->bias;
+  p.resid = a->resid; p.ldr = a->ldr;
+  p.C2 = a->C2; p.ldc2 = a->ldc2;
+  p.arg_out = a->arg_out; p.argval_out = a->argval_out;
+
+  // Tile-N selection: 256 where it divides N (fewest B re-reads per MMA), else 128, 64 for tiny N.
+  int bn;
+  if (a->N % 256 == 0) bn = 256;
+  else if (a->N > 64) bn = 128;
+  else bn = 64;
+  // keep at least ~1 wave of work for mid-sized problems
+  if (bn == 256 && a->epilogue != EPI_ARGMAX &&
+      (long long)ceil_div(a->M, BM) * (a->N / 256) * p.splits < num_sms() && a->N % 128 == 0) bn = 128;
+
+#define CTB_DISPATCH(BN_)                                                                    \
+  do {                                                                                       \
+    if (a->a_major == 0 && a->b_major == 0) return launch_gemm<BN_, 0, 0>(a, p, stream);     \
+    if (a->a_major == 1 && a->b_major == 1) return launch_gemm<BN_, 1, 1>(a, p, stream);     \
+    if (a->a_major == 0 && a->b_major == 1) return launch_gemm<BN_, 0, 1>(a, p, stream);     \
+    return launch_gemm<BN_, 1, 0>(a, p, stream);                                             \
+  } while (0)
+  if (bn == 256) CTB_DISPATCH(256);
+  if (bn == 128) CTB_DISPATCH(128);
+  CTB_DISPATCH(64);
+#undef CTB_DISPATCH
+}

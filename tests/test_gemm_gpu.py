@@ -1,0 +1,104 @@
+"""GEMM family (tcgen05/TMA) against a plain fp32 matmul of the same bf16-rounded operands.
+
+Tolerance: operands are identical bf16 values on both sides, accumulation is fp32 on both, so
+the only difference is summation order -> rel 2e-3 of the output scale (bf16 outputs: + 2^-8).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(rows, cols, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _close(got, ref, tol):
+    got = got.float()
+    ref = ref.float()
+    denom = ref.abs().max().clamp_min(1e-6)
+    err = ((got - ref).abs().max() / denom).item()
+    assert err < tol, f"rel err {err:.3e} >= {tol}"
+    return err
+
+
+SHAPES = [
+    (128, 256, 64), (256, 512, 512), (384, 768, 512), (1000, 2816, 512), (4096, 512, 1408),
+    (130, 96, 200), (128, 64, 4000), (256, 8192, 512), (8, 512, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_nt_bf16_out(M, N, K):
+    from ct_clip_b200 import ops
+    A, B = _mk(M, K, 1), _mk(N, K, 2)
+    Cb = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, M=M, N=N, K=K, epilogue=ops.EPI_BF16, C_out=Cb)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    _close(Cb, ref, 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (1000, 2816, 512), (130, 96, 200)])
+def test_gemm_f32_bias_resid(M, N, K):
+    from ct_clip_b200 import ops
+    A, B = _mk(M, K, 3), _mk(N, K, 4)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    Cf = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, M=M, N=N, K=K, epilogue=ops.EPI_F32, C_out=Cf, bias=bias)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias
+    _close(Cf, ref, 2e-3)
+    out = resid.clone()
+    ops.gemm(A, B, M=M, N=N, K=K, epilogue=ops.EPI_RESID_F32, C_out=out, resid=out, bias=bias)
+    torch.cuda.synchronize()
+    _close(out, ref + resid, 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2816, 512), (384, 256, 128)])
+def test_gemm_geglu(M, N, K):
+    from ct_clip_b200 import ops
+    A, B = _mk(M, K, 5), _mk(N, K, 6, 0.05)
+    H = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    G = torch.empty(M, N // 2, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(A, B, M=M, N=N, K=K, epilogue=ops.EPI_GEGLU, C_out=H, C2=G)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    _close(H, ref, 1e-2)
+    refg = torch.nn.functional.gelu(ref[:, 1::2]) * ref[:, 0::2]
+    _close(G, refg, 1e-2)
+
+
+@pytest.mark.parametrize("amaj,bmaj", [(1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K,splits", [(768, 512, 4096, 1), (2816, 512, 8192, 8), (512, 4000, 1024, 3), (256, 128, 200, 2)])
+def test_gemm_mn_major_atomic(amaj, bmaj, M, N, K, splits):
+    """Weight-gradient form: operands stored [K, rows]; split-K accumulation with red.add."""
+    from ct_clip_b200 import ops
+    At, Bt = _mk(K, M, 7), _mk(K, N, 8)  # stored reduction-major
+    A = At if amaj == 1 else At.t().contiguous()
+    B = Bt if bmaj == 1 else Bt.t().contiguous()
+    Cf = torch.zeros(M, N, device="cuda")
+    ops.gemm(A, B, M=M, N=N, K=K, a_major=amaj, b_major=bmaj, epilogue=ops.EPI_ATOMIC_F32, C_out=Cf, splits=splits)
+    torch.cuda.synchronize()
+    ref = At.float().t() @ Bt.float()
+    _close(Cf, ref, 2e-3)
+
+
+def test_gemm_argmax():
+    from ct_clip_b200 import ops
+    M, N, K = 1000, 8192, 512
+    A, B = _mk(M, K, 9), _mk(N, K, 10)
+    idx = torch.empty(M, dtype=torch.int32, device="cuda")
+    val = torch.empty(M, device="cuda")
+    ops.gemm(A, B, M=M, N=N, K=K, epilogue=ops.EPI_ARGMAX, arg_out=idx, argval_out=val)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    rv, ri = ref.max(dim=1)
+    # values must agree; indices may differ only where the top-2 gap is below fp32 summation noise
+    _close(val, rv, 2e-3)
+    agree = (idx.long() == ri).float().mean().item()
+    assert agree > 0.995, agree
+    picked = ref.gather(1, idx.long()[:, None])[:, 0]
+    assert ((rv - picked).abs() <= 1e-3 * rv.abs().max()).all()
