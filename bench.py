@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- CT volumes/sec through the full contrastive step (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W                  our arm (B200 kernels)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...          data parallel, one rank per GPU
+  python bench.py --impl reference ...                           reference arm: the reference algorithm's own CPU
+                                                                 PyTorch path (oracle port; the Python reference
+                                                                 cannot travel to the GPU box) on the host cores
+
+A "step" = forward + InfoNCE loss + backward + gradient all-reduce + clip(0.5) + Adam on one synthetic batch
+(BASELINE.json configs[1]: CTViT dim 512, 12+12 layers, 480x480x240 int16 volumes, patch (20,20,10), 128-token
+text, bs 8 per GPU). `value` is timed with inputs resident in HBM; `e2e` adds the pinned-host -> device copy of
+every batch and the loss read-back, through the public CTClipTrainer API.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--depth", type=int, default=12, help="spatial_depth = temporal_depth (configs[1]: 12; reference scripts: 4)")
+    ap.add_argument("--batch", type=int, default=8, help="volumes per GPU")
+    ap.add_argument("--image", type=int, default=480)
+    ap.add_argument("--frames", type=int, default=240)
+    ap.add_argument("--text-len", type=int, default=128)
+    ap.add_argument("--bert-layers", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-volumes", type=int, default=1)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sus=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def flops_per_volume(cfgd):
+    """SURVEY 8(d) algorithmic FLOPs of one forward pass per volume (and the x3 step estimate)."""
+    D, I, F, P, C, L = 512, 256, 1365, cfgd["P"], 8192, 512
+    N, S, T = cfgd["N"], cfgd["S"], cfgd["T"]
+    layer_s = 54 * N * D + 8 * N * D * I + 4 * N * S * I + 6 * N * D * F
+    layer_t = 54 * N * D + 8 * N * D * I + 4 * N * T * I + 6 * N * D * F
+    fwd = 2 * N * P * D + cfgd["depth"] * (layer_s + layer_t) + 2 * N * D * C + 2 * S * D * L
+    return fwd, 3 * (fwd - 2 * N * D * C) + 2 * N * D * C
+
+
+def build_model(args, device):
+    from transformers import BertConfig, BertModel
+
+    from ct_clip_b200 import CTCLIP, CTViT
+    torch.manual_seed(0)
+    vit = CTViT(dim=512, codebook_size=8192, image_size=args.image, patch_size=args.image // 24 if args.image % 24 == 0 else 16,
+                temporal_patch_size=args.frames // 24 if args.frames % 24 == 0 else 8, spatial_depth=args.depth,
+                temporal_depth=args.depth, dim_head=32, heads=8)
+    bert = BertModel(BertConfig(num_hidden_layers=args.bert_layers, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    h, w = vit.patch_height_width
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=h * w * 512, dim_latent=512)
+    return clip.to(device)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    from ct_clip_b200 import _lib, ops
+    from ct_clip_b200.data import SyntheticCTReportDataset
+    from ct_clip_b200.trainer import CTClipTrainer, _Tokens
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N > 1)"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    clip = build_model(args, device)
+    ds = SyntheticCTReportDataset(10 ** 9, frames=args.frames, image=args.image, n_text=args.text_len, seed=1234 + 7919 * rank)
+    trainer = CTClipTrainer(clip, num_train_steps=10 ** 9, batch_size=args.batch, train_dataset=ds, num_workers=0,
+                            save_model_every=0, save_results_every=0, results_folder="/tmp/ctclip_bench")
+    # two distinct synthetic batches in pinned host memory (885 MB of int16 per batch: larger than the 126 MB L2,
+    # so consecutive steps cannot reuse cached inputs)
+    host = []
+    for j in range(2):
+        items = [ds[j * args.batch + i] for i in range(args.batch)]
+        vol, tok = ds.collate(items)
+        host.append((vol.pin_memory(), tok["input_ids"].pin_memory(), tok["attention_mask"].pin_memory()))
+    dev = [(v.to(device), _Tokens(i.to(device), m.to(device))) for v, i, m in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps (value)
+    for w_ in range(args.warmup):
+        trainer.step_on_batch(*dev[w_ % 2])
+    barrier()
+    gemm_events = []
+    ops.GEMM_TIMER = gemm_events
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        loss = trainer.step_on_batch(*dev[s % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = (_lib.launch_count - launches0) // max(1, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ops.GEMM_TIMER = None
+    loss_val = float(loss.item())
+
+    # ---- end-to-end through the public API path: pinned host -> device every step + loss read-back
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(args.steps):
+        v, i, m = host[s % 2]
+        vd = v.to(device, non_blocking=True)
+        tk = _Tokens(i.to(device, non_blocking=True), m.to(device, non_blocking=True))
+        l_ = trainer.step_on_batch(vd, tk)
+        _ = l_.item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM family) from CUDA events recorded around its launches
+    gsum_ms, gflops, n_g = 0.0, 0.0, 0
+    for ev0, ev1, fl in gemm_events:
+        gsum_ms += ev0.elapsed_time(ev1)
+        gflops += fl
+        n_g += 1
+    peaks = load_peaks()
+    achieved = (gflops / (gsum_ms * 1e-3) / 1e12) if gsum_ms > 0 else 0.0
+    vit = clip.visual_transformer
+    g = vit.geom
+    T = args.frames // g.temporal_patch
+    cfgd = dict(P=g.patch_voxels, N=T * g.S, S=g.S, T=T, depth=args.depth)
+    fwd_flops, step_flops = flops_per_volume(cfgd)
+    if rank != 0:
+        return
+    vols = args.batch * world * args.steps
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+    out = {
+        "metric": "CT volumes/sec contrastive step @ 480x480x240, bs8/GPU",
+        "value": vols / (ms * 1e-3), "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: CTViT dim512 depth{args.depth}+{args.depth}, {args.image}x{args.image}x{args.frames} "
+                               f"int16 volumes, patch ({g.patch_hw[0]},{g.patch_hw[1]},{g.temporal_patch}), {args.text_len}-token text, "
+                               f"BERT-base({args.bert_layers}L, random init), bs{args.batch}/GPU",
+                   "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "l2": "two alternating input batches of 885 MB each (> 126 MB L2); activations of a step exceed L2 by >100x",
+                   "text_tower": "HF BertModel executed by PyTorch (not yet on the native kernels)",
+                   "step_tflop_per_volume_algorithmic": step_flops / 1e12},
+        "e2e": {"value": vols / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "loss": loss_val,
+        "clocks": clocks,
+        "roofline": {"kernel": "gemm_tc_kernel (tcgen05/TMA GEMM family, all instantiations)", "bound": "tensor",
+                     "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tf_sus"] if peaks["tf_sus"] else None, "traffic": None,
+                     "peak_source": f"{peaks['src']} bf16_tflops_sustained", "launches_per_step": n_g // max(1, args.steps),
+                     "share_of_step": gsum_ms / ms if ms > 0 else None},
+        "model_tflops": step_flops * vols / (ms * 1e-3) / 1e12,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, sample_volumes=args.cpu_sample_volumes, timed_steps=1)
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(args, sample_volumes=1, timed_steps=1):
+    """The reference algorithm's CPU PyTorch path (oracle port: the Python reference itself cannot travel to the GPU
+    box) on the host cores: forward + loss + backward of `sample_volumes` full-size volumes."""
+    from oracle import ctclip_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = args.image // 24 if args.image % 24 == 0 else 16
+    pt = args.frames // 24 if args.frames % 24 == 0 else 8
+    cfg = O.CTCLIPConfig(vit=O.CTViTConfig(image_size=args.image, patch_size=p, temporal_patch_size=pt, spatial_depth=args.depth,
+                                           temporal_depth=args.depth), bert=O.BertConfigLite(layers=args.bert_layers))
+    shapes = oracle_shapes(cfg)
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "_codebook" not in k else v)
+          for k, v in O.synth_state_dict(shapes, 0).items()}
+    hu, ids, mask = O.synth_inputs(sample_volumes, args.frames, args.image, args.text_len)
+    video = hu.float() / 1000.0
+    t0 = time.time()
+    for _ in range(timed_steps):
+        out = O.ctclip_forward(sd, cfg, ids, mask, video, training=True)
+        out["loss"].backward()
+    dt = time.time() - t0
+    return {"value": sample_volumes * timed_steps / dt, "unit": "volumes/s", "cores": cores, "kind": "port",
+            "sample": f"{timed_steps} step(s) of forward+loss+backward on {sample_volumes} full-size volume(s) "
+                      f"({args.image}x{args.image}x{args.frames}, depth {args.depth}+{args.depth}, BERT {args.bert_layers}L), "
+                      f"fp32, torch CPU {cores} threads, no optimiser step", "seconds": dt}
+
+
+def oracle_shapes(cfg):
+    """State-dict shapes of the reference layout for an oracle config (no module construction needed)."""
+    v, b = cfg.vit, cfg.bert
+    D, I, F, P, Hd = v.dim, v.dim_head * v.heads, v.ff_inner, v.patch_voxels, v.heads
+    s = {"temperature": (), "to_text_latent.weight": (cfg.dim_latent, cfg.dim_text),
+         "to_visual_latent.weight": (cfg.dim_latent, cfg.dim_image())}
+    pre = "visual_transformer."
+    s.update({pre + "spatial_rel_pos_bias.net.0.0.weight": (D, 2), pre + "spatial_rel_pos_bias.net.0.0.bias": (D,),
+              pre + "spatial_rel_pos_bias.net.1.0.weight": (D, D), pre + "spatial_rel_pos_bias.net.1.0.bias": (D,),
+              pre + "spatial_rel_pos_bias.net.2.weight": (Hd, D), pre + "spatial_rel_pos_bias.net.2.bias": (Hd,),
+              pre + "to_patch_emb.1.weight": (P,), pre + "to_patch_emb.1.bias": (P,), pre + "to_patch_emb.2.weight": (D, P),
+              pre + "to_patch_emb.2.bias": (D,), pre + "to_patch_emb.3.weight": (D,), pre + "to_patch_emb.3.bias": (D,),
+              pre + "vq._codebook.embed": (1, v.codebook_size, D), pre + "vq._codebook.cluster_size": (1, v.codebook_size)})
+    for stack, depth in (("enc_spatial_transformer", v.spatial_depth), ("enc_temporal_transformer", v.temporal_depth)):
+        for i in range(depth):
+            lp = f"{pre}{stack}.layers.{i}."
+            s.update({lp + "0.dsconv.weight": (D, 1, 3, 3, 3), lp + "0.dsconv.bias": (D,), lp + "1.norm.gamma": (D,),
+                      lp + "1.norm.beta": (D,), lp + "1.q_scale": (v.dim_head,), lp + "1.k_scale": (v.dim_head,),
+                      lp + "1.to_q.weight": (I, D), lp + "1.to_kv.weight": (2 * I, D), lp + "1.to_out.weight": (D, I),
+                      lp + "3.0.weight": (D,), lp + "3.0.bias": (D,), lp + "3.1.weight": (2 * F, D), lp + "3.4.weight": (D, F)})
+        s.update({f"{pre}{stack}.norm_out.gamma": (D,), f"{pre}{stack}.norm_out.beta": (D,)})
+    t = "text_transformer."
+    s.update({t + "embeddings.word_embeddings.weight": (b.vocab_size, b.hidden), t + "embeddings.position_embeddings.weight": (b.max_pos, b.hidden),
+              t + "embeddings.token_type_embeddings.weight": (b.type_vocab, b.hidden), t + "embeddings.LayerNorm.weight": (b.hidden,),
+              t + "embeddings.LayerNorm.bias": (b.hidden,)})
+    for i in range(b.layers):
+        lp = f"{t}encoder.layer.{i}."
+        for nm in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+            s.update({lp + nm + ".weight": (b.hidden, b.hidden), lp + nm + ".bias": (b.hidden,)})
+        s.update({lp + "attention.output.LayerNorm.weight": (b.hidden,), lp + "attention.output.LayerNorm.bias": (b.hidden,),
+                  lp + "intermediate.dense.weight": (b.intermediate, b.hidden), lp + "intermediate.dense.bias": (b.intermediate,),
+                  lp + "output.dense.weight": (b.hidden, b.intermediate), lp + "output.dense.bias": (b.hidden,),
+                  lp + "output.LayerNorm.weight": (b.hidden,), lp + "output.LayerNorm.bias": (b.hidden,)})
+    return s
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vols_per_step = 1
+    t_all = []
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(args, sample_volumes=vols_per_step, timed_steps=1)
+    for _ in range(max(1, min(args.steps, 2))):
+        r = cpu_baseline(args, sample_volumes=vols_per_step, timed_steps=1)
+        t_all.append(r["seconds"])
+    ms = 1e3 * sum(t_all) / len(t_all)
+    val = vols_per_step / (ms * 1e-3)
+    cores = os.cpu_count() or 1
+    out = {"impl": "reference", "metric": "CT volumes/sec contrastive step @ 480x480x240, bs8/GPU", "value": val,
+           "unit": "volumes/s", "n_gpus": args.gpus, "steps": len(t_all), "warmup": min(args.warmup, 1), "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"same model/config as the b200 arm; each step = a bounded sample of {vols_per_step} volume "
+                                  "(forward+loss+backward, fp32, torch CPU)", "parallelism": "cpu"},
+           "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": cores, "kind": "port",
+                            "sample": f"{vols_per_step} full-size volume per step, {len(t_all)} timed step(s)"},
+           "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -12,6 +12,11 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libctclip_b200.so"
 _lib = None
 
+P = C.c_void_p
+I32 = C.c_int32
+I64 = C.c_int64
+F32 = C.c_float
+
 
 class CtclipError(RuntimeError):
     pass
@@ -19,20 +24,95 @@ class CtclipError(RuntimeError):
 
 class GemmArgs(C.Structure):
     _fields_ = [
-        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("a_major", C.c_int32), ("b_major", C.c_int32),
-        ("A", C.c_void_p), ("lda", C.c_int64),
-        ("B", C.c_void_p), ("ldb", C.c_int64),
-        ("epilogue", C.c_int32), ("splits", C.c_int32),
-        ("C", C.c_void_p), ("ldc", C.c_int64),
-        ("bias", C.c_void_p),
-        ("resid", C.c_void_p), ("ldr", C.c_int64),
-        ("C2", C.c_void_p), ("ldc2", C.c_int64),
-        ("arg_out", C.c_void_p), ("argval_out", C.c_void_p),
+        ("M", I32), ("N", I32), ("K", I32), ("a_major", I32), ("b_major", I32),
+        ("A", P), ("lda", I64), ("B", P), ("ldb", I64),
+        ("epilogue", I32), ("splits", I32),
+        ("C", P), ("ldc", I64), ("bias", P), ("resid", P), ("ldr", I64),
+        ("C2", P), ("ldc2", I64), ("arg_out", P), ("argval_out", P),
+        ("norm_cols", I32), ("norm_scale", P),
     ]
 
 
-EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_ATOMIC_F32, EPI_ARGMAX = range(6)
+class LnFwdArgs(C.Structure):
+    _fields_ = [("x", P), ("M", I64), ("D", I32), ("eps", F32), ("gamma", P), ("beta", P),
+                ("xhat_bf16", P), ("raw_bf16", P), ("y_f32", P), ("y_bf16", P), ("rstd_out", P)]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [("M", I64), ("D", I32), ("g_f32", P), ("g_bf16", P), ("gamma", P), ("xhat", P), ("rstd", P),
+                ("dres_in", P), ("add_bf16", P), ("dx_f32", P), ("dx_bf16", P), ("dgamma", P), ("dbeta", P)]
+
+
+class PatchifyArgs(C.Structure):
+    _fields_ = [("video", P), ("dtype", I32), ("scale", F32), ("B", I32), ("C", I32), ("F", I32), ("H", I32),
+                ("W", I32), ("pt", I32), ("p1", I32), ("p2", I32), ("eps", F32), ("xhat", P), ("ld_out", I64)]
+
+
+class PegArgs(C.Structure):
+    _fields_ = [("x", P), ("dy", P), ("y", P), ("y_bf16", P), ("weight", P), ("bias", P), ("dweight", P),
+                ("dbias", P), ("B", I32), ("T", I32), ("H", I32), ("W", I32), ("D", I32), ("temporal", I32),
+                ("lines", I32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("q", P), ("ldq", I64), ("k", P), ("ldk", I64), ("v", P), ("ldv", I64), ("o", P), ("ldo", I64),
+                ("lse", P), ("bias", P), ("bias_t", P),
+                ("n", I32), ("heads", I32), ("dim_head", I32), ("num_seqs", I32), ("seq_inner", I32),
+                ("seq_outer_stride", I64), ("tok_stride", I64), ("scale", F32),
+                ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
+                ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64)]
+
+
+class SgemmArgs(C.Structure):
+    _fields_ = [("M", I32), ("N", I32), ("K", I32), ("A", P), ("lda", I64), ("trans_a", I32),
+                ("B", P), ("ldb", I64), ("trans_b", I32), ("C", P), ("ldc", I64), ("bias", P), ("act", I32),
+                ("mask_ref", P), ("ld_mask", I64), ("accumulate", I32)]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("t_raw", P), ("i_raw", P), ("B", I32), ("L", I32), ("temperature", P), ("t_hat", P), ("i_hat", P),
+                ("inv_norm", P), ("sim", P), ("loss", P), ("dtemperature", P), ("d_t_raw", P), ("d_i_raw", P),
+                ("row0", I32), ("nrows", I32), ("loss_scale", F32)]
+
+
+EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_L2NORM, EPI_BIAS_GELU = range(8)
+
+# name -> argtypes (every entry point returns int and takes the stream last)
+SIGNATURES = {
+    "ctclip_gemm_bf16": [C.POINTER(GemmArgs), P],
+    "ctclip_ln_fwd": [C.POINTER(LnFwdArgs), P],
+    "ctclip_ln_bwd": [C.POINTER(LnBwdArgs), P],
+    "ctclip_patchify": [C.POINTER(PatchifyArgs), P],
+    "ctclip_peg_fwd": [C.POINTER(PegArgs), P],
+    "ctclip_peg_bwd_data": [C.POINTER(PegArgs), P],
+    "ctclip_peg_bwd_weight": [C.POINTER(PegArgs), P],
+    "ctclip_attn_fwd": [C.POINTER(AttnArgs), P],
+    "ctclip_attn_bwd": [C.POINTER(AttnArgs), P],
+    "ctclip_l2norm_bwd": [P, I64, P, I64, P, P, I64, P, I64, I32, I32, P],
+    "ctclip_sgemm_f32": [C.POINTER(SgemmArgs), P],
+    "ctclip_colsum": [P, I32, I64, I64, I32, P, P],
+    "ctclip_cast_f32_bf16": [P, P, I64, P],
+    "ctclip_cpb_inputs": [P, I32, I32, P],
+    "ctclip_cpb_expand": [P, I32, I32, I32, P, P, P],
+    "ctclip_cpb_reduce": [P, I32, I32, I32, P, P],
+    "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
+    "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
+    "ctclip_vq_gather": [P, P, P, I64, I32, P],
+    "ctclip_vq_gather_pool": [P, P, I32, I32, I32, I32, P, P, P],
+    "ctclip_pool_bwd": [P, I32, I32, I32, I32, P, P],
+    "ctclip_vq_ema_accum": [P, P, I64, I32, P, P, P],
+    "ctclip_vq_ema_update": [P, P, P, P, I32, I32, F32, P],
+    "ctclip_prep_weight": [P, I64, I32, P, P, I32, I32, P, P],
+    "ctclip_prep_bias": [P, I64, I32, P, P, P, I32, P, P],
+    "ctclip_unprep_wgrad": [P, I64, P, I64, I32, P, P, I32, P, P, P, P, P, P],
+    "ctclip_clip_loss": [C.POINTER(LossArgs), P],
+    "ctclip_clip_sims": [P, I32, P, I32, I32, P, P, P],
+    "ctclip_grad_sumsq": [P, I64, P, P],
+    "ctclip_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, I32, F32, P, F32, P],
+}
+
+# launches of our own kernels issued through this binding (bench.py reports it as gpu_launches)
+launch_count = 0
 
 
 def lib() -> C.CDLL:
@@ -46,16 +126,21 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(LIB_PATH))
         _lib.ctclip_version.restype = C.c_int
         _lib.ctclip_last_error.restype = C.c_char_p
-        for name in dir(_sigs):
-            if name.startswith("ctclip_"):
-                fn = getattr(_lib, name)
-                fn.restype = C.c_int
-                fn.argtypes = getattr(_sigs, name)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
     return _lib
 
 
-class _sigs:
-    ctclip_gemm_bf16 = [C.POINTER(GemmArgs), C.c_void_p]
+def call(name: str, *args) -> None:
+    """Invoke an entry point; raise CtclipError with the library's message on failure."""
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    launch_count += 1
+    if rc != 0:
+        msg = lib().ctclip_last_error().decode(errors="replace")
+        raise CtclipError(f"{name} failed (rc={rc}): {msg}")
 
 
 def check(rc: int, what: str = "") -> None:

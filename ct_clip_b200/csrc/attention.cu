@@ -1,0 +1,681 @@
+// Cosine-similarity multi-head attention core, forward and backward, flash-style (scores never
+// leave the SM). Replaces attention.py:156-178:
+//     sim = q_hat k_hat^T * scale (+ attn_bias[h,i,j]);  attn = softmax(sim);  out = attn v
+// where q_hat / k_hat are the l2-normalised, per-channel-scaled projections (produced by the
+// L2NORM epilogue of the projection GEMM), plus the autograd backward of the same ops.
+//
+// Why warp-level mma.sync (m16n8k16 bf16) and not tcgen05 here: with dim_head = 32 a 128x576 score
+// block needs 73.7k exponentials (16/clk/SM on the SFU = 4.6k cycles) but only 9.4 MFLOP of
+// tensor work (1.15k cycles at tcgen05 rate, ~2.3k with mma.sync). The kernel is SFU-bound either
+// way; the tcgen05 variant would add TMEM<->register round trips per KV block for no gain.
+// ("attention roofline".)
+//
+// Token addressing is strided so that both factorised stacks run on the single canonical
+// [b,t,h,w,D] layout: row(seq, i) = (seq / seq_inner) * seq_outer_stride + (seq % seq_inner) + i * tok_stride.
+//   spatial : seq=(b,t), i=(h,w): seq_inner=1, seq_outer_stride=S, tok_stride=1
+//   temporal: seq=(b,h,w), i=t  : seq_inner=S, seq_outer_stride=T*S, tok_stride=S
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/ctclip_b200.h"
+
+namespace ctb {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnGeom {
+  int n, heads, seq_inner;
+  long long seq_outer_stride, tok_stride;
+  __device__ __forceinline__ long long row(int seq, int i) const {
+    return (long long)(seq / seq_inner) * seq_outer_stride + (seq % seq_inner) + (long long)i * tok_stride;
+  }
+};
+
+template <int WPG>
+__device__ __forceinline__ void group_sync(int group) {
+  if (WPG == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(WPG * 32) : "memory");
+}
+
+constexpr int DH = 32;           // dim_head of the CTViT stacks (run_train.py:25)
+constexpr int KROW = DH + 8;     // padded row (bf16 elements) of row-major [token][d] tiles: conflict-free frag loads
+
+// Row-major tile loader: dst[n_pad][KROW] <- src rows (64 B each), zero-filled beyond n.
+__device__ __forceinline__ void load_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int head,
+                                          const AttnGeom& g, int seq, int n_pad, int tid, int nthreads) {
+  for (int idx = tid; idx < n_pad * 4; idx += nthreads) {
+    const int r = idx >> 2, part = idx & 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < g.n) val = *reinterpret_cast<const uint4*>(src + g.row(seq, r) * ld + head * DH + part * 8);
+    *reinterpret_cast<uint4*>(dst + r * KROW + part * 8) = val;
+  }
+}
+// Transposed tile loader: dst[DH][tstride] <- src rows, zero-filled beyond n.
+__device__ __forceinline__ void load_rows_t(__nv_bfloat16* dst, int tstride, const __nv_bfloat16* src, long long ld,
+                                            int head, const AttnGeom& g, int seq, int n_pad, int tid, int nthreads) {
+  for (int idx = tid; idx < n_pad * 4; idx += nthreads) {
+    const int r = idx >> 2, part = idx & 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < g.n) val = *reinterpret_cast<const uint4*>(src + g.row(seq, r) * ld + head * DH + part * 8);
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&val);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[(part * 8 + i) * tstride + r] = e[i];
+  }
+}
+// A-operand fragments (16 rows x DH) straight from global memory; rows >= n read as zero.
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[DH / 16][4], const __nv_bfloat16* src, long long ld,
+                                             int head, const AttnGeom& g, int seq, int r0, int lane) {
+  const int gq = lane >> 2, t = lane & 3;
+  const int ra = r0 + gq, rb = r0 + gq + 8;
+  const __nv_bfloat16* pa = src + g.row(seq, ra < g.n ? ra : 0) * ld + head * DH;
+  const __nv_bfloat16* pb = src + g.row(seq, rb < g.n ? rb : 0) * ld + head * DH;
+#pragma unroll
+  for (int kt = 0; kt < DH / 16; kt++) {
+    a[kt][0] = ra < g.n ? *reinterpret_cast<const uint32_t*>(pa + kt * 16 + 2 * t) : 0u;
+    a[kt][1] = rb < g.n ? *reinterpret_cast<const uint32_t*>(pb + kt * 16 + 2 * t) : 0u;
+    a[kt][2] = ra < g.n ? *reinterpret_cast<const uint32_t*>(pa + kt * 16 + 2 * t + 8) : 0u;
+    a[kt][3] = rb < g.n ? *reinterpret_cast<const uint32_t*>(pb + kt * 16 + 2 * t + 8) : 0u;
+  }
+}
+// C[16 x 8*NT] = A[16 x DH] * rows(tile)[key0 .. key0+8*NT)^T  with tile row-major [key][KROW]
+template <int NT>
+__device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[DH / 16][4],
+                                         const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
+  const int gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    if (nt >= nt_valid) continue;  // warp-uniform; tiles beyond the padded sequence stay zero
+    const __nv_bfloat16* kr = tile + (key0 + nt * 8 + gq) * KROW + 2 * t;
+#pragma unroll
+    for (int kt = 0; kt < DH / 16; kt++) {
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kt * 16);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kt * 16 + 8);
+      mma_16816(s[nt], a[kt], b0, b1);
+    }
+  }
+}
+// acc[16 x DH] += P[16 x 8*NT] * X[key0.., :]  with X given transposed: xt[d][tstride] (keys contiguous)
+template <int NT>
+__device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&p)[NT][4],
+                                         const __nv_bfloat16* xt, int tstride, int key0, int lane, int nt_valid = NT) {
+  const int gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; kk++) {
+    if (2 * kk >= nt_valid) continue;
+    uint32_t a[4];
+    a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+    a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+    a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; dt++) {
+      const __nv_bfloat16* vr = xt + (dt * 8 + gq) * tstride + key0 + kk * 16 + 2 * t;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
+      mma_16816(acc[dt], a, b0, b1);
+    }
+  }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int WPG, int GROUPS>
+__global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_attn_args a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
+  const int n_pad = (a.n + 15) & ~15;
+  const int tstride = n_pad + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WPG, wig = warp % WPG;
+  const int gq = lane >> 2, t = lane & 3;
+  const long long item = (long long)blockIdx.x * GROUPS + group;
+  const size_t group_bytes = (size_t)(n_pad * KROW + DH * tstride) * 2;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
+  __nv_bfloat16* sVt = sK + n_pad * KROW;
+  const bool active = item < (long long)a.num_seqs * a.heads;
+  const int head = active ? (int)(item % a.heads) : 0;
+  const int seq = active ? (int)(item / a.heads) : 0;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.o);
+  if (active) {
+    load_rows(sK, k, a.ldk, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+    load_rows_t(sVt, tstride, v, a.ldv, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+  }
+  group_sync<WPG>(group);
+  if (!active) return;
+  const float sc2 = a.scale * kLog2e;
+  const int row_tiles = n_pad / 16;
+  for (int rt = wig; rt < row_tiles; rt += WPG) {
+    const int r0 = rt * 16;
+    uint32_t qa[DH / 16][4];
+    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
+    const int ra = r0 + gq, rb = r0 + gq + 8;
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+    float oacc[DH / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; dt++) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+    for (int key0 = 0; key0 < n_pad; key0 += 64) {
+      float s[8][4];
+      const int rem = n_pad - key0;  // multiple of 16
+      const int ntv = rem >= 64 ? 8 : rem / 8;
+      qk_block<8>(s, qa, sK, key0, lane, ntv);
+      float bm_a = -INFINITY, bm_b = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        const int key = key0 + nt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int kk = key + (e & 1);
+          const int rr = (e < 2) ? ra : rb;
+          float val = s[nt][e] * sc2;
+          if (bias != nullptr && rr < a.n && kk < a.n)
+            val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
+          if (kk >= a.n) val = -INFINITY;
+          s[nt][e] = val;
+        }
+        bm_a = fmaxf(bm_a, fmaxf(s[nt][0], s[nt][1]));
+        bm_b = fmaxf(bm_b, fmaxf(s[nt][2], s[nt][3]));
+      }
+      bm_a = quad_max(bm_a);
+      bm_b = quad_max(bm_b);
+      const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
+      const float corr_a = exp2f(m_a - mn_a), corr_b = exp2f(m_b - mn_b);
+      m_a = mn_a;
+      m_b = mn_b;
+      float ps_a = 0.f, ps_b = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        s[nt][0] = exp2f(s[nt][0] - mn_a);
+        s[nt][1] = exp2f(s[nt][1] - mn_a);
+        s[nt][2] = exp2f(s[nt][2] - mn_b);
+        s[nt][3] = exp2f(s[nt][3] - mn_b);
+        ps_a += s[nt][0] + s[nt][1];
+        ps_b += s[nt][2] + s[nt][3];
+      }
+      l_a = l_a * corr_a + ps_a;
+      l_b = l_b * corr_b + ps_b;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++) {
+        oacc[dt][0] *= corr_a; oacc[dt][1] *= corr_a;
+        oacc[dt][2] *= corr_b; oacc[dt][3] *= corr_b;
+      }
+      // masked / beyond-n_pad keys carry p == 0 and V^T rows are zero-filled there
+      pv_block<8>(oacc, s, sVt, tstride, key0, lane, ntv);
+    }
+    l_a = quad_sum(l_a);
+    l_b = quad_sum(l_b);
+    const float inv_a = 1.f / l_a, inv_b = 1.f / l_b;
+    if (ra < a.n) {
+      __nv_bfloat16* orow = o + g.row(seq, ra) * a.ldo + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++)
+        *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(oacc[dt][0] * inv_a, oacc[dt][1] * inv_a);
+      if (t == 0 && a.lse != nullptr) a.lse[g.row(seq, ra) * a.heads + head] = m_a + log2f(l_a);
+    }
+    if (rb < a.n) {
+      __nv_bfloat16* orow = o + g.row(seq, rb) * a.ldo + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++)
+        *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(oacc[dt][2] * inv_b, oacc[dt][3] * inv_b);
+      if (t == 0 && a.lse != nullptr) a.lse[g.row(seq, rb) * a.heads + head] = m_b + log2f(l_b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, part 1 (query-row parallel): dq_hat.   dlogits = P * (dP - delta), dq = scale * dlogits K
+// ------------------------------------------------------------------------------------------------
+template <int WPG, int GROUPS>
+__global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_attn_args a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
+  const int n_pad = (a.n + 15) & ~15;
+  const int tstride = n_pad + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WPG, wig = warp % WPG;
+  const int gq = lane >> 2, t = lane & 3;
+  const long long item = (long long)blockIdx.x * GROUPS + group;
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW + DH * tstride) * 2;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
+  __nv_bfloat16* sV = sK + n_pad * KROW;
+  __nv_bfloat16* sKt = sV + n_pad * KROW;
+  const bool active = item < (long long)a.num_seqs * a.heads;
+  const int head = active ? (int)(item % a.heads) : 0;
+  const int seq = active ? (int)(item / a.heads) : 0;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
+  const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(a.d_o);
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(a.dq);
+  if (active) {
+    const int tid = wig * 32 + lane;
+    load_rows(sK, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows(sV, v, a.ldv, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t(sKt, tstride, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
+  }
+  group_sync<WPG>(group);
+  if (!active) return;
+  const float sc2 = a.scale * kLog2e;
+  const int row_tiles = n_pad / 16;
+  for (int rt = wig; rt < row_tiles; rt += WPG) {
+    const int r0 = rt * 16;
+    uint32_t qa[DH / 16][4], da[DH / 16][4];
+    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags(da, dO, a.ldo, head, g, seq, r0, lane);
+    const int ra = r0 + gq, rb = r0 + gq + 8;
+    float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
+    if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
+    if (rb < a.n) { lse_b = a.lse[g.row(seq, rb) * a.heads + head]; del_b = a.delta[g.row(seq, rb) * a.heads + head]; }
+    float dqa[DH / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; dt++) dqa[dt][0] = dqa[dt][1] = dqa[dt][2] = dqa[dt][3] = 0.f;
+    for (int key0 = 0; key0 < n_pad; key0 += 32) {
+      float s[4][4], dp[4][4];
+      const int rem = n_pad - key0;
+      const int ntv = rem >= 32 ? 4 : 2;
+      qk_block<4>(s, qa, sK, key0, lane, ntv);
+      qk_block<4>(dp, da, sV, key0, lane, ntv);
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int key = key0 + nt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int kk = key + (e & 1);
+          const int rr = (e < 2) ? ra : rb;
+          float val = s[nt][e] * sc2;
+          if (bias != nullptr && rr < a.n && kk < a.n)
+            val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
+          const float p = (kk < a.n && rr < a.n) ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
+          s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;  // d(q_hat . k_hat)
+        }
+      }
+      pv_block<4>(dqa, s, sKt, tstride, key0, lane, ntv);
+    }
+    if (ra < a.n) {
+      __nv_bfloat16* orow = dq + g.row(seq, ra) * a.ld_dq + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(dqa[dt][0], dqa[dt][1]);
+    }
+    if (rb < a.n) {
+      __nv_bfloat16* orow = dq + g.row(seq, rb) * a.ld_dq + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_bf16x2(dqa[dt][2], dqa[dt][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, part 2 (key-row parallel): dk_hat, dv.  Works on S^T = K Q^T so that P^T / dS^T come out
+// of the MMA in the register layout the next MMA needs as its A operand.
+// ------------------------------------------------------------------------------------------------
+template <int WPG, int GROUPS>
+__global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_attn_args a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
+  const int n_pad = (a.n + 15) & ~15;
+  const int tstride = n_pad + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WPG, wig = warp % WPG;
+  const int gq = lane >> 2, t = lane & 3;
+  const long long item = (long long)blockIdx.x * GROUPS + group;
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW + 2 * DH * tstride) * 2 + (size_t)n_pad * 8;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
+  __nv_bfloat16* sDO = sQ + n_pad * KROW;
+  __nv_bfloat16* sQt = sDO + n_pad * KROW;
+  __nv_bfloat16* sDOt = sQt + DH * tstride;
+  float* sLse = reinterpret_cast<float*>(sDOt + DH * tstride);
+  float* sDel = sLse + n_pad;
+  const bool active = item < (long long)a.num_seqs * a.heads;
+  const int head = active ? (int)(item % a.heads) : 0;
+  const int seq = active ? (int)(item / a.heads) : 0;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
+  const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(a.d_o);
+  const __nv_bfloat16* biasT = reinterpret_cast<const __nv_bfloat16*>(a.bias_t);
+  __nv_bfloat16* dk = reinterpret_cast<__nv_bfloat16*>(a.dk);
+  __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(a.dv);
+  if (active) {
+    const int tid = wig * 32 + lane;
+    load_rows(sQ, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows(sDO, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t(sQt, tstride, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t(sDOt, tstride, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
+    for (int i = tid; i < n_pad; i += WPG * 32) {
+      sLse[i] = i < a.n ? a.lse[g.row(seq, i) * a.heads + head] : 0.f;
+      sDel[i] = i < a.n ? a.delta[g.row(seq, i) * a.heads + head] : 0.f;
+    }
+  }
+  group_sync<WPG>(group);
+  if (!active) return;
+  const float sc2 = a.scale * kLog2e;
+  const int key_tiles = n_pad / 16;
+  for (int kt_ = wig; kt_ < key_tiles; kt_ += WPG) {
+    const int k0 = kt_ * 16;
+    uint32_t ka[DH / 16][4], va[DH / 16][4];
+    load_a_frags(ka, k, a.ldk, head, g, seq, k0, lane);
+    load_a_frags(va, v, a.ldv, head, g, seq, k0, lane);
+    const int ka_ = k0 + gq, kb_ = k0 + gq + 8;  // key rows owned by this thread
+    float dka[DH / 8][4], dva[DH / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; dt++) {
+      dka[dt][0] = dka[dt][1] = dka[dt][2] = dka[dt][3] = 0.f;
+      dva[dt][0] = dva[dt][1] = dva[dt][2] = dva[dt][3] = 0.f;
+    }
+    for (int q0 = 0; q0 < n_pad; q0 += 32) {
+      float s[4][4], dp[4][4];
+      const int rem = n_pad - q0;
+      const int ntv = rem >= 32 ? 4 : 2;
+      qk_block<4>(s, ka, sQ, q0, lane, ntv);
+      qk_block<4>(dp, va, sDO, q0, lane, ntv);
+      float ds[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int qr = q0 + nt * 8 + 2 * t;  // query index of elements e&1
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int qq = qr + (e & 1);
+          const int kk = (e < 2) ? ka_ : kb_;
+          float val = s[nt][e] * sc2;
+          if (biasT != nullptr && qq < a.n && kk < a.n)
+            val += __bfloat162float(biasT[((long long)head * a.n + kk) * a.n + qq]) * kLog2e;
+          const bool valid = (kk < a.n) && (qq < a.n);              // also keeps the smem reads in range
+          const float lq = valid ? sLse[qq] : 0.f;
+          const float dq_ = valid ? sDel[qq] : 0.f;
+          const float p = valid ? exp2f(val - lq) : 0.f;
+          s[nt][e] = p;                                             // P^T
+          ds[nt][e] = p * (dp[nt][e] - dq_) * a.scale;              // dS^T (w.r.t. q_hat.k_hat)
+        }
+      }
+      pv_block<4>(dva, s, sDOt, tstride, q0, lane, ntv);
+      pv_block<4>(dka, ds, sQt, tstride, q0, lane, ntv);
+    }
+    if (ka_ < a.n) {
+      __nv_bfloat16* r1 = dk + g.row(seq, ka_) * a.ld_dk + head * DH + 2 * t;
+      __nv_bfloat16* r2 = dv + g.row(seq, ka_) * a.ld_dv + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++) {
+        *reinterpret_cast<uint32_t*>(r1 + dt * 8) = pack_bf16x2(dka[dt][0], dka[dt][1]);
+        *reinterpret_cast<uint32_t*>(r2 + dt * 8) = pack_bf16x2(dva[dt][0], dva[dt][1]);
+      }
+    }
+    if (kb_ < a.n) {
+      __nv_bfloat16* r1 = dk + g.row(seq, kb_) * a.ld_dk + head * DH + 2 * t;
+      __nv_bfloat16* r2 = dv + g.row(seq, kb_) * a.ld_dv + head * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt++) {
+        *reinterpret_cast<uint32_t*>(r1 + dt * 8) = pack_bf16x2(dka[dt][2], dka[dt][3]);
+        *reinterpret_cast<uint32_t*>(r2 + dt * 8) = pack_bf16x2(dva[dt][2], dva[dt][3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, part 3 (spatial stack only): dbias[h,i,j] += sum_seq dlogits_seq[h,i,j].
+// CTA = (head, 128 query rows, 64 keys); loops over all sequences; 8 warps x 16 rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a) {
+  __shared__ __align__(16) __nv_bfloat16 sK[64 * KROW];
+  __shared__ __align__(16) __nv_bfloat16 sV[64 * KROW];
+  const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int head = blockIdx.z;
+  const int r0 = blockIdx.y * 128 + warp * 16;
+  const int key0 = blockIdx.x * 64;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
+  const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(a.d_o);
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  const float sc2 = a.scale * kLog2e;
+  const int ra = r0 + gq, rb = r0 + gq + 8;
+  float acc[8][4];
+  float bz[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    const int key = key0 + nt * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      acc[nt][e] = 0.f;
+      const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
+      bz[nt][e] = (bias != nullptr && rr < a.n && kk < a.n)
+                      ? __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e : 0.f;
+    }
+  }
+  for (int seq = 0; seq < a.num_seqs; seq++) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * 4; idx += 256) {
+      const int r = idx >> 2, part = idx & 3;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (key0 + r < a.n) {
+        kv = *reinterpret_cast<const uint4*>(k + g.row(seq, key0 + r) * a.ldk + head * DH + part * 8);
+        vv = *reinterpret_cast<const uint4*>(v + g.row(seq, key0 + r) * a.ldv + head * DH + part * 8);
+      }
+      *reinterpret_cast<uint4*>(sK + r * KROW + part * 8) = kv;
+      *reinterpret_cast<uint4*>(sV + r * KROW + part * 8) = vv;
+    }
+    __syncthreads();
+    if (r0 >= a.n) continue;
+    uint32_t qa[DH / 16][4], da[DH / 16][4];
+    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags(da, dO, a.ldo, head, g, seq, r0, lane);
+    float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
+    if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
+    if (rb < a.n) { lse_b = a.lse[g.row(seq, rb) * a.heads + head]; del_b = a.delta[g.row(seq, rb) * a.heads + head]; }
+    float s[8][4], dp[8][4];
+    qk_block<8>(s, qa, sK, 0, lane);
+    qk_block<8>(dp, da, sV, 0, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      const int key = key0 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
+        const float val = s[nt][e] * sc2 + bz[nt][e];
+        const float p = (kk < a.n && rr < a.n) ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
+        acc[nt][e] += p * (dp[nt][e] - ((e < 2) ? del_a : del_b));
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    const int key = key0 + nt * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
+      if (rr < a.n && kk < a.n) a.dbias[((long long)head * a.n + rr) * a.n + kk] += acc[nt][e];
+    }
+  }
+}
+
+// delta[row, head] = sum_d dO[row, head, d] * O[row, head, d]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                  long long ldo, float* __restrict__ delta, long long rows, int heads) {
+  const long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);  // (row, head)
+  const int part = threadIdx.x & 3;
+  float s = 0.f;
+  if (idx < rows * heads) {
+    const long long row = idx / heads;
+    const int head = (int)(idx % heads);
+    const uint4 uo = *reinterpret_cast<const uint4*>(o + row * ldo + head * DH + part * 8);
+    const uint4 ud = *reinterpret_cast<const uint4*>(d_o + row * ldo + head * DH + part * 8);
+    const uint32_t* po = reinterpret_cast<const uint32_t*>(&uo);
+    const uint32_t* pd = reinterpret_cast<const uint32_t*>(&ud);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 x = unpack_bf16x2(po[i]), y = unpack_bf16x2(pd[i]);
+      s += x.x * y.x + x.y * y.y;
+    }
+  }
+  s = quad_sum(s);
+  if (part == 0 && idx < rows * heads) delta[idx] = s;
+}
+
+// Backward of  x_hat = x / max(||x||, eps) * scale  per (row, head):  given d(x_hat) and raw x:
+//   u = scale * dxh;  dx = (u - xn * (xn . u)) / ||x||  with xn = x/||x||;   dscale[d] += dxh[d] * xn[d]
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ dxh, long long ld_dxh,
+                                                        const __nv_bfloat16* __restrict__ xraw, long long ld_x,
+                                                        const float* __restrict__ scale, __nv_bfloat16* __restrict__ dx,
+                                                        long long ld_dx, float* __restrict__ dscale, long long rows,
+                                                        int heads) {
+  __shared__ float sds[DH];
+  if (threadIdx.x < DH) sds[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int part = threadIdx.x & 3;
+  float sc[8], dsc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { sc[i] = scale[part * 8 + i]; dsc[i] = 0.f; }
+  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); idx < rows * heads;
+       idx += (long long)gridDim.x * (blockDim.x >> 2)) {
+    const long long row = idx / heads;
+    const int head = (int)(idx % heads);
+    const uint4 ug = *reinterpret_cast<const uint4*>(dxh + row * ld_dxh + head * DH + part * 8);
+    const uint4 ux = *reinterpret_cast<const uint4*>(xraw + row * ld_x + head * DH + part * 8);
+    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&ug);
+    const uint32_t* px = reinterpret_cast<const uint32_t*>(&ux);
+    float gg[8], xx[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 a = unpack_bf16x2(pg[i]), b = unpack_bf16x2(px[i]);
+      gg[2 * i] = a.x; gg[2 * i + 1] = a.y;
+      xx[2 * i] = b.x; xx[2 * i + 1] = b.y;
+      ss += b.x * b.x + b.y * b.y;
+    }
+    ss = quad_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      xx[i] *= inv;                 // xn
+      dsc[i] += gg[i] * xx[i];
+      gg[i] *= sc[i];               // u
+      dot += gg[i] * xx[i];
+    }
+    dot = quad_sum(dot);
+    uint4 out;
+    uint32_t* po = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      po[i] = pack_bf16x2((gg[2 * i] - xx[2 * i] * dot) * inv, (gg[2 * i + 1] - xx[2 * i + 1] * dot) * inv);
+    *reinterpret_cast<uint4*>(dx + row * ld_dx + head * DH + part * 8) = out;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) atomicAdd(&sds[part * 8 + i], dsc[i]);
+  __syncthreads();
+  if (threadIdx.x < DH) atomicAdd(dscale + threadIdx.x, sds[threadIdx.x]);
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+static int attn_check(const ctclip_attn_args* a, const char* who) {
+  CTB_CHECK_ARG(a != nullptr, "%s: null args", who);
+  CTB_CHECK_ARG(a->dim_head == DH, "%s: dim_head must be %d (got %d)", who, DH, a->dim_head);
+  CTB_CHECK_ARG(a->n > 0 && a->heads > 0 && a->num_seqs > 0 && a->seq_inner > 0, "%s: bad geometry", who);
+  CTB_CHECK_ARG(a->q && a->k && a->v, "%s: null q/k/v", who);
+  CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0, "%s: q/k/v rows must be 16B aligned", who);
+  return CTCLIP_OK;
+}
+
+template <typename Kern>
+static int launch_grouped(Kern kern, const ctclip_attn_args* a, size_t group_bytes, int wpg, int groups,
+                          cudaStream_t stream) {
+  const size_t smem = group_bytes * groups;
+  CTB_CHECK_ARG(smem <= 227 * 1024, "attention: sequence of %d tokens needs %zu B of shared memory (> 227 KB)", a->n, smem);
+  CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)a->num_seqs * a->heads;
+  const int grid = (int)((items + groups - 1) / groups);
+  kern<<<grid, wpg * groups * 32, smem, stream>>>(*a);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_attn_fwd(const ctclip_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = attn_check(a, "attn_fwd")) return rc;
+  CTB_CHECK_ARG(a->o != nullptr && a->ldo % 8 == 0, "attn_fwd: bad o");
+  const int n_pad = (a->n + 15) & ~15;
+  const size_t gb = (size_t)(n_pad * KROW + DH * (n_pad + 8)) * 2;
+  if (a->n <= 64) return launch_grouped(attn_fwd_kernel<1, 8>, a, gb, 1, 8, stream);
+  return launch_grouped(attn_fwd_kernel<9, 1>, a, gb, 9, 1, stream);
+}
+
+extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = attn_check(a, "attn_bwd")) return rc;
+  CTB_CHECK_ARG(a->o && a->d_o && a->lse && a->delta && a->dq && a->dk && a->dv, "attn_bwd: null pointer");
+  CTB_CHECK_ARG(a->bias == nullptr || a->bias_t != nullptr, "attn_bwd: bias needs its transposed copy bias_t");
+  const long long rows = a->total_rows;
+  CTB_CHECK_ARG(rows > 0, "attn_bwd: total_rows must be set");
+  {
+    const long long items = rows * a->heads;
+    const int per_cta = 64;
+    attn_delta_kernel<<<(int)((items + per_cta - 1) / per_cta), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->o), reinterpret_cast<const __nv_bfloat16*>(a->d_o), a->ldo, a->delta,
+        rows, a->heads);
+    CTB_LAUNCH_CHECK();
+  }
+  const int n_pad = (a->n + 15) & ~15;
+  const size_t gb_dq = (size_t)(2 * n_pad * KROW + DH * (n_pad + 8)) * 2;
+  const size_t gb_dkv = (size_t)(2 * n_pad * KROW + 2 * DH * (n_pad + 8)) * 2 + (size_t)n_pad * 8;
+  int rc;
+  if (a->n <= 64) {
+    rc = launch_grouped(attn_bwd_dq_kernel<1, 8>, a, gb_dq, 1, 8, stream);
+    if (rc) return rc;
+    rc = launch_grouped(attn_bwd_dkv_kernel<1, 8>, a, gb_dkv, 1, 8, stream);
+  } else {
+    rc = launch_grouped(attn_bwd_dq_kernel<12, 1>, a, gb_dq, 12, 1, stream);
+    if (rc) return rc;
+    rc = launch_grouped(attn_bwd_dkv_kernel<12, 1>, a, gb_dkv, 12, 1, stream);
+  }
+  if (rc) return rc;
+  if (a->dbias != nullptr) {
+    dim3 grid((a->n + 63) / 64, (a->n + 127) / 128, a->heads);
+    attn_bwd_dbias_kernel<<<grid, 256, 0, stream>>>(*a);
+    CTB_LAUNCH_CHECK();
+  }
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_l2norm_bwd(const void* dxh, int64_t ld_dxh, const void* xraw, int64_t ld_x, const float* scale,
+                                 void* dx, int64_t ld_dx, float* dscale, int64_t rows, int32_t heads, int32_t dim_head,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dim_head == DH, "l2norm_bwd: dim_head must be %d", DH);
+  CTB_CHECK_ARG(dxh && xraw && scale && dx && dscale && rows > 0 && heads > 0, "l2norm_bwd: bad args");
+  CTB_CHECK_ARG(ld_dxh % 8 == 0 && ld_x % 8 == 0 && ld_dx % 8 == 0, "l2norm_bwd: rows must be 16B aligned");
+  long long ctas = (rows * heads + 63) / 64;
+  const long long cap = (long long)num_sms() * 8;
+  if (ctas > cap) ctas = cap;
+  l2norm_bwd_kernel<<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,
+                                                  reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,
+                                                  reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, rows, heads);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}

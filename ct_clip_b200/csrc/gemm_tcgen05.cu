@@ -18,7 +18,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5 };
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5, EPI_L2NORM = 6, EPI_BIAS_GELU = 7 };
 
 struct GemmKParams {
   int M, N, K;
@@ -37,6 +37,8 @@ struct GemmKParams {
   long long ldc2;
   int* arg_out;
   float* argval_out;
+  int norm_cols;
+  const float* norm_scale;
 };
 
 template <int BN>
@@ -286,6 +288,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < 16; i++)
                 if (2 * i < ncols) gdst[i] = __float2bfloat16(g[i]);
             }
+          } else if (p.epi == EPI_L2NORM) {
+            // one 32-column chunk == one attention head (dim_head 32): raw -> C, l2norm*scale -> C2
+            if (p.C != nullptr) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, v);
+            if (col0 < p.norm_cols) {
+              float ss = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i++) ss += v[i] * v[i];
+              const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] = v[i] * inv * __ldg(p.norm_scale + i);
+              store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C2) + row * p.ldc2 + col0, v);
+            }
+          } else if (p.epi == EPI_BIAS_GELU) {
+            // C(bf16) = gelu_erf(acc + bias); C2(bf16, optional) = acc + bias (pre-activation)
+            if (p.C2 != nullptr) {
+              __nv_bfloat16* pdst = reinterpret_cast<__nv_bfloat16*>(p.C2) + row * p.ldc2 + col0;
+              if (ncols == 32) store_bf16x32(pdst, v);
+              else {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                  if (i < ncols) pdst[i] = __float2bfloat16(v[i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+            if (ncols == 32) store_bf16x32(dst, v);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (i < ncols) dst[i] = __float2bfloat16(v[i]);
+            }
           } else if (p.epi == EPI_ATOMIC_F32) {
             float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
             if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -372,11 +406,16 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
                 "gemm: operand pitch must be a multiple of 16 bytes (lda=%lld ldb=%lld)",
                 (long long)a->lda, (long long)a->ldb);
   CTB_CHECK_ARG(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: operands must be 16B aligned");
-  CTB_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 5, "gemm: bad epilogue %d", a->epilogue);
+  CTB_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 7, "gemm: bad epilogue %d", a->epilogue);
+  if (a->epilogue == EPI_L2NORM)
+    CTB_CHECK_ARG(a->C2 != nullptr && a->norm_scale != nullptr && a->N % 32 == 0 && a->norm_cols % 32 == 0 &&
+                      a->ldc % 8 == 0 && a->ldc2 % 8 == 0,
+                  "gemm: L2NORM needs C2, norm_scale, N/norm_cols multiples of 32 and 16B-aligned rows");
+  if (a->epilogue == EPI_BIAS_GELU) CTB_CHECK_ARG(a->ldc % 8 == 0 && (a->C2 == nullptr || a->ldc2 % 8 == 0), "gemm: BIAS_GELU needs 16B-aligned rows");
   CTB_CHECK_ARG(a->splits >= 1, "gemm: splits must be >= 1");
   CTB_CHECK_ARG(a->splits == 1 || a->epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the ATOMIC_F32 epilogue");
   if (a->epilogue == EPI_ARGMAX) CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
-  else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU, "gemm: null C");
+  else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU || a->epilogue == EPI_L2NORM, "gemm: null C");
   if (a->epilogue == EPI_GEGLU) CTB_CHECK_ARG(a->C2 != nullptr && (a->N % 2) == 0, "gemm: GEGLU needs C2 and even N");
   if (a->epilogue == EPI_RESID_F32) CTB_CHECK_ARG(a->resid != nullptr, "gemm: RESID_F32 needs resid");
 
@@ -393,6 +432,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   p.resid = a->resid; p.ldr = a->ldr;
   p.C2 = a->C2; p.ldc2 = a->ldc2;
   p.arg_out = a->arg_out; p.argval_out = a->argval_out;
+  p.norm_cols = a->norm_cols; p.norm_scale = a->norm_scale;
 
   // Tile-N selection: 256 where it divides N (fewest B re-reads per MMA), else 128, 64 for tiny N.
   int bn;

@@ -1,0 +1,502 @@
+// Small / bandwidth-bound kernels around the GEMM and attention cores:
+//   * fp32 CUDA-core GEMM for the tiny continuous-position-bias MLP (attention.py:257-276, "fp32 forced")
+//   * CPB table -> per-head bias expansion / gradient reduction (2209 distinct offsets instead of S^2 rows)
+//   * GEGLU backward (attention.py:39-42), column sums (bias gradients), casts
+//   * vector-quantiser pieces (vector_quantize_pytorch 1.1.2 CosineSimCodebook): code-book l2norm,
+//     gather + temporal mean pool (ct_clip.py:724), EMA statistics and update
+//   * weight preparation: LayerNorm-affine folding, GEGLU column interleave, zero padding, and the
+//     matching un-folding of weight gradients
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/ctclip_b200.h"
+
+namespace ctb {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 GEMM (tiny problems only): C[m,n] = epi( sum_k opA(m,k) * opB(k,n) )
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_small_kernel(ctclip_sgemm_args a) {
+  __shared__ float sA[32][33];
+  __shared__ float sB[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < a.K; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      // sA[r][c] = opA(m0+r, k0+c)
+      float va = 0.f, vb = 0.f;
+      if (m0 + r < a.M && k0 + c < a.K)
+        va = a.trans_a ? a.A[(long long)(k0 + c) * a.lda + m0 + r] : a.A[(long long)(m0 + r) * a.lda + k0 + c];
+      // sB[r][c] = opB(k0+r, n0+c)
+      if (k0 + r < a.K && n0 + c < a.N)
+        vb = a.trans_b ? a.B[(long long)(n0 + c) * a.ldb + k0 + r] : a.B[(long long)(k0 + r) * a.ldb + n0 + c];
+      sA[r][c] = va;
+      sB[r][c] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const float a0 = sA[ty][k], a1 = sA[ty + 16][k];
+      const float b0 = sB[k][tx], b1 = sB[k][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m >= a.M || n >= a.N) continue;
+      float v = acc[i][j];
+      if (a.bias != nullptr) v += a.bias[n];
+      if (a.act == 1) v = v > 0.f ? v : 0.1f * v;                       // LeakyReLU(0.1), attention.py:17
+      if (a.mask_ref != nullptr) v *= (a.mask_ref[(long long)m * a.ld_mask + n] > 0.f) ? 1.f : 0.1f;
+      float* dst = a.C + (long long)m * a.ldc + n;
+      *dst = a.accumulate ? (*dst + v) : v;
+    }
+}
+
+// column sums: out[n] (+)= sum_m X[m,n]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, long long M, int N,
+                                                    float* __restrict__ out, int rows_per_cta) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const long long m0 = (long long)blockIdx.y * rows_per_cta;
+  const long long m1 = (m0 + rows_per_cta < M) ? m0 + rows_per_cta : M;
+  if (n >= N) return;
+  float s = 0.f;
+  for (long long m = m0; m < m1; m++) s += (float)x[m * ld + n];
+  atomicAdd(out + n, s);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// continuous position bias (attention.py:229-276), evaluated on the (2h-1)(2w-1) distinct offsets
+// ------------------------------------------------------------------------------------------------
+__global__ void cpb_inputs_kernel(float* __restrict__ X, int h, int w) {
+  const int R = (2 * h - 1) * (2 * w - 1);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int dy = r / (2 * w - 1) - (h - 1), dx = r % (2 * w - 1) - (w - 1);
+  const float fy = (float)dy, fx = (float)dx;
+  X[2 * r] = (dy > 0 ? 1.f : (dy < 0 ? -1.f : 0.f)) * logf(fabsf(fy) + 1.f);   // sign(rel) * log(|rel| + 1)
+  X[2 * r + 1] = (dx > 0 ? 1.f : (dx < 0 ? -1.f : 0.f)) * logf(fabsf(fx) + 1.f);
+}
+// bias[hd][i][j] = table[rel(i,j)][hd]; also the (i<->j) transposed copy used by the dK/dV kernel
+__global__ void cpb_expand_kernel(const float* __restrict__ table, int heads, int h, int w,
+                                  __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ bias_t) {
+  const int n = h * w;
+  const long long total = (long long)heads * n * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % n);
+    const int i = (int)((idx / n) % n);
+    const int hd = (int)(idx / ((long long)n * n));
+    const int r = ((i / w) - (j / w) + h - 1) * (2 * w - 1) + ((i % w) - (j % w) + w - 1);
+    const __nv_bfloat16 v = __float2bfloat16(table[(long long)r * heads + hd]);
+    bias[idx] = v;
+    if (bias_t != nullptr) bias_t[((long long)hd * n + j) * n + i] = v;
+  }
+}
+// dtable[r][hd] = sum over (i,j) with rel(i,j) == r of dbias[hd][i][j]
+__global__ void cpb_reduce_kernel(const float* __restrict__ dbias, int heads, int h, int w, float* __restrict__ dtable) {
+  const int r = blockIdx.x;
+  const int n = h * w;
+  const int dy = r / (2 * w - 1) - (h - 1), dx = r % (2 * w - 1) - (w - 1);
+  const int iy0 = dy > 0 ? dy : 0, iy1 = dy < 0 ? h - 1 + dy : h - 1;
+  const int ix0 = dx > 0 ? dx : 0, ix1 = dx < 0 ? w - 1 + dx : w - 1;
+  const int ny = iy1 - iy0 + 1, nx = ix1 - ix0 + 1;
+  __shared__ float red[256];
+  for (int hd = 0; hd < heads; hd++) {
+    float s = 0.f;
+    for (int p = threadIdx.x; p < ny * nx; p += blockDim.x) {
+      const int iy = iy0 + p / nx, ix = ix0 + p % nx;
+      const int i = iy * w + ix, j = (iy - dy) * w + (ix - dx);
+      s += dbias[((long long)hd * n + i) * n + j];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) dtable[(long long)r * heads + hd] = red[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU backward on the interleaved pre-activation h[m, 2j] = value, h[m, 2j+1] = gate:
+//   dvalue = dg * gelu(gate),  dgate = dg * value * gelu'(gate);  written in place of h;  colsum -> s
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dg, long long ld_dg,
+                                                       __nv_bfloat16* __restrict__ h, long long ld_h, long long M,
+                                                       int n_pairs, float* __restrict__ colsum, int rows_per_cta) {
+  // thread = (column group of 4 pairs = 8 h-columns, row lane)
+  const int cg = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  const long long m0 = (long long)blockIdx.y * rows_per_cta;
+  const long long m1 = (m0 + rows_per_cta < M) ? m0 + rows_per_cta : M;
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) cs[i] = 0.f;
+  const bool ok = cg * 4 < n_pairs;
+  if (ok) {
+    for (long long m = m0 + rl; m < m1; m += 4) {
+      const uint2 ud = *reinterpret_cast<const uint2*>(dg + m * ld_dg + cg * 4);
+      uint4 uh = *reinterpret_cast<const uint4*>(h + m * ld_h + cg * 8);
+      const float2 d01 = unpack_bf16x2(ud.x), d23 = unpack_bf16x2(ud.y);
+      const float dgv[4] = {d01.x, d01.y, d23.x, d23.y};
+      uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 xv = unpack_bf16x2(ph[i]);  // (value, gate)
+        const float dval = dgv[i] * gelu_erf(xv.y);
+        const float dgate = dgv[i] * xv.x * gelu_erf_grad(xv.y);
+        ph[i] = pack_bf16x2(dval, dgate);
+        cs[2 * i] += dval;
+        cs[2 * i + 1] += dgate;
+      }
+      *reinterpret_cast<uint4*>(h + m * ld_h + cg * 8) = uh;
+    }
+  }
+  if (colsum == nullptr) return;
+  __shared__ float red[4][64][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) red[rl][threadIdx.x & 63][i] = cs[i];
+  __syncthreads();
+  if (rl == 0 && ok) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float t = red[0][threadIdx.x][i] + red[1][threadIdx.x][i] + red[2][threadIdx.x][i] + red[3][threadIdx.x][i];
+      atomicAdd(colsum + cg * 8 + i, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector quantiser
+// ------------------------------------------------------------------------------------------------
+// row-wise l2 normalisation fp32 -> bf16 (code-book operand of the distance GEMM)
+__global__ void l2norm_rows_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)warp * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) ss += xr[c] * xr[c];
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int c = lane; c < D; c += 32) y[(long long)warp * D + c] = __float2bfloat16(xr[c] * inv);
+}
+// tokens[m, :] = embed[idx[m], :]
+__global__ void vq_gather_kernel(const int* __restrict__ idx, const float* __restrict__ embed, float* __restrict__ out,
+                                 long long M, int D) {
+  const int d4 = D / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * d4; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / d4;
+    const int c = (int)(i % d4);
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(embed + (long long)idx[m] * D)[c];
+  }
+}
+// pooled[b, s, :] = mean_t embed[idx[b, t, s], :]   (ct_clip.py:724 fused with the code-book gather)
+__global__ void vq_gather_pool_kernel(const int* __restrict__ idx, const float* __restrict__ embed, int B, int T, int S,
+                                      int D, float* __restrict__ pooled_f32, __nv_bfloat16* __restrict__ pooled_bf16) {
+  const int d4 = D / 4;
+  const long long total = (long long)B * S * d4;
+  const float invT = 1.f / T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const long long bs = i / d4;
+    const int s = (int)(bs % S);
+    const int b = (int)(bs / S);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; t++) {
+      const int code = idx[((long long)b * T + t) * S + s];
+      const float4 e = reinterpret_cast<const float4*>(embed + (long long)code * D)[c];
+      acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+    }
+    acc.x *= invT; acc.y *= invT; acc.z *= invT; acc.w *= invT;
+    if (pooled_f32 != nullptr) reinterpret_cast<float4*>(pooled_f32)[i] = acc;
+    if (pooled_bf16 != nullptr)
+      reinterpret_cast<uint2*>(pooled_bf16)[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  }
+}
+// dtokens[b, t, s, :] = dpooled[b, s, :] / T    (backward of the mean pool through the straight-through VQ)
+__global__ void pool_bwd_kernel(const float* __restrict__ dpooled, int B, int T, int S, int D, float* __restrict__ dtok) {
+  const int d4 = D / 4;
+  const long long total = (long long)B * T * S * d4;
+  const float invT = 1.f / T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d4);
+    const long long bts = i / d4;
+    const int s = (int)(bts % S);
+    const int b = (int)(bts / ((long long)T * S));
+    float4 v = reinterpret_cast<const float4*>(dpooled)[((long long)b * S + s) * d4 + c];
+    v.x *= invT; v.y *= invT; v.z *= invT; v.w *= invT;
+    reinterpret_cast<float4*>(dtok)[i] = v;
+  }
+}
+// EMA statistics: bins[code] += 1, embed_sum[code, :] += l2norm(x[m, :])
+__global__ void vq_ema_accum_kernel(const float* __restrict__ x, const int* __restrict__ idx, long long M, int D,
+                                    float* __restrict__ bins, float* __restrict__ embed_sum) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* xr = x + warp * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) ss += xr[c] * xr[c];
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  const int code = idx[warp];
+  if (lane == 0) atomicAdd(bins + code, 1.f);
+  for (int c = lane; c < D; c += 32) atomicAdd(embed_sum + (long long)code * D + c, xr[c] * inv);
+}
+// embed <- embed*decay + (1-decay) * (bins>0 ? l2norm(embed_sum/bins) : l2norm(embed)); cluster_size likewise
+__global__ void vq_ema_update_kernel(float* __restrict__ embed, float* __restrict__ cluster_size,
+                                     const float* __restrict__ bins, const float* __restrict__ embed_sum, int C, int D,
+                                     float decay) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  const float b = bins[warp];
+  float* er = embed + (long long)warp * D;
+  const float* sr = embed_sum + (long long)warp * D;
+  const bool zero = (b == 0.f);
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = zero ? er[c] : sr[c] / b;
+    ss += v * v;
+  }
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int c = lane; c < D; c += 32) {
+    const float v = (zero ? er[c] : sr[c] / b) * inv;
+    er[c] = er[c] * decay + v * (1.f - decay);
+  }
+  if (lane == 0) cluster_size[warp] = cluster_size[warp] * decay + b * (1.f - decay);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation (fp32 master -> bf16 GEMM operand) and gradient un-folding
+// ------------------------------------------------------------------------------------------------
+// out[r, k] = rowmap[r] >= 0 && k < K ? W[rowmap[r], k] * (gamma ? gamma[k] : 1) : 0      out: bf16 [Np, Kp]
+__global__ void prep_weight_kernel(const float* __restrict__ W, long long ldw, int K, const float* __restrict__ gamma,
+                                   const int* __restrict__ rowmap, int Np, int Kp, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)Np * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    const int r = (int)(i / Kp);
+    const int src = rowmap ? rowmap[r] : r;
+    float v = 0.f;
+    if (src >= 0 && k < K) v = W[(long long)src * ldw + k] * (gamma ? gamma[k] : 1.f);
+    out[i] = __float2bfloat16(v);
+  }
+}
+// out[r] = sum_k W[rowmap[r], k] * beta[k] + (bias_in ? bias_in[rowmap[r]] : 0)
+__global__ void prep_bias_kernel(const float* __restrict__ W, long long ldw, int K, const float* __restrict__ beta,
+                                 const float* __restrict__ bias_in, const int* __restrict__ rowmap, int Np,
+                                 float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Np) return;
+  const int src = rowmap ? rowmap[warp] : warp;
+  float s = 0.f;
+  if (src >= 0 && beta != nullptr)
+    for (int k = lane; k < K; k += 32) s += W[(long long)src * ldw + k] * beta[k];
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = (src >= 0) ? s + (bias_in ? bias_in[src] : 0.f) : 0.f;
+}
+// Given G = dL/dW' (W' = prepared weight, fp32 [Np, ldg]) and s[r] = dL/db'[r]:
+//   dW[src, k] += G[r, k] * gamma[k];  dgamma[k] += sum_r W[src,k] * G[r,k];  dbeta[k] += sum_r W[src,k] * s[r]
+//   dbias[src] += s[r]
+__global__ void __launch_bounds__(128) unprep_wgrad_kernel(const float* __restrict__ G, long long ldg,
+                                                          const float* __restrict__ W, long long ldw, int K,
+                                                          const float* __restrict__ gamma, const int* __restrict__ rowmap,
+                                                          int Np, const float* __restrict__ s, float* __restrict__ dW,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                          float* __restrict__ dbias, int rows_per_cta) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = (r0 + rows_per_cta < Np) ? r0 + rows_per_cta : Np;
+  if (dbias != nullptr && blockIdx.x == 0 && s != nullptr) {
+    for (int r = r0 + threadIdx.x; r < r1; r += 128) {
+      const int src = rowmap ? rowmap[r] : r;
+      if (src >= 0) atomicAdd(dbias + src, s[r]);
+    }
+  }
+  if (k >= K) return;
+  const float gm = gamma ? gamma[k] : 1.f;
+  float ag = 0.f, ab = 0.f;
+  for (int r = r0; r < r1; r++) {
+    const int src = rowmap ? rowmap[r] : r;
+    if (src < 0) continue;
+    const float g = G[(long long)r * ldg + k];
+    const float w = W[(long long)src * ldw + k];
+    dW[(long long)src * ldw + k] += g * gm;
+    ag += w * g;
+    if (s != nullptr) ab += w * s[r];
+  }
+  if (dgamma != nullptr) atomicAdd(dgamma + k, ag);
+  if (dbeta != nullptr && s != nullptr) atomicAdd(dbeta + k, ab);
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+static inline int grid_for(long long n, int block, int per_sm = 16) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int ctclip_sgemm_f32(const ctclip_sgemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(a && a->A && a->B && a->C && a->M > 0 && a->N > 0 && a->K > 0, "sgemm: bad args");
+  dim3 grid(ceil_div(a->N, 32), ceil_div(a->M, 32));
+  sgemm_small_kernel<<<grid, 256, 0, stream>>>(*a);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_colsum(const void* x, int32_t is_bf16, int64_t ld, int64_t M, int32_t N, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && out && M > 0 && N > 0, "colsum: bad args");
+  const int rows_per_cta = 512;
+  dim3 grid(ceil_div(N, 256), ceil_div(M, rows_per_cta));
+  if (is_bf16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out, rows_per_cta);
+  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ld, M, N, out, rows_per_cta);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && y && n > 0 && n % 4 == 0, "cast: n must be a positive multiple of 4");
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n / 4);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_cpb_inputs(float* X, int32_t h, int32_t w, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(X && h > 0 && w > 0, "cpb_inputs: bad args");
+  const int R = (2 * h - 1) * (2 * w - 1);
+  cpb_inputs_kernel<<<ceil_div(R, 256), 256, 0, stream>>>(X, h, w);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, int32_t w, void* bias, void* bias_t,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(table && bias && heads > 0 && h > 0 && w > 0, "cpb_expand: bad args");
+  const long long total = (long long)heads * h * w * h * w;
+  cpb_expand_kernel<<<grid_for(total, 256), 256, 0, stream>>>(table, heads, h, w, reinterpret_cast<__nv_bfloat16*>(bias),
+                                                            reinterpret_cast<__nv_bfloat16*>(bias_t));
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dbias && dtable && heads > 0 && h > 0 && w > 0, "cpb_reduce: bad args");
+  cpb_reduce_kernel<<<(2 * h - 1) * (2 * w - 1), 256, 0, stream>>>(dbias, heads, h, w, dtable);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_geglu_bwd(const void* dg, int64_t ld_dg, void* h, int64_t ld_h, int64_t M, int32_t n_pairs,
+                                float* colsum, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dg && h && M > 0 && n_pairs > 0 && n_pairs % 4 == 0, "geglu_bwd: n_pairs must be a multiple of 4");
+  CTB_CHECK_ARG(ld_dg % 4 == 0 && ld_h % 8 == 0, "geglu_bwd: bad leading dimensions");
+  const int rows_per_cta = 256;
+  dim3 grid(ceil_div(n_pairs / 4, 64), ceil_div(M, rows_per_cta));
+  geglu_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dg), ld_dg,
+                                            reinterpret_cast<__nv_bfloat16*>(h), ld_h, M, n_pairs, colsum, rows_per_cta);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_l2norm_rows_bf16(const float* x, void* y, int32_t rows, int32_t D, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && y && rows > 0 && D > 0, "l2norm_rows: bad args");
+  l2norm_rows_bf16_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), rows, D);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_vq_gather(const int32_t* idx, const float* embed, float* out, int64_t M, int32_t D, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(idx && embed && out && M > 0 && D % 4 == 0, "vq_gather: bad args");
+  vq_gather_kernel<<<grid_for(M * (D / 4), 256), 256, 0, stream>>>(idx, embed, out, M, D);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_vq_gather_pool(const int32_t* idx, const float* embed, int32_t B, int32_t T, int32_t S, int32_t D,
+                                     float* pooled_f32, void* pooled_bf16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(idx && embed && (pooled_f32 || pooled_bf16) && B > 0 && T > 0 && S > 0 && D % 4 == 0, "vq_gather_pool: bad args");
+  vq_gather_pool_kernel<<<grid_for((long long)B * S * (D / 4), 256), 256, 0, stream>>>(
+      idx, embed, B, T, S, D, pooled_f32, reinterpret_cast<__nv_bfloat16*>(pooled_bf16));
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_pool_bwd(const float* dpooled, int32_t B, int32_t T, int32_t S, int32_t D, float* dtok, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dpooled && dtok && B > 0 && T > 0 && S > 0 && D % 4 == 0, "pool_bwd: bad args");
+  pool_bwd_kernel<<<grid_for((long long)B * T * S * (D / 4), 256), 256, 0, stream>>>(dpooled, B, T, S, D, dtok);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_vq_ema_accum(const float* x, const int32_t* idx, int64_t M, int32_t D, float* bins, float* embed_sum,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && idx && bins && embed_sum && M > 0 && D > 0, "vq_ema_accum: bad args");
+  vq_ema_accum_kernel<<<ceil_div(M * 32, 256), 256, 0, stream>>>(x, idx, M, D, bins, embed_sum);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_vq_ema_update(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int32_t C,
+                                    int32_t D, float decay, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(embed && cluster_size && bins && embed_sum && C > 0 && D > 0, "vq_ema_update: bad args");
+  vq_ema_update_kernel<<<ceil_div((long long)C * 32, 256), 256, 0, stream>>>(embed, cluster_size, bins, embed_sum, C, D, decay);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_prep_weight(const float* W, int64_t ldw, int32_t K, const float* gamma, const int32_t* rowmap,
+                                  int32_t Np, int32_t Kp, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(W && out && K > 0 && Np > 0 && Kp >= K, "prep_weight: bad args");
+  prep_weight_kernel<<<grid_for((long long)Np * Kp, 256), 256, 0, stream>>>(W, ldw, K, gamma, rowmap, Np, Kp,
+                                                                          reinterpret_cast<__nv_bfloat16*>(out));
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_prep_bias(const float* W, int64_t ldw, int32_t K, const float* beta, const float* bias_in,
+                                const int32_t* rowmap, int32_t Np, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(W && out && K > 0 && Np > 0, "prep_bias: bad args");
+  prep_bias_kernel<<<ceil_div((long long)Np * 32, 256), 256, 0, stream>>>(W, ldw, K, beta, bias_in, rowmap, Np, out);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_unprep_wgrad(const float* G, int64_t ldg, const float* W, int64_t ldw, int32_t K, const float* gamma,
+                                   const int32_t* rowmap, int32_t Np, const float* s, float* dW, float* dgamma,
+                                   float* dbeta, float* dbias, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(G && W && dW && K > 0 && Np > 0, "unprep_wgrad: bad args");
+  const int rows_per_cta = 64;
+  dim3 grid(ceil_div(K, 128), ceil_div(Np, rows_per_cta));
+  unprep_wgrad_kernel<<<grid, 128, 0, stream>>>(G, ldg, W, ldw, K, gamma, rowmap, Np, s, dW, dgamma, dbeta, dbias, rows_per_cta);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}

@@ -1,6 +1,7 @@
 """Torch-tensor front ends of the C-ABI kernels (raw device pointers + current stream).
 
-Every function launches on torch's current CUDA stream and never synchronises.
+Every function launches on torch's current CUDA stream and never synchronises. PyTorch is used
+for device memory and streams only; all arithmetic happens inside libctclip_b200.so.
 """
 from __future__ import annotations
 
@@ -9,8 +10,13 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_F32, EPI_GEGLU, EPI_RESID_F32,  # noqa: F401
-                   GemmArgs, check)
+from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_BIAS_GELU, EPI_F32, EPI_GEGLU, EPI_L2NORM,  # noqa: F401
+                   EPI_RESID_F32, AttnArgs, GemmArgs, LnBwdArgs, LnFwdArgs, LossArgs, PatchifyArgs, PegArgs,
+                   SgemmArgs, call)
+
+
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per GEMM launch
+GEMM_TIMER = None
 
 
 def _stream() -> int:
@@ -21,11 +27,10 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_major: int = 0,
-         epilogue: int = EPI_BF16, C_out: torch.Tensor | None = None, bias: torch.Tensor | None = None,
-         resid: torch.Tensor | None = None, C2: torch.Tensor | None = None, arg_out: torch.Tensor | None = None,
-         argval_out: torch.Tensor | None = None, splits: int = 1, lda: int | None = None, ldb: int | None = None,
-         ldc: int | None = None) -> None:
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, bias=None, resid=None, C2=None,
+         arg_out=None, argval_out=None, splits=1, lda=None, ldb=None, ldc=None, ldc2=None, norm_cols=0,
+         norm_scale=None):
     """C[M,N] = sum_k A(m,k) B(n,k); see include/ctclip_b200.h for the epilogues."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
     a = GemmArgs()
@@ -40,7 +45,216 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_major: i
     a.resid = _ptr(resid)
     a.ldr = resid.stride(0) if resid is not None else 0
     a.C2 = _ptr(C2)
-    a.ldc2 = C2.stride(0) if C2 is not None else 0
+    a.ldc2 = ldc2 if ldc2 is not None else (C2.stride(0) if C2 is not None else 0)
     a.arg_out = _ptr(arg_out)
     a.argval_out = _ptr(argval_out)
-    check(_lib.lib().ctclip_gemm_bf16(C.byref(a), _stream()), "ctclip_gemm_bf16")
+    a.norm_cols = norm_cols
+    a.norm_scale = _ptr(norm_scale)
+    if GEMM_TIMER is None:
+        call("ctclip_gemm_bf16", C.byref(a), _stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("ctclip_gemm_bf16", C.byref(a), _stream())
+        e1.record()
+        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K))
+
+
+def wgrad_splits(k_red: int, out_tiles: int, sms: int = 148) -> int:
+    """Split-K factor for a weight-gradient GEMM reducing over k_red rows: aim for ~4 waves of units."""
+    kb = (k_red + 63) // 64
+    want = max(1, (4 * sms + out_tiles - 1) // out_tiles)
+    return max(1, min(kb, want))
+
+
+def ln_fwd(x, M, D, *, eps=1e-5, gamma=None, beta=None, xhat=None, raw=None, y_f32=None, y_bf16=None, rstd=None):
+    a = LnFwdArgs()
+    a.x, a.M, a.D, a.eps = x.data_ptr(), M, D, eps
+    a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+    a.xhat_bf16, a.raw_bf16, a.y_f32, a.y_bf16, a.rstd_out = _ptr(xhat), _ptr(raw), _ptr(y_f32), _ptr(y_bf16), _ptr(rstd)
+    call("ctclip_ln_fwd", C.byref(a), _stream())
+
+
+def ln_bwd(M, D, *, g_f32=None, g_bf16=None, gamma=None, xhat, rstd, dres_in=None, add_bf16=None, dx_f32=None,
+           dx_bf16=None, dgamma=None, dbeta=None):
+    a = LnBwdArgs()
+    a.M, a.D = M, D
+    a.g_f32, a.g_bf16, a.gamma = _ptr(g_f32), _ptr(g_bf16), _ptr(gamma)
+    a.xhat, a.rstd = xhat.data_ptr(), rstd.data_ptr()
+    a.dres_in, a.add_bf16 = _ptr(dres_in), _ptr(add_bf16)
+    a.dx_f32, a.dx_bf16, a.dgamma, a.dbeta = _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta)
+    call("ctclip_ln_bwd", C.byref(a), _stream())
+
+
+def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
+    a = PatchifyArgs()
+    a.video = video.data_ptr()
+    if video.dtype == torch.int16:
+        a.dtype, a.scale = 1, 1.0 / 1000.0
+    elif video.dtype == torch.float32:
+        a.dtype, a.scale = 0, 1.0
+    else:
+        raise TypeError(f"patchify: unsupported volume dtype {video.dtype} (need float32 or int16 HU)")
+    a.B, a.C, a.F, a.H, a.W = B, Cc, F, H, W
+    a.pt, a.p1, a.p2, a.eps = pt, p1, p2, eps
+    a.xhat = xhat.data_ptr()
+    a.ld_out = ld_out if ld_out is not None else xhat.stride(0)
+    call("ctclip_patchify", C.byref(a), _stream())
+
+
+def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
+              dbias=None, lines=4):
+    a = PegArgs()
+    a.x, a.dy, a.y, a.y_bf16 = x.data_ptr(), _ptr(dy), _ptr(y), _ptr(y_bf16)
+    a.weight, a.bias, a.dweight, a.dbias = _ptr(weight), _ptr(bias), _ptr(dweight), _ptr(dbias)
+    a.B, a.T, a.H, a.W, a.D, a.temporal, a.lines = B, T, H, W, D, int(temporal), lines
+    return a
+
+
+def peg_fwd(x, y, weight, bias, **kw):
+    call("ctclip_peg_fwd", C.byref(_peg_args(x, y=y, weight=weight, bias=bias, **kw)), _stream())
+
+
+def peg_bwd_data(dy, dx, weight, dx_bf16=None, **kw):
+    call("ctclip_peg_bwd_data", C.byref(_peg_args(dy, y=dx, y_bf16=dx_bf16, weight=weight, **kw)), _stream())
+
+
+def peg_bwd_weight(x, dy, dweight, dbias, **kw):
+    call("ctclip_peg_bwd_weight", C.byref(_peg_args(x, dy=dy, dweight=dweight, dbias=dbias, **kw)), _stream())
+
+
+def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
+               bias=None, bias_t=None, scale=8.0, dim_head=32):
+    a = AttnArgs()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv
+    a.o, a.ldo, a.lse = o.data_ptr(), ldo, _ptr(lse)
+    a.bias, a.bias_t = _ptr(bias), _ptr(bias_t)
+    a.n, a.heads, a.dim_head, a.num_seqs, a.seq_inner = n, heads, dim_head, num_seqs, seq_inner
+    a.seq_outer_stride, a.tok_stride, a.scale = seq_outer_stride, tok_stride, scale
+    return a
+
+
+def attn_fwd(q, k, v, o, lse, **kw):
+    call("ctclip_attn_fwd", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream())
+
+
+def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, **kw):
+    a = _attn_args(q, k, v, o, lse, **kw)
+    a.d_o, a.delta = d_o.data_ptr(), delta.data_ptr()
+    a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = dq.data_ptr(), ld_dq, dk.data_ptr(), ld_dk, dv.data_ptr(), ld_dv
+    a.dbias = _ptr(dbias)
+    a.total_rows = total_rows
+    call("ctclip_attn_bwd", C.byref(a), _stream())
+
+
+def l2norm_bwd(dxh, ld_dxh, xraw, ld_x, scale, dx, ld_dx, dscale, rows, heads, dim_head=32):
+    call("ctclip_l2norm_bwd", dxh.data_ptr(), ld_dxh, xraw.data_ptr(), ld_x, scale.data_ptr(), dx.data_ptr(), ld_dx,
+         dscale.data_ptr(), rows, heads, dim_head, _stream())
+
+
+def sgemm(A, B, Cm, *, M, N, K, trans_a=False, trans_b=False, lda=None, ldb=None, ldc=None, bias=None, act=0,
+          mask_ref=None, accumulate=False):
+    a = SgemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.trans_a = A.data_ptr(), (lda if lda is not None else A.stride(0)), int(trans_a)
+    a.B, a.ldb, a.trans_b = B.data_ptr(), (ldb if ldb is not None else B.stride(0)), int(trans_b)
+    a.C, a.ldc = Cm.data_ptr(), (ldc if ldc is not None else Cm.stride(0))
+    a.bias, a.act = _ptr(bias), act
+    a.mask_ref, a.ld_mask = _ptr(mask_ref), (mask_ref.stride(0) if mask_ref is not None else 0)
+    a.accumulate = int(accumulate)
+    call("ctclip_sgemm_f32", C.byref(a), _stream())
+
+
+def colsum(x, out, *, M, N, ld=None):
+    call("ctclip_colsum", x.data_ptr(), int(x.dtype == torch.bfloat16), ld if ld is not None else x.stride(0), M, N,
+         out.data_ptr(), _stream())
+
+
+def cast_bf16(x, y, n):
+    call("ctclip_cast_f32_bf16", x.data_ptr(), y.data_ptr(), n, _stream())
+
+
+def cpb_inputs(X, h, w):
+    call("ctclip_cpb_inputs", X.data_ptr(), h, w, _stream())
+
+
+def cpb_expand(table, heads, h, w, bias, bias_t=None):
+    call("ctclip_cpb_expand", table.data_ptr(), heads, h, w, bias.data_ptr(), _ptr(bias_t), _stream())
+
+
+def cpb_reduce(dbias, heads, h, w, dtable):
+    call("ctclip_cpb_reduce", dbias.data_ptr(), heads, h, w, dtable.data_ptr(), _stream())
+
+
+def geglu_bwd(dg, h, *, M, n_pairs, colsum_out=None, ld_dg=None, ld_h=None):
+    call("ctclip_geglu_bwd", dg.data_ptr(), ld_dg if ld_dg is not None else dg.stride(0), h.data_ptr(),
+         ld_h if ld_h is not None else h.stride(0), M, n_pairs, _ptr(colsum_out), _stream())
+
+
+def l2norm_rows_bf16(x, y, rows, D):
+    call("ctclip_l2norm_rows_bf16", x.data_ptr(), y.data_ptr(), rows, D, _stream())
+
+
+def vq_gather(idx, embed, out, M, D):
+    call("ctclip_vq_gather", idx.data_ptr(), embed.data_ptr(), out.data_ptr(), M, D, _stream())
+
+
+def vq_gather_pool(idx, embed, *, B, T, S, D, pooled_f32=None, pooled_bf16=None):
+    call("ctclip_vq_gather_pool", idx.data_ptr(), embed.data_ptr(), B, T, S, D, _ptr(pooled_f32), _ptr(pooled_bf16),
+         _stream())
+
+
+def pool_bwd(dpooled, dtok, *, B, T, S, D):
+    call("ctclip_pool_bwd", dpooled.data_ptr(), B, T, S, D, dtok.data_ptr(), _stream())
+
+
+def vq_ema_accum(x, idx, bins, embed_sum, M, D):
+    call("ctclip_vq_ema_accum", x.data_ptr(), idx.data_ptr(), M, D, bins.data_ptr(), embed_sum.data_ptr(), _stream())
+
+
+def vq_ema_update(embed, cluster_size, bins, embed_sum, Cn, D, decay=0.8):
+    call("ctclip_vq_ema_update", embed.data_ptr(), cluster_size.data_ptr(), bins.data_ptr(), embed_sum.data_ptr(), Cn, D,
+         decay, _stream())
+
+
+def prep_weight(W, out, *, K, Np, Kp, gamma=None, rowmap=None, ldw=None):
+    call("ctclip_prep_weight", W.data_ptr(), ldw if ldw is not None else W.stride(0), K, _ptr(gamma), _ptr(rowmap), Np,
+         Kp, out.data_ptr(), _stream())
+
+
+def prep_bias(W, out, *, K, Np, beta=None, bias_in=None, rowmap=None, ldw=None):
+    call("ctclip_prep_bias", W.data_ptr(), ldw if ldw is not None else W.stride(0), K, _ptr(beta), _ptr(bias_in),
+         _ptr(rowmap), Np, out.data_ptr(), _stream())
+
+
+def unprep_wgrad(G, W, dW, *, K, Np, ldg=None, ldw=None, gamma=None, rowmap=None, s=None, dgamma=None, dbeta=None,
+                 dbias=None):
+    call("ctclip_unprep_wgrad", G.data_ptr(), ldg if ldg is not None else G.stride(0), W.data_ptr(),
+         ldw if ldw is not None else W.stride(0), K, _ptr(gamma), _ptr(rowmap), Np, _ptr(s), dW.data_ptr(),
+         _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream())
+
+
+def clip_loss(t_raw, i_raw, temperature, *, B, L, t_hat, i_hat, inv_norm, sim, loss=None, dtemperature=None,
+              d_t_raw=None, d_i_raw=None, row0=0, nrows=0, loss_scale=1.0):
+    a = LossArgs()
+    a.t_raw, a.i_raw, a.B, a.L = t_raw.data_ptr(), i_raw.data_ptr(), B, L
+    a.temperature = temperature.data_ptr()
+    a.t_hat, a.i_hat, a.inv_norm, a.sim = t_hat.data_ptr(), i_hat.data_ptr(), inv_norm.data_ptr(), sim.data_ptr()
+    a.loss, a.dtemperature = _ptr(loss), _ptr(dtemperature)
+    a.d_t_raw, a.d_i_raw = _ptr(d_t_raw), _ptr(d_i_raw)
+    a.row0, a.nrows, a.loss_scale = row0, nrows, loss_scale
+    call("ctclip_clip_loss", C.byref(a), _stream())
+
+
+def clip_sims(t_hat, Bt, i_hat, Bi, L, temperature, out):
+    call("ctclip_clip_sims", t_hat.data_ptr(), Bt, i_hat.data_ptr(), Bi, L, temperature.data_ptr(), out.data_ptr(),
+         _stream())
+
+
+def grad_sumsq(g, n, out):
+    call("ctclip_grad_sumsq", g.data_ptr(), n, out.data_ptr(), _stream())
+
+
+def adam_step(p, g, m, v, n, *, lr, beta1=0.9, beta2=0.99, eps=1e-8, step, max_norm=0.0, sumsq=None, grad_scale=1.0):
+    call("ctclip_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
+         max_norm, _ptr(sumsq), grad_scale, _stream())

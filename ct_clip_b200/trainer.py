@@ -1,0 +1,230 @@
+"""CTClipTrainer -- drop-in for scripts/CTCLIPTrainer.py:113-348 (reference), B200-native step loop.
+
+What one `train_step()` does (reference lines in brackets):
+  batch -> device [CTCLIPTrainer.py:244-251] -> contrastive forward + loss [:254-255] -> backward [:257]
+  -> gradient all-reduce across ranks [accelerate DDP] -> clip_grad_norm_(0.5) [:259-260] -> Adam step [:262-263].
+
+B200-first differences (all documented in DESIGN.md):
+  * one process per GPU with torch.distributed/NCCL (launched by torchrun) instead of HF accelerate;
+  * every trainable tensor lives in ONE flat fp32 arena (params / grads / Adam m / Adam v), so the
+    gradient all-reduce is a single NCCL call over NVLink/NVSwitch and clip + Adam are two kernels;
+  * the loss is the GLOBAL-batch InfoNCE: latents are all-gathered before the similarity matrix
+    (north_star; the reference's DDP loss is rank-local) and gradients are summed, which equals the
+    single-process reference at the global batch size;
+  * parameters that can never receive a gradient on this path (the *_extra projection copies,
+    ct_clip.py:579-581) are left out of the arena, like torch's Adam skips grad-less tensors.
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from .ctclip import CTCLIP
+from .data import SyntheticCTReportDataset, cycle  # noqa: F401
+
+
+def _dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+class ParamArena:
+    """Flat fp32 storage for parameters, gradients and Adam moments; module parameters become views into it."""
+
+    def __init__(self, named_params, device):
+        self.names, self.params, self.offsets = [], [], []
+        off = 0
+        for n, p in named_params:
+            self.names.append(n)
+            self.params.append(p)
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        self.numel = max(off, 4)
+        self.p = torch.zeros(self.numel, device=device)
+        self.g = torch.zeros(self.numel, device=device)
+        self.m = torch.zeros(self.numel, device=device)
+        self.v = torch.zeros(self.numel, device=device)
+        self.grad_views = {}
+        for n, p, o in zip(self.names, self.params, self.offsets):
+            k = p.numel()
+            self.p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.p[o:o + k].view(p.shape)
+            gv = self.g[o:o + k].view(p.shape)
+            p.grad = gv
+            self.grad_views[n] = gv
+        self.sumsq = torch.zeros(1, device=device)
+        self.step = 0
+
+    def zero_grad(self):
+        self.g.zero_()
+        for p, n in zip(self.params, self.names):   # autograd may have replaced .grad; pin it to the arena view again
+            if p.grad is None or p.grad.data_ptr() != self.grad_views[n].data_ptr():
+                p.grad = self.grad_views[n]
+
+    def adam_step(self, *, lr, max_norm, grad_scale=1.0, betas=(0.9, 0.99), eps=1e-8):
+        self.step += 1
+        self.sumsq.zero_()
+        ops.grad_sumsq(self.g, self.numel, self.sumsq)
+        ops.adam_step(self.p, self.g, self.m, self.v, self.numel, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                      step=self.step, max_norm=(max_norm or 0.0), sumsq=self.sumsq, grad_scale=grad_scale)
+
+    def state_dict(self):
+        return dict(step=self.step, names=list(self.names), offsets=list(self.offsets), exp_avg=self.m.cpu(),
+                    exp_avg_sq=self.v.cpu())
+
+    def load_state_dict(self, sd):
+        assert list(sd["names"]) == list(self.names), "optimizer state does not match this model"
+        self.step = int(sd["step"])
+        self.m.copy_(sd["exp_avg"])
+        self.v.copy_(sd["exp_avg_sq"])
+
+
+class CTClipTrainer(nn.Module):
+    def __init__(self, CTClip: CTCLIP, *, num_train_steps, batch_size, data_train="train", data_valid="valid",
+                 reports_file_train="data_reports.xslx", reports_file_valid="data_reports.xslx",
+                 train_meta_file="meta_data.csv", valid_meta_file="meta_data.csv", labels="labels.csv", tokenizer=None,
+                 lr=1.25e-6, wd=0., max_grad_norm=0.5, save_results_every=1, save_model_every=1,
+                 results_folder='./ctclip/', num_workers=8, accelerate_kwargs: dict = dict(),
+                 train_dataset=None, valid_dataset=None, text_max_length=512):
+        super().__init__()
+        assert wd == 0., "the reference trains with wd=0 (Adam, optimizer.py:23-24); AdamW is not part of this build"
+        if not torch.cuda.is_available():
+            raise RuntimeError("CTClipTrainer needs a CUDA (sm_100a) device: there is no CPU training path")
+        self.world, self.rank, local = _dist_env()
+        self.device = torch.device("cuda", local)
+        torch.cuda.set_device(self.device)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.device)
+        self.CTClip = CTClip.to(self.device)
+        self.tokenizer = tokenizer if tokenizer is not None else CTClip.tokenizer
+        self.text_max_length = text_max_length
+        self.register_buffer('steps', torch.Tensor([0]))
+        self.num_train_steps, self.batch_size = num_train_steps, batch_size
+        self.max_grad_norm, self.lr = max_grad_norm, lr
+        self.save_model_every, self.save_results_every = save_model_every, save_results_every
+
+        # ---- data (scripts/data.py output contract: (1,F,H,W) fp32 in [-1,1] or int16 HU + report text / token ids)
+        if train_dataset is None:
+            from .data import load_reference_dataset
+            train_dataset = load_reference_dataset(data_train, reports_file_train, train_meta_file)
+        self.ds = train_dataset
+        self.valid_ds = valid_dataset
+        self.dl = torch.utils.data.DataLoader(self.ds, num_workers=num_workers, batch_size=batch_size, shuffle=True,
+                                              pin_memory=True, collate_fn=getattr(self.ds, "collate", None))
+        self.dl_iter = cycle(self.dl)
+
+        # ---- flat arena over everything that can receive a gradient
+        live = [(n, p) for n, p in self.CTClip.named_parameters()
+                if not n.startswith(("to_text_latent_extra", "to_visual_latent_extra"))]
+        self.arena = ParamArena(live, self.device)
+        self.CTClip.mark_weights_dirty()
+        self.CTClip._grad_sink = {n: self.arena.grad_views[n] for n in self.arena.names}
+        self._setup_dp()
+
+        self.results_folder = Path(results_folder)
+        self.results_folder.mkdir(parents=True, exist_ok=True)
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_dp(self):
+        clip = self.CTClip
+        clip.dp_rank, clip.dp_world = self.rank, self.world
+        if self.world == 1:
+            return
+        # identical initial weights on every rank (DDP broadcasts module state at construction)
+        dist.broadcast(self.arena.p, src=0)
+        for _, b in clip.named_buffers():
+            if b.is_floating_point() and b.numel() > 0:
+                dist.broadcast(b, src=0)
+        clip.mark_weights_dirty()
+
+        def gather(t_raw, i_raw):
+            packed = torch.cat([t_raw, i_raw], dim=1).contiguous()                 # one 32 KB message per rank
+            out = torch.empty(self.world * packed.shape[0], packed.shape[1], device=packed.device)
+            dist.all_gather_into_tensor(out, packed)
+            L = t_raw.shape[1]
+            return out[:, :L].contiguous(), out[:, L:].contiguous()
+
+        clip.dp_all_gather = gather
+        clip.visual_transformer.ema_all_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    @property
+    def is_main(self):
+        return self.rank == 0
+
+    def print(self, msg):
+        if self.is_main:
+            print(msg, flush=True)
+
+    def save(self, path):
+        if not self.is_main:
+            return
+        torch.save(dict(model=self.CTClip.state_dict(), optim=self.arena.state_dict()), path)
+
+    def load(self, path):
+        path = Path(path)
+        assert path.exists()
+        pkg = torch.load(path, map_location="cpu")
+        self.CTClip.load_state_dict(pkg['model'])
+        self.arena.load_state_dict(pkg['optim'])
+        self.CTClip.mark_weights_dirty()
+
+    # ------------------------------------------------------------------------------------------
+    def _tokenize(self, text):
+        if hasattr(text, "input_ids"):
+            return text
+        if isinstance(text, dict):
+            return _Tokens(text["input_ids"], text["attention_mask"])
+        if self.tokenizer is None:
+            raise RuntimeError("no tokenizer (offline): the dataset must yield token ids")
+        return self.tokenizer(list(text), return_tensors="pt", padding="max_length", truncation=True,
+                              max_length=self.text_max_length)
+
+    def step_on_batch(self, video, text_tokens):
+        """forward + backward + all-reduce + clip + Adam on a batch already resident on the device."""
+        self.CTClip.train()
+        self.arena.zero_grad()
+        loss = self.CTClip(text_tokens, video, return_loss=True, device=self.device)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)
+        self.arena.adam_step(lr=self.lr, max_norm=self.max_grad_norm)
+        self.CTClip.mark_weights_dirty()
+        return loss
+
+    def train_step(self):
+        steps = int(self.steps.item())
+        logs = {}
+        video, text = next(self.dl_iter)
+        video = video.to(self.device, non_blocking=True)
+        tok = self._tokenize(text)
+        tok = _Tokens(tok.input_ids.to(self.device, non_blocking=True), tok.attention_mask.to(self.device, non_blocking=True))
+        loss = self.step_on_batch(video, tok)
+        logs['loss'] = loss.item()                      # device->host sync, as the reference (:258)
+        self.print(f"{steps}: loss: {logs['loss']}")
+        if self.is_main and self.save_model_every and not (steps % self.save_model_every):
+            model_path = str(self.results_folder / f'CTClip.{steps}.pt')
+            torch.save(self.CTClip.state_dict(), model_path)
+            self.print(f'{steps}: saving model to {str(self.results_folder)}')
+        self.steps += 1
+        return logs
+
+    def train(self, log_fn=lambda logs: None):
+        while self.steps < self.num_train_steps:
+            logs = self.train_step()
+            log_fn(logs)
+        self.print('training complete')
+
+
+class _Tokens:
+    def __init__(self, input_ids, attention_mask):
+        self.input_ids, self.attention_mask = input_ids, attention_mask
+
+    def to(self, device):
+        return _Tokens(self.input_ids.to(device), self.attention_mask.to(device))

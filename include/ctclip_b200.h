@@ -51,6 +51,11 @@ const char* ctclip_last_error(void);
  *                C2(bf16)[m,j] = gelu_erf(gate_j) * value_j
  *   4 ATOMIC_F32 C(f32)[m,n]  += acc      (red.global.add; with splits > 1 = split-K)
  *   5 ARGMAX     arg_out[m] = argmax_n acc (first max wins), argval_out[m] = max (optional)
+ *   6 L2NORM     per 32-column group (= one attention head, dim_head 32):
+ *                C(bf16)[m,n]  = acc                      (raw q/k/v, optional)
+ *                C2(bf16)[m,n] = acc / max(||acc_group||, 1e-12) * norm_scale[n % 32]   for n < norm_cols
+ *                (attention.py:152-154 l2norm(q)*q_scale fused into the projection)
+ *   7 BIAS_GELU  C(bf16) = gelu_erf(acc + bias), C2(bf16, optional) = acc + bias  (BERT intermediate)
  * splits: split-K factor (only with ATOMIC_F32), >= 1.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -71,9 +76,225 @@ typedef struct {
   int64_t ldc2;
   int32_t* arg_out;
   float* argval_out;
+  int32_t norm_cols;
+  const float* norm_scale;
 } ctclip_gemm_args;
 
 int ctclip_gemm_bf16(const ctclip_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over rows of an fp32 [M, D] tensor (D multiple of 128, <= 1024).
+ * Replaces F.layer_norm at attention.py:35, attention.py:47, ctvit.py:174, attention.py:333 and
+ * BERT's LayerNorms. Outputs are optional (NULL = skip):
+ *   xhat_bf16 = (x-mean)*rstd (standardised row: the GEMM operand when gamma/beta are folded into
+ *   the next Linear), raw_bf16 = bf16(x) (K/V projections read the raw stream, attention.py:139-145),
+ *   y_f32 / y_bf16 = xhat*gamma + beta, rstd_out[M].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* x;
+  int64_t M;
+  int32_t D;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  uint16_t* xhat_bf16;
+  uint16_t* raw_bf16;
+  float* y_f32;
+  uint16_t* y_bf16;
+  float* rstd_out;
+} ctclip_ln_fwd_args;
+int ctclip_ln_fwd(const ctclip_ln_fwd_args* args, void* stream);
+
+/* Backward of the above. g_* = gradient w.r.t. the LN output (gamma != NULL; dgamma/dbeta are
+ * accumulated with atomics) or w.r.t. xhat (gamma == NULL).
+ *   dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) + dres_in + add_bf16   (optional terms)
+ * written as fp32 (dx_f32) and/or bf16 (dx_bf16). dx_f32 may alias dres_in. */
+typedef struct {
+  int64_t M;
+  int32_t D;
+  const float* g_f32;
+  const uint16_t* g_bf16;
+  const float* gamma;
+  const uint16_t* xhat;
+  const float* rstd;
+  const float* dres_in;
+  const uint16_t* add_bf16;
+  float* dx_f32;
+  uint16_t* dx_bf16;
+  float* dgamma;
+  float* dbeta;
+} ctclip_ln_bwd_args;
+int ctclip_ln_bwd(const ctclip_ln_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tubelet im2col + per-patch standardisation: ctvit.py:171-172 (Rearrange + LayerNorm(P) without its
+ * affine, which is folded into the patch Linear). video: [B,C,F,H,W] fp32 (dtype 0) or int16 HU
+ * (dtype 1, value = int16 * scale; scripts/data.py:122-125 uses 1/1000). xhat: bf16 [B*T*Ht*Wt, ld_out],
+ * feature order (c, pt, p1, p2).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* video;
+  int32_t dtype;
+  float scale;
+  int32_t B, C, F, H, W;
+  int32_t pt, p1, p2;
+  float eps;
+  uint16_t* xhat;
+  int64_t ld_out;
+} ctclip_patchify_args;
+int ctclip_patchify(const ctclip_patchify_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PEG: causal depthwise 3x3x3 conv + residual on the canonical fp32 token stream [B,T,H,W,D].
+ * attention.py:63-84 + the residual at :324. temporal = 1 reproduces the reference's reshape of
+ * the (b,h,w,t)-ordered tokens as (b,T,H,W) (SURVEY trap T1).
+ *   ctclip_peg_fwd        : y = x + conv(x) + bias          (y_bf16 optional bf16 copy)
+ *   ctclip_peg_bwd_data   : y = x + conv^T(x)  with x = upstream gradient
+ *   ctclip_peg_bwd_weight : dweight[D,27] += ..., dbias[D] += ...  (x = forward input, dy = upstream)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* x;
+  const float* dy;
+  float* y;
+  uint16_t* y_bf16;
+  const float* weight; /* [D, 27] = dsconv.weight (D,1,3,3,3) */
+  const float* bias;   /* [D] */
+  float* dweight;
+  float* dbias;
+  int32_t B, T, H, W, D;
+  int32_t temporal;
+  int32_t lines;       /* (a0,a1) lines per CTA */
+} ctclip_peg_args;
+int ctclip_peg_fwd(const ctclip_peg_args* args, void* stream);
+int ctclip_peg_bwd_data(const ctclip_peg_args* args, void* stream);
+int ctclip_peg_bwd_weight(const ctclip_peg_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention core (attention.py:156-178), dim_head 32. q/k are the l2-normalised, scaled projections
+ * (GEMM epilogue 6), v raw; all bf16 [rows, heads*32] with leading dimensions ldq/ldk/ldv.
+ * Token rows: row(seq,i) = (seq / seq_inner)*seq_outer_stride + seq % seq_inner + i*tok_stride.
+ * bias (optional): bf16 [heads, n, n]; bias_t its transpose over the last two dims (backward only).
+ * lse: fp32 [rows, heads] log2-domain log-sum-exp (forward output, backward input).
+ * Backward: o, d_o (ld = ldo), delta (fp32 [rows, heads] scratch) -> dq, dk (w.r.t. the normalised
+ * q/k), dv; dbias (fp32 [heads,n,n], accumulated; NULL to skip). total_rows = rows of the token matrix.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const uint16_t* q; int64_t ldq;
+  const uint16_t* k; int64_t ldk;
+  const uint16_t* v; int64_t ldv;
+  uint16_t* o; int64_t ldo;
+  float* lse;
+  const uint16_t* bias;
+  const uint16_t* bias_t;
+  int32_t n, heads, dim_head, num_seqs, seq_inner;
+  int64_t seq_outer_stride, tok_stride;
+  float scale;
+  /* backward only */
+  const uint16_t* d_o;
+  float* delta;
+  uint16_t* dq; int64_t ld_dq;
+  uint16_t* dk; int64_t ld_dk;
+  uint16_t* dv; int64_t ld_dv;
+  float* dbias;
+  int64_t total_rows;
+} ctclip_attn_args;
+int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
+int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
+
+/* Backward of x_hat = x/max(||x||,1e-12)*scale per (row, head) (attention.py:152-154):
+ * dxh, xraw, dx: bf16 [rows, heads*32]; dscale[32] accumulated. */
+int ctclip_l2norm_bwd(const void* dxh, int64_t ld_dxh, const void* xraw, int64_t ld_x, const float* scale, void* dx,
+                      int64_t ld_dx, float* dscale, int64_t rows, int32_t heads, int32_t dim_head, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small fp32 GEMM on CUDA cores for the continuous-position-bias MLP (attention.py:257-276 forces
+ * fp32): C[M,N] = epi(sum_k opA(m,k) opB(k,n)); opA = A^T if trans_a (A stored [K,M]); opB = B^T if
+ * trans_b (B stored [N,K], i.e. an nn.Linear weight). epi: +bias[n], act 1 = LeakyReLU(0.1),
+ * mask_ref: multiply by LeakyReLU'(ref) where ref is the forward activation output; accumulate: C += .
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t M, N, K;
+  const float* A; int64_t lda; int32_t trans_a;
+  const float* B; int64_t ldb; int32_t trans_b;
+  float* C; int64_t ldc;
+  const float* bias;
+  int32_t act;
+  const float* mask_ref; int64_t ld_mask;
+  int32_t accumulate;
+} ctclip_sgemm_args;
+int ctclip_sgemm_f32(const ctclip_sgemm_args* args, void* stream);
+
+/* out[n] += sum_m x[m,n]   (x fp32 or bf16 [M, ld]) -- bias gradients */
+int ctclip_colsum(const void* x, int32_t is_bf16, int64_t ld, int64_t M, int32_t N, float* out, void* stream);
+int ctclip_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* Continuous position bias on the (2h-1)(2w-1) distinct relative offsets (attention.py:263-267):
+ * inputs X[R,2] = sign(rel)*log(|rel|+1); expand table[R,heads] -> bias bf16 [heads,n,n] (+ transposed
+ * copy); reduce dbias fp32 [heads,n,n] -> dtable[R,heads]. */
+int ctclip_cpb_inputs(float* X, int32_t h, int32_t w, void* stream);
+int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, int32_t w, void* bias, void* bias_t, void* stream);
+int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream);
+
+/* GEGLU backward (attention.py:39-42) on the interleaved pre-activation h bf16 [M, 2*n_pairs] (in place):
+ * h[:,2j] <- dg[:,j]*gelu(gate_j), h[:,2j+1] <- dg[:,j]*value_j*gelu'(gate_j); colsum[2*n_pairs] += column sums. */
+int ctclip_geglu_bwd(const void* dg, int64_t ld_dg, void* h, int64_t ld_h, int64_t M, int32_t n_pairs, float* colsum,
+                     void* stream);
+
+/* Vector quantiser pieces (vector_quantize_pytorch==1.1.2 CosineSimCodebook, called at ctvit.py:403):
+ * the argmax itself is GEMM epilogue 5 on (tokens, l2norm(embed)). */
+int ctclip_l2norm_rows_bf16(const float* x, void* y, int32_t rows, int32_t D, void* stream);
+int ctclip_vq_gather(const int32_t* idx, const float* embed, float* out, int64_t M, int32_t D, void* stream);
+int ctclip_vq_gather_pool(const int32_t* idx, const float* embed, int32_t B, int32_t T, int32_t S, int32_t D,
+                          float* pooled_f32, void* pooled_bf16, void* stream);   /* + ct_clip.py:724 mean over t */
+int ctclip_pool_bwd(const float* dpooled, int32_t B, int32_t T, int32_t S, int32_t D, float* dtok, void* stream);
+int ctclip_vq_ema_accum(const float* x, const int32_t* idx, int64_t M, int32_t D, float* bins, float* embed_sum,
+                        void* stream);
+int ctclip_vq_ema_update(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int32_t C, int32_t D,
+                         float decay, void* stream);
+
+/* Weight preparation: out bf16 [Np,Kp] = W[rowmap[r], k] * gamma[k] (zero where rowmap[r] < 0 or k >= K);
+ * bias' [Np] = W[rowmap[r], :] . beta + bias_in[rowmap[r]]; and the reverse mapping of gradients. */
+int ctclip_prep_weight(const float* W, int64_t ldw, int32_t K, const float* gamma, const int32_t* rowmap, int32_t Np,
+                       int32_t Kp, void* out, void* stream);
+int ctclip_prep_bias(const float* W, int64_t ldw, int32_t K, const float* beta, const float* bias_in, const int32_t* rowmap,
+                     int32_t Np, float* out, void* stream);
+int ctclip_unprep_wgrad(const float* G, int64_t ldg, const float* W, int64_t ldw, int32_t K, const float* gamma,
+                        const int32_t* rowmap, int32_t Np, const float* s, float* dW, float* dgamma, float* dbeta,
+                        float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Contrastive head, forward + backward in one call (ct_clip.py:771, :796, :845-878).
+ * t_raw/i_raw: fp32 [B, L] un-normalised latents of the GLOBAL batch. Scratch (caller-allocated):
+ * t_hat/i_hat [B,L], inv_norm [2B], sim [B,B]. Outputs: loss[1], dtemperature[1], and for the rows
+ * [row0, row0+nrows) owned by this rank d_t_raw/d_i_raw [nrows, L]. loss == NULL: only normalise
+ * (inference). loss_scale multiplies all gradients.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* t_raw;
+  const float* i_raw;
+  int32_t B, L;
+  const float* temperature;
+  float* t_hat;
+  float* i_hat;
+  float* inv_norm;
+  float* sim;
+  float* loss;
+  float* dtemperature;
+  float* d_t_raw;
+  float* d_i_raw;
+  int32_t row0, nrows;
+  float loss_scale;
+} ctclip_loss_args;
+int ctclip_clip_loss(const ctclip_loss_args* args, void* stream);
+/* inference similarity (ct_clip.py:805-807), broadcasting a batch of 1 */
+int ctclip_clip_sims(const float* t_hat, int32_t Bt, const float* i_hat, int32_t Bi, int32_t L, const float* temperature,
+                     float* out, void* stream);
+
+/* Optimiser over a flat fp32 arena: out[0] += sum g^2; then clip_grad_norm_(max_norm) + Adam
+ * (CTCLIPTrainer.py:259-263, optimizer.py:23-24). grad_scale multiplies g before everything else. */
+int ctclip_grad_sumsq(const float* g, int64_t n, float* out, void* stream);
+int ctclip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                     int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,95 @@
+"""End-to-end contrastive step (CTCLIP.forward(return_loss=True) + backward) on the sm_100a kernels vs the CPU
+oracle at BASELINE.json configs[0] geometry (dim 512, 4+4 layers, 64x64x32 volume, 32-token text, bs 2).
+
+Tolerance policy (north_star: 1e-2 on the bf16 path): loss to 1e-2 relative; latents / gradients by relative RMS
+error <= 2e-2 (bf16 operands, fp32 accumulation, errors compound over 8 layers forward + backward). Because a
+flipped VQ argmax replaces a whole 512-vector, the oracle's indices are forced when comparing
+tensors downstream of the quantiser; index agreement itself is asserted in tests/test_ctvit_gpu.py.
+"""
+import pytest
+import torch
+
+from tests.helpers import CFG1_VIT, oracle_vit_cfg, rel_err, rms_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Tok:
+    def __init__(self, ids, mask):
+        self.input_ids, self.attention_mask = ids, mask
+
+
+def build_clip(kw, bert_layers=2, seed=0):
+    from transformers import BertConfig, BertModel
+
+    from ct_clip_b200 import CTCLIP, CTViT
+    from oracle import ctclip_oracle as O
+    vit = CTViT(**kw)
+    bert = BertModel(BertConfig(num_hidden_layers=bert_layers, attn_implementation="eager", hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.0))
+    hw = kw["image_size"] // kw["patch_size"]
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=hw * hw * kw["dim"], dim_latent=512)
+    shapes = {k: tuple(v.shape) for k, v in clip.state_dict().items()}
+    sd = O.synth_state_dict(shapes, seed)
+    clip.load_state_dict(sd, strict=True)
+    cfg = O.CTCLIPConfig(vit=oracle_vit_cfg(kw), bert=O.BertConfigLite(layers=bert_layers))
+    return clip.cuda(), sd, cfg
+
+
+def test_contrastive_step_matches_oracle():
+    from oracle import ctclip_oracle as O
+    kw = CFG1_VIT
+    clip, sd, cfg = build_clip(kw)
+    hu, ids, mask = O.synth_inputs(2, 32, 64, 32)
+    video = hu.float() / 1000.0
+    # ---- oracle (CPU fp32, autograd)
+    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
+    out["loss"].backward()
+    # ---- B200 path
+    clip.train()
+    clip.visual_transformer._force_indices = out["indices"]
+    loss = clip(_Tok(ids.cuda(), mask.cuda()), video.cuda(), device="cuda", return_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - out["loss"].item()) < 1e-2 * abs(out["loss"].item()), (loss.item(), out["loss"].item())
+    gmax = max(v.grad.abs().max().item() for v in sdp.values() if v.is_floating_point() and v.grad is not None)
+    report, bad = {}, []
+    for name, p in clip.named_parameters():
+        ref = sdp[name].grad
+        if ref is None or ref.numel() == 0 or ref.abs().max().item() < 1e-6 * gmax:
+            # no gradient in the reference (dead parameters) or analytically-zero gradients (softmax shift invariance)
+            if p.grad is not None and p.grad.numel() > 0:
+                assert p.grad.abs().max().item() < 1e-2 * gmax, name
+            continue
+        assert p.grad is not None, f"missing gradient for {name}"
+        e = rms_err(p.grad, ref)
+        report[name] = e
+        if e > 2e-2:
+            bad.append((name, e))
+    worst = sorted(report.items(), key=lambda kv: -kv[1])[:8]
+    print("worst gradient rms errors:", worst)
+    assert not bad, bad
+    # ---- code-book EMA side effect of the training-mode forward
+    emb = clip.visual_transformer.vq._codebook.embed[0]
+    cs = clip.visual_transformer.vq._codebook.cluster_size[0]
+    assert rms_err(emb, out["ema"][0]) < 1e-2
+    assert rel_err(cs, out["ema"][1]) < 1e-5
+
+
+def test_inference_paths_match_oracle():
+    from oracle import ctclip_oracle as O
+    kw = CFG1_VIT
+    clip, sd, cfg = build_clip(kw)
+    clip.eval()
+    hu, ids, mask = O.synth_inputs(2, 32, 64, 32)
+    video = hu.float() / 1000.0
+    with torch.no_grad():
+        ref = O.ctclip_forward(sd, cfg, ids, mask, video[:1], training=False, return_loss=False)
+        clip.visual_transformer._force_indices = ref["indices"]
+        sims = clip(_Tok(ids.cuda(), mask.cuda()), video[:1].cuda(), device="cuda")       # 2 prompts x 1 volume (zero_shot.py:138)
+        tl, il, toks = clip(_Tok(ids.cuda(), mask.cuda()), video[:1].cuda(), device="cuda", return_latents=True)
+    assert sims.shape == (2,)
+    assert rel_err(sims, ref["sims"]) < 2e-2
+    assert rms_err(tl, ref["text_latents"]) < 1e-2 and rms_err(il, ref["image_latents"]) < 1e-2
+    assert toks.shape == (1, 4, 4, 4, 512) and rel_err(toks, ref["tokens"]) < 1e-6
