@@ -60,7 +60,7 @@ class AttnArgs(C.Structure):
                 ("n", I32), ("heads", I32), ("dim_head", I32), ("num_seqs", I32), ("seq_inner", I32),
                 ("seq_outer_stride", I64), ("tok_stride", I64), ("scale", F32),
                 ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
-                ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64)]
+                ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P)]
 
 
 class SgemmArgs(C.Structure):
@@ -109,6 +109,10 @@ SIGNATURES = {
     "ctclip_clip_sims": [P, I32, P, I32, I32, P, P, P],
     "ctclip_grad_sumsq": [P, I64, P, P],
     "ctclip_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, I32, F32, P, F32, P],
+    "ctclip_bert_embed": [P, P, P, P, P, I64, I32, I32, P],
+    "ctclip_bert_embed_bwd": [P, P, P, P, I64, I32, I32, P],
+    "ctclip_gelu_bwd": [P, I64, P, I64, I64, I32, P, P],
+    "ctclip_zero_shot_probs": [P, P, I32, I32, I32, P, P, P],
 }
 
 # launches of our own kernels issued through this binding (bench.py reports it as gpu_launches)

@@ -44,24 +44,29 @@ __device__ __forceinline__ void group_sync(int group) {
   else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(WPG * 32) : "memory");
 }
 
-constexpr int DH = 32;           // dim_head of the CTViT stacks (run_train.py:25)
-constexpr int KROW = DH + 8;     // padded row (bf16 elements) of row-major [token][d] tiles: conflict-free frag loads
+// DH = dim_head: 32 for the CTViT stacks (run_train.py:25), 64 for the BERT text tower.
+// KROW = DH + 8: padded row (bf16 elements) of row-major [token][d] tiles -> conflict-free fragment loads.
+#define KROW (DH + 8)
 
 // Row-major tile loader: dst[n_pad][KROW] <- src rows (64 B each), zero-filled beyond n.
+template <int DH>
 __device__ __forceinline__ void load_rows(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int head,
                                           const AttnGeom& g, int seq, int n_pad, int tid, int nthreads) {
-  for (int idx = tid; idx < n_pad * 4; idx += nthreads) {
-    const int r = idx >> 2, part = idx & 3;
+  constexpr int PARTS = DH / 8;
+  for (int idx = tid; idx < n_pad * PARTS; idx += nthreads) {
+    const int r = idx / PARTS, part = idx % PARTS;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (r < g.n) val = *reinterpret_cast<const uint4*>(src + g.row(seq, r) * ld + head * DH + part * 8);
     *reinterpret_cast<uint4*>(dst + r * KROW + part * 8) = val;
   }
 }
 // Transposed tile loader: dst[DH][tstride] <- src rows, zero-filled beyond n.
+template <int DH>
 __device__ __forceinline__ void load_rows_t(__nv_bfloat16* dst, int tstride, const __nv_bfloat16* src, long long ld,
                                             int head, const AttnGeom& g, int seq, int n_pad, int tid, int nthreads) {
-  for (int idx = tid; idx < n_pad * 4; idx += nthreads) {
-    const int r = idx >> 2, part = idx & 3;
+  constexpr int PARTS = DH / 8;
+  for (int idx = tid; idx < n_pad * PARTS; idx += nthreads) {
+    const int r = idx / PARTS, part = idx % PARTS;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (r < g.n) val = *reinterpret_cast<const uint4*>(src + g.row(seq, r) * ld + head * DH + part * 8);
     const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&val);
@@ -70,6 +75,7 @@ __device__ __forceinline__ void load_rows_t(__nv_bfloat16* dst, int tstride, con
   }
 }
 // A-operand fragments (16 rows x DH) straight from global memory; rows >= n read as zero.
+template <int DH>
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[DH / 16][4], const __nv_bfloat16* src, long long ld,
                                              int head, const AttnGeom& g, int seq, int r0, int lane) {
   const int gq = lane >> 2, t = lane & 3;
@@ -85,7 +91,7 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[DH / 16][4], const __
   }
 }
 // C[16 x 8*NT] = A[16 x DH] * rows(tile)[key0 .. key0+8*NT)^T  with tile row-major [key][KROW]
-template <int NT>
+template <int NT, int DH>
 __device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[DH / 16][4],
                                          const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
   const int gq = lane >> 2, t = lane & 3;
@@ -103,7 +109,7 @@ __device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[
   }
 }
 // acc[16 x DH] += P[16 x 8*NT] * X[key0.., :]  with X given transposed: xt[d][tstride] (keys contiguous)
-template <int NT>
+template <int NT, int DH>
 __device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&p)[NT][4],
                                          const __nv_bfloat16* xt, int tstride, int key0, int lane, int nt_valid = NT) {
   const int gq = lane >> 2, t = lane & 3;
@@ -137,7 +143,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int WPG, int GROUPS>
+template <int DH, int WPG, int GROUPS, bool MASK>
 __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -147,9 +153,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   const int group = warp / WPG, wig = warp % WPG;
   const int gq = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * GROUPS + group;
-  const size_t group_bytes = (size_t)(n_pad * KROW + DH * tstride) * 2;
+  const size_t group_bytes = (size_t)(n_pad * KROW + DH * tstride) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
   __nv_bfloat16* sVt = sK + n_pad * KROW;
+  int* sMask = reinterpret_cast<int*>(sVt + DH * tstride);   // 1 = key is masked out (only when MASK)
   const bool active = item < (long long)a.num_seqs * a.heads;
   const int head = active ? (int)(item % a.heads) : 0;
   const int seq = active ? (int)(item / a.heads) : 0;
@@ -159,8 +166,11 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.o);
   if (active) {
-    load_rows(sK, k, a.ldk, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
-    load_rows_t(sVt, tstride, v, a.ldv, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+    load_rows<DH>(sK, k, a.ldk, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+    load_rows_t<DH>(sVt, tstride, v, a.ldv, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+    if (MASK)
+      for (int i = wig * 32 + lane; i < n_pad; i += WPG * 32)
+        sMask[i] = (i < a.n && a.key_mask[(long long)seq * a.n + i] != 0) ? 0 : 1;
   }
   group_sync<WPG>(group);
   if (!active) return;
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   for (int rt = wig; rt < row_tiles; rt += WPG) {
     const int r0 = rt * 16;
     uint32_t qa[DH / 16][4];
-    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
     const int ra = r0 + gq, rb = r0 + gq + 8;
     float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
     float oacc[DH / 8][4];
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       float s[8][4];
       const int rem = n_pad - key0;  // multiple of 16
       const int ntv = rem >= 64 ? 8 : rem / 8;
-      qk_block<8>(s, qa, sK, key0, lane, ntv);
+      qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
       float bm_a = -INFINITY, bm_b = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
@@ -192,6 +202,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
           if (bias != nullptr && rr < a.n && kk < a.n)
             val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
           if (kk >= a.n) val = -INFINITY;
+          if (MASK && kk < a.n && sMask[kk]) val = -INFINITY;
           s[nt][e] = val;
         }
         bm_a = fmaxf(bm_a, fmaxf(s[nt][0], s[nt][1]));
@@ -200,16 +211,18 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       bm_a = quad_max(bm_a);
       bm_b = quad_max(bm_b);
       const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
-      const float corr_a = exp2f(m_a - mn_a), corr_b = exp2f(m_b - mn_b);
+      // a fully masked prefix keeps the running max at -inf: use 0 as the reference there (all terms are exp2(-inf) = 0)
+      const float rf_a = (mn_a == -INFINITY) ? 0.f : mn_a, rf_b = (mn_b == -INFINITY) ? 0.f : mn_b;
+      const float corr_a = exp2f(m_a - rf_a), corr_b = exp2f(m_b - rf_b);
       m_a = mn_a;
       m_b = mn_b;
       float ps_a = 0.f, ps_b = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        s[nt][0] = exp2f(s[nt][0] - mn_a);
-        s[nt][1] = exp2f(s[nt][1] - mn_a);
-        s[nt][2] = exp2f(s[nt][2] - mn_b);
-        s[nt][3] = exp2f(s[nt][3] - mn_b);
+        s[nt][0] = exp2f(s[nt][0] - rf_a);
+        s[nt][1] = exp2f(s[nt][1] - rf_a);
+        s[nt][2] = exp2f(s[nt][2] - rf_b);
+        s[nt][3] = exp2f(s[nt][3] - rf_b);
         ps_a += s[nt][0] + s[nt][1];
         ps_b += s[nt][2] + s[nt][3];
       }
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
         oacc[dt][2] *= corr_b; oacc[dt][3] *= corr_b;
       }
       // masked / beyond-n_pad keys carry p == 0 and V^T rows are zero-filled there
-      pv_block<8>(oacc, s, sVt, tstride, key0, lane, ntv);
+      pv_block<8, DH>(oacc, s, sVt, tstride, key0, lane, ntv);
     }
     l_a = quad_sum(l_a);
     l_b = quad_sum(l_b);
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
 // ------------------------------------------------------------------------------------------------
 // backward, part 1 (query-row parallel): dq_hat.   dlogits = P * (dP - delta), dq = scale * dlogits K
 // ------------------------------------------------------------------------------------------------
-template <int WPG, int GROUPS>
+template <int DH, int WPG, int GROUPS, bool MASK>
 __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -256,10 +269,11 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
   const int group = warp / WPG, wig = warp % WPG;
   const int gq = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * GROUPS + group;
-  const size_t group_bytes = (size_t)(2 * n_pad * KROW + DH * tstride) * 2;
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW + DH * tstride) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
   __nv_bfloat16* sV = sK + n_pad * KROW;
   __nv_bfloat16* sKt = sV + n_pad * KROW;
+  int* sMask = reinterpret_cast<int*>(sKt + DH * tstride);
   const bool active = item < (long long)a.num_seqs * a.heads;
   const int head = active ? (int)(item % a.heads) : 0;
   const int seq = active ? (int)(item / a.heads) : 0;
@@ -271,9 +285,12 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
   __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(a.dq);
   if (active) {
     const int tid = wig * 32 + lane;
-    load_rows(sK, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows(sV, v, a.ldv, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t(sKt, tstride, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows<DH>(sK, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows<DH>(sV, v, a.ldv, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t<DH>(sKt, tstride, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
+    if (MASK)
+      for (int i = tid; i < n_pad; i += WPG * 32)
+        sMask[i] = (i < a.n && a.key_mask[(long long)seq * a.n + i] != 0) ? 0 : 1;
   }
   group_sync<WPG>(group);
   if (!active) return;
@@ -282,8 +299,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
   for (int rt = wig; rt < row_tiles; rt += WPG) {
     const int r0 = rt * 16;
     uint32_t qa[DH / 16][4], da[DH / 16][4];
-    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
-    load_a_frags(da, dO, a.ldo, head, g, seq, r0, lane);
+    load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags<DH>(da, dO, a.ldo, head, g, seq, r0, lane);
     const int ra = r0 + gq, rb = r0 + gq + 8;
     float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
     if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
@@ -295,8 +312,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
       float s[4][4], dp[4][4];
       const int rem = n_pad - key0;
       const int ntv = rem >= 32 ? 4 : 2;
-      qk_block<4>(s, qa, sK, key0, lane, ntv);
-      qk_block<4>(dp, da, sV, key0, lane, ntv);
+      qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
+      qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
         const int key = key0 + nt * 8 + 2 * t;
@@ -307,11 +324,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
           float val = s[nt][e] * sc2;
           if (bias != nullptr && rr < a.n && kk < a.n)
             val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
-          const float p = (kk < a.n && rr < a.n) ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
+          bool valid = (kk < a.n) && (rr < a.n);
+          if (MASK && valid && sMask[kk]) valid = false;
+          const float p = valid ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
           s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;  // d(q_hat . k_hat)
         }
       }
-      pv_block<4>(dqa, s, sKt, tstride, key0, lane, ntv);
+      pv_block<4, DH>(dqa, s, sKt, tstride, key0, lane, ntv);
     }
     if (ra < a.n) {
       __nv_bfloat16* orow = dq + g.row(seq, ra) * a.ld_dq + head * DH + 2 * t;
@@ -330,7 +349,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
 // backward, part 2 (key-row parallel): dk_hat, dv.  Works on S^T = K Q^T so that P^T / dS^T come out
 // of the MMA in the register layout the next MMA needs as its A operand.
 // ------------------------------------------------------------------------------------------------
-template <int WPG, int GROUPS>
+template <int DH, int WPG, int GROUPS, bool MASK>
 __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -359,10 +378,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
   __nv_bfloat16* dv = reinterpret_cast<__nv_bfloat16*>(a.dv);
   if (active) {
     const int tid = wig * 32 + lane;
-    load_rows(sQ, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows(sDO, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t(sQt, tstride, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t(sDOt, tstride, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows<DH>(sQ, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows<DH>(sDO, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t<DH>(sQt, tstride, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
+    load_rows_t<DH>(sDOt, tstride, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
     for (int i = tid; i < n_pad; i += WPG * 32) {
       sLse[i] = i < a.n ? a.lse[g.row(seq, i) * a.heads + head] : 0.f;
       sDel[i] = i < a.n ? a.delta[g.row(seq, i) * a.heads + head] : 0.f;
@@ -375,9 +394,14 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
   for (int kt_ = wig; kt_ < key_tiles; kt_ += WPG) {
     const int k0 = kt_ * 16;
     uint32_t ka[DH / 16][4], va[DH / 16][4];
-    load_a_frags(ka, k, a.ldk, head, g, seq, k0, lane);
-    load_a_frags(va, v, a.ldv, head, g, seq, k0, lane);
+    load_a_frags<DH>(ka, k, a.ldk, head, g, seq, k0, lane);
+    load_a_frags<DH>(va, v, a.ldv, head, g, seq, k0, lane);
     const int ka_ = k0 + gq, kb_ = k0 + gq + 8;  // key rows owned by this thread
+    bool keep_a = ka_ < a.n, keep_b = kb_ < a.n;
+    if (MASK) {
+      if (keep_a) keep_a = a.key_mask[(long long)seq * a.n + ka_] != 0;
+      if (keep_b) keep_b = a.key_mask[(long long)seq * a.n + kb_] != 0;
+    }
     float dka[DH / 8][4], dva[DH / 8][4];
 #pragma unroll
     for (int dt = 0; dt < DH / 8; dt++) {
@@ -388,8 +412,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       float s[4][4], dp[4][4];
       const int rem = n_pad - q0;
       const int ntv = rem >= 32 ? 4 : 2;
-      qk_block<4>(s, ka, sQ, q0, lane, ntv);
-      qk_block<4>(dp, va, sDO, q0, lane, ntv);
+      qk_block<4, DH>(s, ka, sQ, q0, lane, ntv);
+      qk_block<4, DH>(dp, va, sDO, q0, lane, ntv);
       float ds[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
@@ -401,7 +425,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
           float val = s[nt][e] * sc2;
           if (biasT != nullptr && qq < a.n && kk < a.n)
             val += __bfloat162float(biasT[((long long)head * a.n + kk) * a.n + qq]) * kLog2e;
-          const bool valid = (kk < a.n) && (qq < a.n);              // also keeps the smem reads in range
+          const bool valid = ((e < 2) ? keep_a : keep_b) && (qq < a.n);   // also keeps the smem reads in range
           const float lq = valid ? sLse[qq] : 0.f;
           const float dq_ = valid ? sDel[qq] : 0.f;
           const float p = valid ? exp2f(val - lq) : 0.f;
@@ -409,8 +433,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
           ds[nt][e] = p * (dp[nt][e] - dq_) * a.scale;              // dS^T (w.r.t. q_hat.k_hat)
         }
       }
-      pv_block<4>(dva, s, sDOt, tstride, q0, lane, ntv);
-      pv_block<4>(dka, ds, sQt, tstride, q0, lane, ntv);
+      pv_block<4, DH>(dva, s, sDOt, tstride, q0, lane, ntv);
+      pv_block<4, DH>(dka, ds, sQt, tstride, q0, lane, ntv);
     }
     if (ka_ < a.n) {
       __nv_bfloat16* r1 = dk + g.row(seq, ka_) * a.ld_dk + head * DH + 2 * t;
@@ -438,6 +462,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
 // CTA = (head, 128 query rows, 64 keys); loops over all sequences; 8 warps x 16 rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a) {
+  constexpr int DH = 32;
   __shared__ __align__(16) __nv_bfloat16 sK[64 * KROW];
   __shared__ __align__(16) __nv_bfloat16 sV[64 * KROW];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -481,14 +506,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a)
     __syncthreads();
     if (r0 >= a.n) continue;
     uint32_t qa[DH / 16][4], da[DH / 16][4];
-    load_a_frags(qa, q, a.ldq, head, g, seq, r0, lane);
-    load_a_frags(da, dO, a.ldo, head, g, seq, r0, lane);
+    load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags<DH>(da, dO, a.ldo, head, g, seq, r0, lane);
     float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
     if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
     if (rb < a.n) { lse_b = a.lse[g.row(seq, rb) * a.heads + head]; del_b = a.delta[g.row(seq, rb) * a.heads + head]; }
     float s[8][4], dp[8][4];
-    qk_block<8>(s, qa, sK, 0, lane);
-    qk_block<8>(dp, da, sV, 0, lane);
+    qk_block<8, DH>(s, qa, sK, 0, lane);
+    qk_block<8, DH>(dp, da, sV, 0, lane);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
       const int key = key0 + nt * 8 + 2 * t;
@@ -513,10 +538,12 @@ __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a)
 }
 
 // delta[row, head] = sum_d dO[row, head, d] * O[row, head, d]
+template <int DH>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                   long long ldo, float* __restrict__ delta, long long rows, int heads) {
-  const long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);  // (row, head)
-  const int part = threadIdx.x & 3;
+  constexpr int PARTS = DH / 8;
+  const long long idx = (long long)blockIdx.x * (blockDim.x / PARTS) + (threadIdx.x / PARTS);  // (row, head)
+  const int part = threadIdx.x % PARTS;
   float s = 0.f;
   if (idx < rows * heads) {
     const long long row = idx / heads;
@@ -532,6 +559,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     }
   }
   s = quad_sum(s);
+  if (PARTS == 8) s += __shfl_xor_sync(0xffffffffu, s, 4);
   if (part == 0 && idx < rows * heads) delta[idx] = s;
 }
 
@@ -542,6 +570,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
                                                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ dx,
                                                         long long ld_dx, float* __restrict__ dscale, long long rows,
                                                         int heads) {
+  constexpr int DH = 32;
   __shared__ float sds[DH];
   if (threadIdx.x < DH) sds[threadIdx.x] = 0.f;
   __syncthreads();
@@ -596,10 +625,11 @@ using namespace ctb;
 
 static int attn_check(const ctclip_attn_args* a, const char* who) {
   CTB_CHECK_ARG(a != nullptr, "%s: null args", who);
-  CTB_CHECK_ARG(a->dim_head == DH, "%s: dim_head must be %d (got %d)", who, DH, a->dim_head);
+  CTB_CHECK_ARG(a->dim_head == 32 || a->dim_head == 64, "%s: dim_head must be 32 or 64 (got %d)", who, a->dim_head);
   CTB_CHECK_ARG(a->n > 0 && a->heads > 0 && a->num_seqs > 0 && a->seq_inner > 0, "%s: bad geometry", who);
   CTB_CHECK_ARG(a->q && a->k && a->v, "%s: null q/k/v", who);
   CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0, "%s: q/k/v rows must be 16B aligned", who);
+  CTB_CHECK_ARG(a->key_mask == nullptr || a->bias == nullptr, "%s: key_mask and bias are not combined on this path", who);
   return CTCLIP_OK;
 }
 
@@ -616,14 +646,42 @@ static int launch_grouped(Kern kern, const ctclip_attn_args* a, size_t group_byt
   return CTCLIP_OK;
 }
 
+// which: 0 = forward, 1 = backward dq, 2 = backward dk/dv.  Group shapes: tiny sequences pack 8 (seq, head) pairs per
+// CTA with one warp each, mid-size (BERT, n <= 256) 2 pairs x 4 warps, long (spatial, n = 576/1024) one pair per CTA.
+template <int DH, bool MASK>
+static int attn_dispatch(int which, const ctclip_attn_args* a, cudaStream_t stream) {
+  const int n_pad = (a->n + 15) & ~15;
+  const int ts = n_pad + 8;
+  const size_t mk = MASK ? (size_t)n_pad * 4 : 0;
+  const size_t gb_fwd = (size_t)(n_pad * (DH + 8) + DH * ts) * 2 + mk;
+  const size_t gb_dq = (size_t)(2 * n_pad * (DH + 8) + DH * ts) * 2 + mk;
+  const size_t gb_dkv = (size_t)(2 * n_pad * (DH + 8) + 2 * DH * ts) * 2 + (size_t)n_pad * 8;
+  if (a->n <= 64) {
+    if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 1, 8, MASK>, a, gb_fwd, 1, 8, stream);
+    if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 1, 8, MASK>, a, gb_dq, 1, 8, stream);
+    return launch_grouped(attn_bwd_dkv_kernel<DH, 1, 8, MASK>, a, gb_dkv, 1, 8, stream);
+  }
+  if (a->n <= 256) {
+    if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 4, 2, MASK>, a, gb_fwd, 4, 2, stream);
+    if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 4, 2, MASK>, a, gb_dq, 4, 2, stream);
+    return launch_grouped(attn_bwd_dkv_kernel<DH, 4, 2, MASK>, a, gb_dkv, 4, 2, stream);
+  }
+  if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 9, 1, MASK>, a, gb_fwd, 9, 1, stream);
+  if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 12, 1, MASK>, a, gb_dq, 12, 1, stream);
+  return launch_grouped(attn_bwd_dkv_kernel<DH, 12, 1, MASK>, a, gb_dkv, 12, 1, stream);
+}
+
+static int attn_route(int which, const ctclip_attn_args* a, cudaStream_t stream) {
+  const bool m = a->key_mask != nullptr;
+  if (a->dim_head == 32) return m ? attn_dispatch<32, true>(which, a, stream) : attn_dispatch<32, false>(which, a, stream);
+  return m ? attn_dispatch<64, true>(which, a, stream) : attn_dispatch<64, false>(which, a, stream);
+}
+
 extern "C" int ctclip_attn_fwd(const ctclip_attn_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = attn_check(a, "attn_fwd")) return rc;
   CTB_CHECK_ARG(a->o != nullptr && a->ldo % 8 == 0, "attn_fwd: bad o");
-  const int n_pad = (a->n + 15) & ~15;
-  const size_t gb = (size_t)(n_pad * KROW + DH * (n_pad + 8)) * 2;
-  if (a->n <= 64) return launch_grouped(attn_fwd_kernel<1, 8>, a, gb, 1, 8, stream);
-  return launch_grouped(attn_fwd_kernel<9, 1>, a, gb, 9, 1, stream);
+  return attn_route(0, a, stream);
 }
 
 extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
@@ -631,30 +689,21 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
   if (int rc = attn_check(a, "attn_bwd")) return rc;
   CTB_CHECK_ARG(a->o && a->d_o && a->lse && a->delta && a->dq && a->dk && a->dv, "attn_bwd: null pointer");
   CTB_CHECK_ARG(a->bias == nullptr || a->bias_t != nullptr, "attn_bwd: bias needs its transposed copy bias_t");
+  CTB_CHECK_ARG(a->dbias == nullptr || a->dim_head == 32, "attn_bwd: dbias is implemented for dim_head 32 only");
   const long long rows = a->total_rows;
   CTB_CHECK_ARG(rows > 0, "attn_bwd: total_rows must be set");
   {
     const long long items = rows * a->heads;
-    const int per_cta = 64;
-    attn_delta_kernel<<<(int)((items + per_cta - 1) / per_cta), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a->o), reinterpret_cast<const __nv_bfloat16*>(a->d_o), a->ldo, a->delta,
-        rows, a->heads);
+    const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(a->o);
+    const __nv_bfloat16* d_o = reinterpret_cast<const __nv_bfloat16*>(a->d_o);
+    if (a->dim_head == 32)
+      attn_delta_kernel<32><<<(int)((items + 63) / 64), 256, 0, stream>>>(o, d_o, a->ldo, a->delta, rows, a->heads);
+    else
+      attn_delta_kernel<64><<<(int)((items + 31) / 32), 256, 0, stream>>>(o, d_o, a->ldo, a->delta, rows, a->heads);
     CTB_LAUNCH_CHECK();
   }
-  const int n_pad = (a->n + 15) & ~15;
-  const size_t gb_dq = (size_t)(2 * n_pad * KROW + DH * (n_pad + 8)) * 2;
-  const size_t gb_dkv = (size_t)(2 * n_pad * KROW + 2 * DH * (n_pad + 8)) * 2 + (size_t)n_pad * 8;
-  int rc;
-  if (a->n <= 64) {
-    rc = launch_grouped(attn_bwd_dq_kernel<1, 8>, a, gb_dq, 1, 8, stream);
-    if (rc) return rc;
-    rc = launch_grouped(attn_bwd_dkv_kernel<1, 8>, a, gb_dkv, 1, 8, stream);
-  } else {
-    rc = launch_grouped(attn_bwd_dq_kernel<12, 1>, a, gb_dq, 12, 1, stream);
-    if (rc) return rc;
-    rc = launch_grouped(attn_bwd_dkv_kernel<12, 1>, a, gb_dkv, 12, 1, stream);
-  }
-  if (rc) return rc;
+  if (int rc = attn_route(1, a, stream)) return rc;
+  if (int rc = attn_route(2, a, stream)) return rc;
   if (a->dbias != nullptr) {
     dim3 grid((a->n + 63) / 64, (a->n + 127) / 128, a->heads);
     attn_bwd_dbias_kernel<<<grid, 256, 0, stream>>>(*a);
@@ -667,7 +716,7 @@ extern "C" int ctclip_l2norm_bwd(const void* dxh, int64_t ld_dxh, const void* xr
                                  void* dx, int64_t ld_dx, float* dscale, int64_t rows, int32_t heads, int32_t dim_head,
                                  void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTB_CHECK_ARG(dim_head == DH, "l2norm_bwd: dim_head must be %d", DH);
+  CTB_CHECK_ARG(dim_head == 32, "l2norm_bwd: dim_head must be 32");
   CTB_CHECK_ARG(dxh && xraw && scale && dx && dscale && rows > 0 && heads > 0, "l2norm_bwd: bad args");
   CTB_CHECK_ARG(ld_dxh % 8 == 0 && ld_x % 8 == 0 && ld_dx % 8 == 0, "l2norm_bwd: rows must be 16B aligned");
   long long ctas = (rows * heads + 63) / 64;

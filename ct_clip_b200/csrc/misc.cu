@@ -346,6 +346,99 @@ __global__ void __launch_bounds__(128) unprep_wgrad_kernel(const float* __restri
   if (dbeta != nullptr && s != nullptr) atomicAdd(dbeta + k, ab);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// BERT text tower helpers (transformers BertEmbeddings / BertIntermediate)
+// ------------------------------------------------------------------------------------------------
+// out[row, :] = word[ids[row], :] + pos[row % n, :] + type0[:]
+__global__ void bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                  const float* __restrict__ pos, const float* __restrict__ type0, float* __restrict__ out,
+                                  long long rows, int n, int H) {
+  const int h4 = H / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * h4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / h4;
+    const int c = (int)(i % h4);
+    const float4 w = reinterpret_cast<const float4*>(word + ids[row] * H)[c];
+    const float4 p = reinterpret_cast<const float4*>(pos + (row % n) * H)[c];
+    const float4 t = reinterpret_cast<const float4*>(type0)[c];
+    reinterpret_cast<float4*>(out)[i] = make_float4(w.x + p.x + t.x, w.y + p.y + t.y, w.z + p.z + t.z, w.w + p.w + t.w);
+  }
+}
+// dword[ids[row]] += g[row], dpos[row % n] += g[row]   (dtype0 = column sum of g, done with ctclip_colsum)
+__global__ void bert_embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ g, float* __restrict__ dword,
+                                      float* __restrict__ dpos, long long rows, int n, int H) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * H; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / H;
+    const int c = (int)(i % H);
+    const float v = g[i];
+    atomicAdd(dword + ids[row] * H + c, v);
+    atomicAdd(dpos + (row % n) * H + c, v);
+  }
+}
+// dpre = dy * gelu'(pre)  (bf16, written over dy); colsum[N] += column sums (bias gradient)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(__nv_bfloat16* __restrict__ dy, long long ld_dy,
+                                                      const __nv_bfloat16* __restrict__ pre, long long ld_pre, long long M,
+                                                      int N, float* __restrict__ colsum, int rows_per_cta) {
+  const int cg = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  const long long m0 = (long long)blockIdx.y * rows_per_cta;
+  const long long m1 = (m0 + rows_per_cta < M) ? m0 + rows_per_cta : M;
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) cs[i] = 0.f;
+  const bool ok = cg * 8 < N;
+  if (ok) {
+    for (long long m = m0 + rl; m < m1; m += 4) {
+      uint4 ud = *reinterpret_cast<const uint4*>(dy + m * ld_dy + cg * 8);
+      const uint4 up = *reinterpret_cast<const uint4*>(pre + m * ld_pre + cg * 8);
+      uint32_t* pd = reinterpret_cast<uint32_t*>(&ud);
+      const uint32_t* pp = reinterpret_cast<const uint32_t*>(&up);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 d = unpack_bf16x2(pd[i]), x = unpack_bf16x2(pp[i]);
+        const float a = d.x * gelu_erf_grad(x.x), b = d.y * gelu_erf_grad(x.y);
+        pd[i] = pack_bf16x2(a, b);
+        cs[2 * i] += a;
+        cs[2 * i + 1] += b;
+      }
+      *reinterpret_cast<uint4*>(dy + m * ld_dy + cg * 8) = ud;
+    }
+  }
+  if (colsum == nullptr) return;
+  __shared__ float red[4][64][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) red[rl][threadIdx.x & 63][i] = cs[i];
+  __syncthreads();
+  if (rl == 0 && ok) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      atomicAdd(colsum + cg * 8 + i, red[0][threadIdx.x][i] + red[1][threadIdx.x][i] + red[2][threadIdx.x][i] + red[3][threadIdx.x][i]);
+  }
+}
+// zero-shot head (scripts/zero_shot.py:140-143): probs[v, p] = softmax([s(v,2p), s(v,2p+1)])[0], s = img . text * exp(T)
+__global__ void zero_shot_probs_kernel(const float* __restrict__ img, const float* __restrict__ txt, int V, int P2, int L,
+                                       const float* __restrict__ temperature, float* __restrict__ probs) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= V * (P2 / 2)) return;
+  const int v = warp / (P2 / 2), p = warp % (P2 / 2);
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = lane; c < L; c += 32) {
+    const float x = img[(long long)v * L + c];
+    s0 += x * txt[(long long)(2 * p) * L + c];
+    s1 += x * txt[(long long)(2 * p + 1) * L + c];
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    const float t = expf(temperature[0]);
+    s0 *= t;
+    s1 *= t;
+    const float m = fmaxf(s0, s1);
+    const float e0 = expf(s0 - m), e1 = expf(s1 - m);
+    probs[warp] = e0 / (e0 + e1);
+  }
+}
+
 }  // namespace ctb
 
 using namespace ctb;
@@ -497,6 +590,44 @@ extern "C" int ctclip_unprep_wgrad(const float* G, int64_t ldg, const float* W, 
   const int rows_per_cta = 64;
   dim3 grid(ceil_div(K, 128), ceil_div(Np, rows_per_cta));
   unprep_wgrad_kernel<<<grid, 128, 0, stream>>>(G, ldg, W, ldw, K, gamma, rowmap, Np, s, dW, dgamma, dbeta, dbias, rows_per_cta);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
+                                 int64_t rows, int32_t n, int32_t H, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(ids && word && pos && type0 && out && rows > 0 && n > 0 && H % 4 == 0, "bert_embed: bad args");
+  bert_embed_kernel<<<grid_for(rows * (H / 4), 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(ids), word, pos,
+                                                                     type0, out, rows, n, H);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_bert_embed_bwd(const int64_t* ids, const float* g, float* dword, float* dpos, int64_t rows, int32_t n,
+                                     int32_t H, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(ids && g && dword && dpos && rows > 0 && n > 0 && H > 0, "bert_embed_bwd: bad args");
+  bert_embed_bwd_kernel<<<grid_for(rows * H, 256), 256, 0, stream>>>(reinterpret_cast<const long long*>(ids), g, dword, dpos,
+                                                                   rows, n, H);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_gelu_bwd(void* dy, int64_t ld_dy, const void* pre, int64_t ld_pre, int64_t M, int32_t N, float* colsum,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dy && pre && M > 0 && N > 0 && N % 8 == 0 && ld_dy % 8 == 0 && ld_pre % 8 == 0, "gelu_bwd: bad args");
+  const int rows_per_cta = 128;
+  dim3 grid(ceil_div(N / 8, 64), ceil_div(M, rows_per_cta));
+  gelu_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(dy), ld_dy,
+                                           reinterpret_cast<const __nv_bfloat16*>(pre), ld_pre, M, N, colsum, rows_per_cta);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_zero_shot_probs(const float* img, const float* txt, int32_t V, int32_t P2, int32_t L,
+                                      const float* temperature, float* probs, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(img && txt && temperature && probs && V > 0 && P2 > 0 && P2 % 2 == 0 && L > 0, "zero_shot_probs: bad args");
+  zero_shot_probs_kernel<<<ceil_div((long long)V * (P2 / 2) * 32, 256), 256, 0, stream>>>(img, txt, V, P2, L, temperature, probs);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

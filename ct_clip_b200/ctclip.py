@@ -16,6 +16,7 @@ from pathlib import Path
 import torch
 from torch import nn
 
+from . import bert as bert_native
 from . import ops
 from .ctvit import CTViT, _GradDict
 
@@ -28,21 +29,30 @@ class _Ctx:
 
 
 class _ClipStepFn(torch.autograd.Function):
-    """(CLS text embeddings, volume, parameters) -> contrastive loss, with the hand-written backward.
+    """(text, volume, parameters) -> contrastive loss, with the hand-written backward.
 
-    The loss kernel produces d(latents) together with the loss, so backward() only has to push those
-    through the projections and the image tower."""
+    text tower: native kernels (cls is None, token ids in `text`) or an external module's CLS output (`cls`).
+    The loss kernel produces d(latents) together with the loss, so backward() only has to push those through the
+    projections and the towers."""
 
     @staticmethod
-    def forward(ctx, module, need_grad, cls, video, names, *params):
+    def forward(ctx, module, need_grad, cls, text, video, names, *params):
         P = dict(zip(names, params))
         vit: CTViT = module.visual_transformer
-        vit_names = [n for n in names if n.startswith("visual_transformer.")]
-        PV = {n[len("visual_transformer."):]: P[n] for n in vit_names}
+        PV = {n[len("visual_transformer."):]: P[n] for n in names if n.startswith("visual_transformer.")}
+        tctx = None
+        if cls is None:   # native BERT
+            PT = {n[len("text_transformer."):]: P[n] for n in names if n.startswith("text_transformer.")}
+            last, tctx = module._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=need_grad)
+            cls_in = last[:, 0, :]
+            ctx.PT = PT
+        else:
+            cls_in = cls
         ectx = vit._run_forward(video, PV, save=need_grad)
-        st = module._heads_forward(cls, ectx, P, want_loss=True, want_grads=need_grad)
-        ctx.module, ctx.names, ctx.ectx, ctx.st = module, names, ectx, st
-        ctx.save_for_backward(cls, *params)
+        st = module._heads_forward(cls_in, ectx, P, want_loss=True, want_grads=need_grad)
+        ctx.module, ctx.names, ctx.ectx, ctx.st, ctx.tctx = module, names, ectx, st, tctx
+        ctx.native_text = cls is None
+        ctx.save_for_backward(cls_in if cls is None else cls, *params)
         return st.loss.view(())
 
     @staticmethod
@@ -51,17 +61,23 @@ class _ClipStepFn(torch.autograd.Function):
         cls, *params = ctx.saved_tensors
         P = dict(zip(names, params))
         sink = getattr(module, "_grad_sink", None)
-        if sink is not None:
-            # trainer mode: accumulate straight into the flat gradient arena, hand nothing back to autograd
-            dcls = module._backward_into(st, ectx, P, _GradDict(sink), cls, float(gout))
-            ctx.ectx = ctx.st = None
-            return (None, None, dcls, None, None) + (None,) * len(names)
-        G = {n: torch.zeros_like(p) for n, p in P.items() if p.requires_grad and p.numel() > 0}
-        Gd = _GradDict(G)
+        if sink is not None:   # trainer mode: accumulate straight into the flat gradient arena
+            Gd, G = _GradDict(sink), None
+        else:
+            G = {n: torch.zeros_like(p) for n, p in P.items() if p.requires_grad and p.numel() > 0}
+            Gd = _GradDict(G)
         dcls = module._backward_into(st, ectx, P, Gd, cls, float(gout))
-        ctx.ectx = ctx.st = None
+        if ctx.native_text:
+            tctx = ctx.tctx
+            d_last = torch.zeros(tctx["M"], dcls.shape[1], device=dcls.device)
+            d_last.view(tctx["b"], tctx["n"], -1)[:, 0, :] = dcls            # only the CLS rows carry gradient (ct_clip.py:762)
+            module._bert_engine().backward(tctx, d_last, ctx.PT, _PrefixView(Gd, "text_transformer."))
+            dcls = None
+        ctx.ectx = ctx.st = ctx.tctx = None
+        if sink is not None:
+            return (None, None, dcls, None, None, None) + (None,) * len(names)
         grads = tuple(G[n] if (n in G and n in Gd.touched) else None for n in names)
-        return (None, None, dcls, None, None) + grads
+        return (None, None, dcls, None, None, None) + grads
 
 
 class CTCLIP(nn.Module):
@@ -122,6 +138,8 @@ class CTCLIP(nn.Module):
         self._wv_bf16 = None
         self._wv_version = None
         self._grad_sink = None
+        self._bert = None
+        self.force_torch_text = False     # debugging / comparison switch: run the text encoder as a torch module
 
     # ------------------------------------------------------------------------------------------
     def state_dict(self, *args, **kwargs):
@@ -143,6 +161,8 @@ class CTCLIP(nn.Module):
 
     def mark_weights_dirty(self):
         self._wv_version = None
+        if self._bert is not None:
+            self._bert.mark_dirty()
         if isinstance(self.visual_transformer, CTViT):
             self.visual_transformer.mark_weights_dirty()
 
@@ -162,7 +182,22 @@ class CTCLIP(nn.Module):
         vn, vt = self.visual_transformer.named_live_tensors()
         names += ["visual_transformer." + n for n in vn]
         tensors += vt
+        if self._text_native():
+            for n, p in self.text_transformer.named_parameters():
+                names.append("text_transformer." + n)
+                tensors.append(p)
         return names, tensors
+
+    def _text_native(self):
+        """True when the injected text encoder is a HF BertModel this build runs on its own kernels."""
+        tt = self.text_transformer
+        return (not self.force_torch_text) and bert_native.supports(tt) and not bert_native.dropout_active(tt)
+
+    def _bert_engine(self):
+        dev = self.to_text_latent.weight.device
+        if self._bert is None or self._bert.device != dev:
+            self._bert = bert_native.BertEngine(self.text_transformer, dev)
+        return self._bert
 
     def _visual_weight_bf16(self, W):
         ver = (W._version, W.data_ptr())
@@ -174,7 +209,12 @@ class CTCLIP(nn.Module):
         return self._wv_bf16
 
     def _text_cls(self, text):
-        """ct_clip.py:685-686 + :762: run the injected text encoder, take the CLS row."""
+        """ct_clip.py:685-686 + :762: run the text encoder, take the CLS row. Returns (enc_text, cls)."""
+        if self._text_native():
+            with torch.no_grad():
+                PT = dict(self.text_transformer.named_parameters())
+                enc_text, _ = self._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=False)
+            return enc_text, enc_text[:, 0, :]
         out = self.text_transformer(text.input_ids, attention_mask=text.attention_mask)
         enc_text = out[0]
         return enc_text, enc_text[:, 0, :]
@@ -190,6 +230,7 @@ class CTCLIP(nn.Module):
         st = _Ctx()
         st.pooled_bf16 = torch.empty(b, K, dtype=torch.bfloat16, device=dev)
         ops.vq_gather_pool(ectx["idx"], ectx["P"]["vq._codebook.embed"], B=b, T=T, S=g.S, D=g.dim, pooled_bf16=st.pooled_bf16)
+        vit._finish_quantize(ectx)      # code-book EMA (training mode) only after the codes have been read
         wv = self._visual_weight_bf16(P["to_visual_latent.weight"])
         i_raw = torch.zeros(b, L, device=dev)
         kb = (K + 63) // 64
@@ -257,25 +298,30 @@ class CTCLIP(nn.Module):
             raise NotImplementedError("multiview augmentation (ct_clip.py:651-675) is unused by the reference scripts")
         if not self._fast_path():
             return self._forward_foreign(text, image, return_loss, return_encodings, return_latents)
-        enc_text, cls = self._text_cls(text)
-        if freeze_text_encoder:
-            cls = cls.detach()
         names, tensors = self._live()
         if return_loss:
-            return _ClipStepFn.apply(self, torch.is_grad_enabled(), cls, image, tuple(names), *tensors)
+            if self._text_native() and not freeze_text_encoder:
+                return _ClipStepFn.apply(self, torch.is_grad_enabled(), None, text, image, tuple(names), *tensors)
+            _, cls = self._text_cls(text)
+            if freeze_text_encoder:
+                cls = cls.detach()
+            return _ClipStepFn.apply(self, torch.is_grad_enabled(), cls, None, image, tuple(names), *tensors)
+        enc_text, cls = self._text_cls(text)
         # inference / export paths: no gradient
         with torch.no_grad():
             P = dict(zip(names, tensors))
             vit: CTViT = self.visual_transformer
             vn, vt = vit.named_live_tensors()
             ectx = vit._run_forward(image, dict(zip(vn, vt)), save=False)
-            st = self._heads_forward(cls, ectx, P, want_loss=False, want_grads=False)
             g = vit.engine.g
+            toks = None
+            if return_latents:    # enc_image_send, ct_clip.py:721 (gathered before any code-book EMA)
+                toks = torch.empty(ectx["M"], g.dim, device=cls.device)
+                ops.vq_gather(ectx["idx"], ectx["P"]["vq._codebook.embed"], toks, ectx["M"], g.dim)
+            st = self._heads_forward(cls, ectx, P, want_loss=False, want_grads=False)
             if return_encodings:  # ct_clip.py:746-747: (enc_text, mean-pooled + flattened image tokens)
                 return enc_text, st.pooled_bf16.float()
             if return_latents:    # ct_clip.py:788-792
-                toks = torch.empty(ectx["M"], g.dim, device=cls.device)
-                ops.vq_gather(ectx["idx"], ectx["P"]["vq._codebook.embed"], toks, ectx["M"], g.dim)
                 return st.t_hat, st.i_hat, toks.view(ectx["b"], ectx["T"], g.H, g.W, g.dim)
             Bt, Bi = st.t_hat.shape[0], st.i_hat.shape[0]
             out = torch.empty(max(Bt, Bi), device=cls.device)

@@ -93,7 +93,8 @@ class _CTViTTokensFn(torch.autograd.Function):
         ectx = module._run_forward(video, P, save=need_grad)
         g = module.engine.g
         tokens = torch.empty(ectx["M"], g.dim, device=video.device)
-        ops.vq_gather(ectx["idx"], P["vq._codebook.embed"], tokens, ectx["M"], g.dim)
+        ops.vq_gather(ectx["idx"], ectx["P"]["vq._codebook.embed"], tokens, ectx["M"], g.dim)
+        module._finish_quantize(ectx)
         ctx.module, ctx.names, ctx.ectx = module, names, ectx
         ctx.save_for_backward(*params)
         module._last_indices = ectx["idx"].view(ectx["b"], ectx["T"], g.H, g.W)
@@ -234,12 +235,16 @@ class CTViT(nn.Module):
         ectx = self.engine.forward(video.contiguous(), P, save=save, taps=taps)
         if self._force_indices is not None:
             ectx["idx"] = self._force_indices.to(device=video.device, dtype=torch.int32).reshape(-1).contiguous()
-        if self.training:
-            with torch.no_grad():
-                self.engine.vq_ema(ectx, P, self.vq_decay, self.ema_all_reduce)
-                self.engine.prepare_codebook(P)
         ectx["P"] = P
         return ectx
+
+    def _finish_quantize(self, ectx):
+        """Training-mode code-book EMA. MUST run after the caller has gathered the quantised tokens: the reference
+        looks codes up in the pre-update code-book (CosineSimCodebook.forward: batched_embedding before ema_inplace)."""
+        if self.training:
+            with torch.no_grad():
+                self.engine.vq_ema(ectx, ectx["P"], self.vq_decay, self.ema_all_reduce)
+                self.engine.prepare_codebook(ectx["P"])
 
     # ------------------------------------------------------------------------------------------
     def forward(self, video, mask=None, return_recons=False, return_recons_only=False, return_discr_loss=False,
@@ -257,6 +262,7 @@ class CTViT(nn.Module):
         if return_only_codebook_ids:
             with torch.no_grad():
                 ectx = self._run_forward(video, dict(zip(names, tensors)), save=False)
+                self._finish_quantize(ectx)
             g = self.engine.g
             return ectx["idx"].view(ectx["b"], ectx["T"], g.H, g.W).long()
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)

@@ -124,13 +124,14 @@ def peg_bwd_weight(x, dy, dweight, dbias, **kw):
 
 
 def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
-               bias=None, bias_t=None, scale=8.0, dim_head=32):
+               bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None):
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv
     a.o, a.ldo, a.lse = o.data_ptr(), ldo, _ptr(lse)
     a.bias, a.bias_t = _ptr(bias), _ptr(bias_t)
     a.n, a.heads, a.dim_head, a.num_seqs, a.seq_inner = n, heads, dim_head, num_seqs, seq_inner
     a.seq_outer_stride, a.tok_stride, a.scale = seq_outer_stride, tok_stride, scale
+    a.key_mask = _ptr(key_mask)
     return a
 
 
@@ -258,3 +259,21 @@ def grad_sumsq(g, n, out):
 def adam_step(p, g, m, v, n, *, lr, beta1=0.9, beta2=0.99, eps=1e-8, step, max_norm=0.0, sumsq=None, grad_scale=1.0):
     call("ctclip_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
          max_norm, _ptr(sumsq), grad_scale, _stream())
+
+
+def bert_embed(ids, word, pos, type0, out, rows, n, H):
+    call("ctclip_bert_embed", ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type0.data_ptr(), out.data_ptr(), rows, n, H,
+         _stream())
+
+
+def bert_embed_bwd(ids, g, dword, dpos, rows, n, H):
+    call("ctclip_bert_embed_bwd", ids.data_ptr(), g.data_ptr(), dword.data_ptr(), dpos.data_ptr(), rows, n, H, _stream())
+
+
+def gelu_bwd(dy, pre, *, M, N, colsum_out=None):
+    call("ctclip_gelu_bwd", dy.data_ptr(), dy.stride(0), pre.data_ptr(), pre.stride(0), M, N, _ptr(colsum_out), _stream())
+
+
+def zero_shot_probs(img, txt, temperature, probs):
+    call("ctclip_zero_shot_probs", img.data_ptr(), txt.data_ptr(), img.shape[0], txt.shape[0], img.shape[1],
+         temperature.data_ptr(), probs.data_ptr(), _stream())

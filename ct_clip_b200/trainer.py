@@ -144,13 +144,7 @@ class CTClipTrainer(nn.Module):
                 dist.broadcast(b, src=0)
         clip.mark_weights_dirty()
 
-        def gather(t_raw, i_raw):
-            packed = torch.cat([t_raw, i_raw], dim=1).contiguous()                 # one 32 KB message per rank
-            out = torch.empty(self.world * packed.shape[0], packed.shape[1], device=packed.device)
-            dist.all_gather_into_tensor(out, packed)
-            L = t_raw.shape[1]
-            return out[:, :L].contiguous(), out[:, L:].contiguous()
-
+        from .dist_utils import gather_latents as gather
         clip.dp_all_gather = gather
         clip.visual_transformer.ema_all_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 

@@ -170,7 +170,7 @@ int ctclip_peg_bwd_data(const ctclip_peg_args* args, void* stream);
 int ctclip_peg_bwd_weight(const ctclip_peg_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Attention core (attention.py:156-178), dim_head 32. q/k are the l2-normalised, scaled projections
+ * Attention core (attention.py:156-178; also BERT self-attention), dim_head 32 or 64. q/k are the l2-normalised, scaled projections
  * (GEMM epilogue 6), v raw; all bf16 [rows, heads*32] with leading dimensions ldq/ldk/ldv.
  * Token rows: row(seq,i) = (seq / seq_inner)*seq_outer_stride + seq % seq_inner + i*tok_stride.
  * bias (optional): bf16 [heads, n, n]; bias_t its transpose over the last two dims (backward only).
@@ -197,6 +197,7 @@ typedef struct {
   uint16_t* dv; int64_t ld_dv;
   float* dbias;
   int64_t total_rows;
+  const int32_t* key_mask; /* optional [num_seqs, n]: non-zero = key may be attended (BERT padding mask) */
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
@@ -295,6 +296,21 @@ int ctclip_clip_sims(const float* t_hat, int32_t Bt, const float* i_hat, int32_t
 int ctclip_grad_sumsq(const float* g, int64_t n, float* out, void* stream);
 int ctclip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                      int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
+
+/* BERT text tower helpers (transformers.BertModel, called at ct_clip.py:685): embeddings gather
+ * (word[ids] + position + token_type 0) and its scatter-add backward; GELU backward of BertIntermediate
+ * (dy <- dy * gelu'(pre), colsum += bias gradient). The Linear layers use ctclip_gemm_bf16 (epilogues 0/2/7),
+ * the LayerNorms ctclip_ln_*, self-attention ctclip_attn_* with dim_head 64 and key_mask. */
+int ctclip_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out, int64_t rows,
+                      int32_t n, int32_t H, void* stream);
+int ctclip_bert_embed_bwd(const int64_t* ids, const float* g, float* dword, float* dpos, int64_t rows, int32_t n, int32_t H,
+                          void* stream);
+int ctclip_gelu_bwd(void* dy, int64_t ld_dy, const void* pre, int64_t ld_pre, int64_t M, int32_t N, float* colsum,
+                    void* stream);
+/* zero-shot head (scripts/zero_shot.py:133-143): probs[v, p] = softmax over the prompt pair (2p, 2p+1) of
+ * img_hat[v] . txt_hat[.] * exp(T); img [V,L], txt [P2,L] l2-normalised fp32, probs [V, P2/2]. */
+int ctclip_zero_shot_probs(const float* img, const float* txt, int32_t V, int32_t P2, int32_t L, const float* temperature,
+                           float* probs, void* stream);
 
 #ifdef __cplusplus
 }

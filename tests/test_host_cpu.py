@@ -1,0 +1,149 @@
+"""CPU suite part 3: host-side logic -- drop-in surface (import names, constructor kwargs, state-dict layout),
+parameter arena layout, synthetic data contract, and the data-parallel math on 2 gloo ranks."""
+import os
+import socket
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ctclip_oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_dropin_import_names_and_constructor_surface():
+    from ct_clip import CTCLIP            # scripts/run_train.py:3
+    from transformer_maskgit import CTViT  # scripts/run_train.py:1
+    from transformers import BertConfig, BertModel
+    vit = CTViT(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=8)                               # run_train.py:17-27 keywords
+    assert vit.patch_height_width == (24, 24) and vit.image_num_tokens == 576
+    bert = BertModel(BertConfig(num_hidden_layers=1))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=294912, dim_latent=512,
+                  extra_latent_projection=False, use_mlm=False, downsample_image_embeds=False, use_all_token_embeds=False)  # :31-42
+    sd = clip.state_dict()
+    assert sd["to_visual_latent.weight"].shape == (512, 294912) and sd["temperature"].shape == ()
+    assert "to_visual_latent_extra.weight" in sd and "visual_transformer.vq._codebook.embed" in sd
+    with pytest.raises(NotImplementedError):
+        CTCLIP(image_encoder=vit, text_encoder=bert, use_mlm=True)
+    with pytest.raises(NotImplementedError):
+        CTCLIP(dim_text=768)
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "scripts"))
+    from CTCLIPTrainer import CTClipTrainer  # noqa: F401  (run_train.py:4)
+    from zero_shot import CTClipInference  # noqa: F401    (run_zero_shot.py:4)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "scramble"])
+def test_state_dict_layout_matches_reference_golden(name):
+    """Key set and shapes equal the reference's own state_dict (recorded in the golden file)."""
+    from transformers import BertConfig, BertModel
+
+    from ct_clip_b200 import CTCLIP, CTViT
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    c = g["case"]
+    vit = CTViT(**c["vit"])
+    bert = BertModel(BertConfig(num_hidden_layers=c["bert_layers"]))
+    hw = c["vit"]["image_size"] // c["vit"]["patch_size"]
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=hw * hw * c["vit"]["dim"], dim_latent=512)
+    mine = {k: list(v.shape) for k, v in clip.state_dict().items()}
+    assert mine == g["shapes"]
+    clip.load_state_dict(O.synth_state_dict({k: tuple(v) for k, v in g["shapes"].items()}, 0), strict=True)
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly off-GPU instead of silently computing elsewhere."""
+    from ct_clip_b200 import CTViT
+    vit = CTViT(dim=128, codebook_size=64, image_size=16, patch_size=8, temporal_patch_size=2, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=4)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            vit(torch.zeros(1, 1, 4, 16, 16), return_encoded_tokens=True)
+
+
+def test_param_arena_layout():
+    from ct_clip_b200.trainer import ParamArena
+    ps = [("a", torch.nn.Parameter(torch.randn(3, 5))), ("b", torch.nn.Parameter(torch.randn(()))),
+          ("c", torch.nn.Parameter(torch.randn(7)))]
+    orig = [p.detach().clone() for _, p in ps]
+    ar = ParamArena(ps, torch.device("cpu"))
+    assert ar.offsets == [0, 16, 20] and ar.numel == 28
+    for (n, p), o in zip(ps, orig):
+        assert torch.equal(p.detach(), o)
+        assert p.data.untyped_storage().data_ptr() == ar.p.untyped_storage().data_ptr()
+        assert p.grad.untyped_storage().data_ptr() == ar.g.untyped_storage().data_ptr()
+    ps[0][1].grad.add_(1.0)
+    assert ar.g[:15].eq(1).all() and ar.g[15] == 0
+    ar.zero_grad()
+    assert ar.g.abs().sum() == 0
+
+
+def test_synthetic_dataset_contract():
+    from ct_clip_b200.data import SyntheticCTReportDataset
+    ds = SyntheticCTReportDataset(4, frames=8, image=16, n_text=12)
+    v, t = ds[1]
+    v2, _ = ds[1]
+    assert v.shape == (1, 8, 16, 16) and v.dtype == torch.int16 and torch.equal(v, v2)
+    assert v.min() >= -1000 and v.max() <= 1000
+    assert t["input_ids"][0] == 2 and t["attention_mask"].sum() >= 3
+    last = int(t["attention_mask"].sum()) - 1
+    assert t["input_ids"][last] == 3 and (t["input_ids"][last + 1:] == 0).all()
+    vols, toks = ds.collate([ds[0], ds[1]])
+    assert vols.shape == (2, 1, 8, 16, 16) and toks["input_ids"].shape == (2, 12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, b, L, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ct_clip_b200.dist_utils import gather_latents, rank_rows
+    g = torch.Generator().manual_seed(11)
+    T, I = torch.randn(world * b, L, generator=g), torch.randn(world * b, L, generator=g)     # the global batch
+    W = torch.randn(L, L, generator=g) / L ** 0.5                                               # a shared parameter
+    r0, nr = rank_rows(rank, b)
+    t_loc = T[r0:r0 + nr].clone().requires_grad_(True)
+    Wl = W.clone().requires_grad_(True)
+    i_loc = I[r0:r0 + nr] @ Wl
+    tg, ig = gather_latents(t_loc.detach(), i_loc.detach())
+    # every rank evaluates the GLOBAL loss, differentiating only through its own rows
+    tg = torch.cat([tg[:r0], t_loc, tg[r0 + nr:]])
+    ig = torch.cat([ig[:r0], i_loc, ig[r0 + nr:]])
+    norm = torch.nn.functional.normalize
+    loss = O.clip_loss(norm(tg, dim=-1), norm(ig, dim=-1), torch.tensor(1.0))
+    loss.backward()
+    gw = Wl.grad.clone()
+    dist.all_reduce(gw, op=dist.ReduceOp.SUM)          # gradients are SUMMED across ranks (not averaged)
+    ret[rank] = (loss.item(), t_loc.grad.clone(), gw)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_global_loss_two_ranks_gloo():
+    world, b, L = 2, 3, 32
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, _free_port(), b, L, ret), nprocs=world, join=True)
+    # single-process reference at the global batch size
+    g = torch.Generator().manual_seed(11)
+    T, I = torch.randn(world * b, L, generator=g), torch.randn(world * b, L, generator=g)
+    W = torch.randn(L, L, generator=g) / L ** 0.5
+    T.requires_grad_(True)
+    W.requires_grad_(True)
+    norm = torch.nn.functional.normalize
+    loss = O.clip_loss(norm(T, dim=-1), norm(I @ W, dim=-1), torch.tensor(1.0))
+    loss.backward()
+    for r in range(world):
+        l_r, dt_r, gw_r = ret[r]
+        assert abs(l_r - loss.item()) < 1e-6
+        assert torch.allclose(dt_r, T.grad[r * b:(r + 1) * b], atol=1e-6)
+        assert torch.allclose(gw_r, W.grad, atol=1e-5)

@@ -1,0 +1,133 @@
+"""CPU suite part 1: pin the oracle. (a) against the committed golden vectors produced by the unmodified reference,
+(b) against the reference itself when /root/reference is mounted (build container only), (c) BERT restatement
+against transformers.BertModel, (d) properties of the restated vector quantiser."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import ctclip_oracle as O
+from oracle import ref_shims, vq_restated
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _sub_close(t, ref, tol):
+    f = t.detach().reshape(-1).float()
+    k = ref["head"].numel()
+    scale = max(ref["norm"] / max(ref["numel"], 1) ** 0.5, 1e-12)
+    assert f.numel() == ref["numel"]
+    assert (f[:k] - ref["head"]).abs().max().item() <= tol * max(scale, ref["head"].abs().max().item())
+    assert (f[-k:] - ref["tail"]).abs().max().item() <= tol * max(scale, ref["tail"].abs().max().item())
+    assert abs(f.norm().item() - ref["norm"]) <= tol * max(ref["norm"], 1e-12)
+
+
+def _cfg(case):
+    v = case["vit"]
+    return O.CTCLIPConfig(vit=O.CTViTConfig(dim=v["dim"], codebook_size=v["codebook_size"], image_size=v["image_size"],
+                                            patch_size=v["patch_size"], temporal_patch_size=v["temporal_patch_size"],
+                                            spatial_depth=v["spatial_depth"], temporal_depth=v["temporal_depth"],
+                                            dim_head=v["dim_head"], heads=v["heads"]),
+                          bert=O.BertConfigLite(layers=case["bert_layers"]))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "scramble"])
+def test_oracle_matches_golden_reference_outputs(name):
+    g = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    case, cfg = g["case"], _cfg(g["case"])
+    shapes = {k: tuple(v) for k, v in g["shapes"].items()}
+    sd = O.synth_state_dict(shapes, 0)
+    hu, ids, mask = O.synth_inputs(case["b"], case["frames"], case["vit"]["image_size"], case["n_text"])
+    video = hu.float() / 1000.0
+    with torch.no_grad():
+        ev = O.ctclip_forward(sd, cfg, ids, mask, video, training=False, return_loss=False)
+        assert torch.equal(ev["indices"], g["eval"]["indices"])
+        assert torch.allclose(ev["text_latents"], g["eval"]["text_latents"], atol=2e-6)
+        assert torch.allclose(ev["image_latents"], g["eval"]["image_latents"], atol=2e-6)
+        _sub_close(ev["tokens"], g["eval"]["tokens"], 1e-5)
+        s2 = O.ctclip_forward(sd, cfg, ids[:2], mask[:2], video[:1], training=False, return_loss=False)["sims"]
+        assert torch.allclose(s2, g["eval"]["sims"], atol=1e-5)
+    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
+    out["loss"].backward()
+    assert abs(out["loss"].item() - g["train"]["loss"]) < 1e-5
+    gmax = max(r["norm"] for r in g["train"]["grads"].values())
+    for n, ref in g["train"]["grads"].items():
+        got = sdp[n].grad
+        assert got is not None, n
+        if ref["norm"] < 1e-6 * gmax:      # analytically-zero gradients (key bias, last CPB bias): round-off only
+            assert got.norm().item() < 1e-5 * gmax, n
+            continue
+        _sub_close(got, ref, 2e-3)
+    for n in g["train"]["no_grad"]:        # parameters the reference never reaches must not be reached here either
+        gg = sdp[n].grad
+        assert gg is None or gg.abs().max().item() == 0, n
+    _sub_close(out["ema"][0], g["train"]["embed"], 1e-5)
+    _sub_close(out["ema"][1], g["train"]["cluster_size"], 1e-6)
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference checkout not mounted (GPU box)")
+def test_oracle_matches_reference_live():
+    from transformers import BertConfig, BertModel
+    CTViT, CTCLIP = ref_shims.load_reference()
+    kw = dict(dim=256, codebook_size=256, image_size=32, patch_size=8, temporal_patch_size=4, spatial_depth=2, temporal_depth=1,
+              dim_head=32, heads=8)
+    vit = CTViT(**kw)
+    bert = BertModel(BertConfig(num_hidden_layers=1, attn_implementation="eager", hidden_dropout_prob=0.0,
+                                attention_probs_dropout_prob=0.0))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=16 * 256, dim_latent=512)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in clip.state_dict().items()}, 3)
+    clip.load_state_dict(sd, strict=True)
+    hu, ids, mask = O.synth_inputs(3, 12, 32, 16, seed=7)
+    video = hu.float() / 1000.0
+
+    class Tok:
+        input_ids, attention_mask = ids, mask
+    clip.train()
+    loss = clip(Tok, video, device="cpu", return_loss=True)
+    loss.backward()
+    cfg = O.CTCLIPConfig(vit=O.CTViTConfig(dim=256, codebook_size=256, image_size=32, patch_size=8, temporal_patch_size=4,
+                                           spatial_depth=2, temporal_depth=1), bert=O.BertConfigLite(layers=1))
+    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
+    out["loss"].backward()
+    assert abs(out["loss"].item() - loss.item()) < 1e-6
+    gmax = max(p.grad.abs().max().item() for p in clip.parameters() if p.grad is not None and p.grad.numel())
+    for n, p in clip.named_parameters():
+        if p.grad is None or p.grad.numel() == 0:
+            continue
+        assert (p.grad - sdp[n].grad).abs().max().item() < 2e-5 * gmax, n
+    assert torch.allclose(vit.vq._codebook.embed[0], out["ema"][0], atol=1e-6)
+
+
+def test_bert_restatement_matches_transformers():
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(0)
+    bert = BertModel(BertConfig(num_hidden_layers=2, attn_implementation="eager")).eval()
+    sd = {"t." + k: v for k, v in bert.state_dict().items()}
+    _, ids, mask = O.synth_inputs(3, 4, 16, 24)
+    with torch.no_grad():
+        ref = bert(ids, attention_mask=mask)[0]
+        got = O.bert_forward(ids, mask, sd, "t.", O.BertConfigLite(layers=2))
+    assert torch.allclose(ref, got, atol=2e-5)
+
+
+def test_vq_restated_semantics():
+    torch.manual_seed(1)
+    embed = torch.nn.functional.normalize(torch.randn(8, 4), dim=-1)
+    embed[5] = embed[2]                                   # exact tie: first index must win (torch.argmax semantics)
+    x = embed[[5, 0, 7]] * torch.tensor([[3.0], [0.5], [2.0]])   # positive scaling must not change the winner
+    q, ind, flat = vq_restated.vq_cosine_lookup(x, embed)
+    assert ind.tolist() == [2, 0, 7]
+    assert torch.equal(q, embed[ind])                    # un-renormalised rows of the stored buffer
+    new_e, new_c = vq_restated.vq_ema_update(flat, ind, embed, torch.zeros(8), decay=0.8)
+    assert torch.allclose(new_c, torch.tensor([0.2, 0, 0.2, 0, 0, 0, 0, 0.2]))
+    untouched = [1, 3, 4, 5, 6]
+    assert torch.allclose(new_e[untouched], embed[untouched], atol=1e-6)        # 0.8 e + 0.2 l2norm(e) == e for unit rows
+    vq = vq_restated.VectorQuantize(dim=4, codebook_size=8)
+    vq.train()
+    xx = torch.randn(2, 5, 4, requires_grad=True)
+    qq, ii, loss = vq(xx)
+    qq.sum().backward()
+    assert torch.allclose(xx.grad, torch.ones_like(xx))  # straight-through estimator
+    assert ii.shape == (2, 5) and loss.shape == (1,)
