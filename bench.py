@@ -192,10 +192,21 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM family) from CUDA events recorded around its launches
     gsum_ms, gflops, n_g = 0.0, 0.0, 0
-    for ev0, ev1, fl in gemm_events:
-        gsum_ms += ev0.elapsed_time(ev1)
+    by_shape = {}
+    for ev0, ev1, fl, shp in gemm_events:
+        t_ = ev0.elapsed_time(ev1)
+        gsum_ms += t_
         gflops += fl
         n_g += 1
+        a_ = by_shape.setdefault(shp, [0, 0.0, 0.0])
+        a_[0] += 1
+        a_[1] += t_
+        a_[2] += fl
+    if rank == 0 and os.environ.get("CTCLIP_BENCH_GEMM_TABLE"):
+        with open(os.environ["CTCLIP_BENCH_GEMM_TABLE"], "w") as f:
+            f.write("M N K a_major b_major epi splits | launches total_ms TFLOP/s\n")
+            for shp, (c_, t_, fl_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{shp} | {c_} {t_:.3f} {fl_ / (t_ * 1e-3) / 1e12 if t_ > 0 else 0:.1f}\n")
     peaks = load_peaks()
     achieved = (gflops / (gsum_ms * 1e-3) / 1e12) if gsum_ms > 0 else 0.0
     vit = clip.visual_transformer

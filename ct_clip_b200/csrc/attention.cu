@@ -131,6 +131,60 @@ __device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&
   }
 }
 
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One 16 x 8*NT block of raw dot products -> log2-domain logits  s*sc2 + bias*log2(e);  columns >= n, masked keys and
+// tiles >= nt_valid become -inf (=> probability 0). brow_a / brow_b: bias rows of the two fragment rows (nullptr: none).
+template <int NT, bool MASK>
+__device__ __forceinline__ void logits_tile(float (&s)[NT][4], float sc2, const __nv_bfloat16* brow_a,
+                                            const __nv_bfloat16* brow_b, int c0, int t, int n, bool cols_full, bool pair_ok,
+                                            const int* sMask, int nt_valid) {
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    if (nt >= nt_valid) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
+      continue;
+    }
+    const int c = c0 + nt * 8 + 2 * t;
+    const bool ok0 = cols_full || c < n, ok1 = cols_full || c + 1 < n;
+    float ba0 = 0.f, ba1 = 0.f, bb0 = 0.f, bb1 = 0.f;
+    if (brow_a != nullptr) {
+      if (ok1 && pair_ok) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(brow_a + c));
+        ba0 = f.x; ba1 = f.y;
+      } else {
+        if (ok0) ba0 = __bfloat162float(brow_a[c]);
+        if (ok1) ba1 = __bfloat162float(brow_a[c + 1]);
+      }
+    }
+    if (brow_b != nullptr) {
+      if (ok1 && pair_ok) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(brow_b + c));
+        bb0 = f.x; bb1 = f.y;
+      } else {
+        if (ok0) bb0 = __bfloat162float(brow_b[c]);
+        if (ok1) bb1 = __bfloat162float(brow_b[c + 1]);
+      }
+    }
+    s[nt][0] = fmaf(s[nt][0], sc2, ba0 * kLog2e);
+    s[nt][1] = fmaf(s[nt][1], sc2, ba1 * kLog2e);
+    s[nt][2] = fmaf(s[nt][2], sc2, bb0 * kLog2e);
+    s[nt][3] = fmaf(s[nt][3], sc2, bb1 * kLog2e);
+    bool m0 = !ok0, m1 = !ok1;
+    if (MASK) {
+      if (ok0 && sMask[c]) m0 = true;
+      if (ok1 && sMask[c + 1]) m1 = true;
+    }
+    if (m0) s[nt][0] = s[nt][2] = -INFINITY;
+    if (m1) s[nt][1] = s[nt][3] = -INFINITY;
+  }
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -181,6 +235,9 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
     uint32_t qa[DH / 16][4];
     load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
     const int ra = r0 + gq, rb = r0 + gq + 8;
+    const bool pair_ok = (a.n & 1) == 0;
+    const __nv_bfloat16* brow_a = (bias != nullptr && ra < a.n) ? bias + ((long long)head * a.n + ra) * a.n : nullptr;
+    const __nv_bfloat16* brow_b = (bias != nullptr && rb < a.n) ? bias + ((long long)head * a.n + rb) * a.n : nullptr;
     float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
     float oacc[DH / 8][4];
 #pragma unroll
@@ -190,21 +247,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       const int rem = n_pad - key0;  // multiple of 16
       const int ntv = rem >= 64 ? 8 : rem / 8;
       qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
+      logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv);
       float bm_a = -INFINITY, bm_b = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        const int key = key0 + nt * 8 + 2 * t;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int kk = key + (e & 1);
-          const int rr = (e < 2) ? ra : rb;
-          float val = s[nt][e] * sc2;
-          if (bias != nullptr && rr < a.n && kk < a.n)
-            val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
-          if (kk >= a.n) val = -INFINITY;
-          if (MASK && kk < a.n && sMask[kk]) val = -INFINITY;
-          s[nt][e] = val;
-        }
         bm_a = fmaxf(bm_a, fmaxf(s[nt][0], s[nt][1]));
         bm_b = fmaxf(bm_b, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -213,16 +259,16 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
       // a fully masked prefix keeps the running max at -inf: use 0 as the reference there (all terms are exp2(-inf) = 0)
       const float rf_a = (mn_a == -INFINITY) ? 0.f : mn_a, rf_b = (mn_b == -INFINITY) ? 0.f : mn_b;
-      const float corr_a = exp2f(m_a - rf_a), corr_b = exp2f(m_b - rf_b);
+      const float corr_a = fast_exp2(m_a - rf_a), corr_b = fast_exp2(m_b - rf_b);
       m_a = mn_a;
       m_b = mn_b;
       float ps_a = 0.f, ps_b = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        s[nt][0] = exp2f(s[nt][0] - rf_a);
-        s[nt][1] = exp2f(s[nt][1] - rf_a);
-        s[nt][2] = exp2f(s[nt][2] - rf_b);
-        s[nt][3] = exp2f(s[nt][3] - rf_b);
+        s[nt][0] = fast_exp2(s[nt][0] - rf_a);
+        s[nt][1] = fast_exp2(s[nt][1] - rf_a);
+        s[nt][2] = fast_exp2(s[nt][2] - rf_b);
+        s[nt][3] = fast_exp2(s[nt][3] - rf_b);
         ps_a += s[nt][0] + s[nt][1];
         ps_b += s[nt][2] + s[nt][3];
       }
@@ -302,9 +348,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
     load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
     load_a_frags<DH>(da, dO, a.ldo, head, g, seq, r0, lane);
     const int ra = r0 + gq, rb = r0 + gq + 8;
-    float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
+    // rows beyond n: lse = +inf makes their probabilities exactly 0
+    float lse_a = INFINITY, lse_b = INFINITY, del_a = 0.f, del_b = 0.f;
     if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
     if (rb < a.n) { lse_b = a.lse[g.row(seq, rb) * a.heads + head]; del_b = a.delta[g.row(seq, rb) * a.heads + head]; }
+    const bool pair_ok = (a.n & 1) == 0;
+    const __nv_bfloat16* brow_a = (bias != nullptr && ra < a.n) ? bias + ((long long)head * a.n + ra) * a.n : nullptr;
+    const __nv_bfloat16* brow_b = (bias != nullptr && rb < a.n) ? bias + ((long long)head * a.n + rb) * a.n : nullptr;
     float dqa[DH / 8][4];
 #pragma unroll
     for (int dt = 0; dt < DH / 8; dt++) dqa[dt][0] = dqa[dt][1] = dqa[dt][2] = dqa[dt][3] = 0.f;
@@ -314,20 +364,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
       const int ntv = rem >= 32 ? 4 : 2;
       qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
       qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
+      logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv);
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
-        const int key = key0 + nt * 8 + 2 * t;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const int kk = key + (e & 1);
-          const int rr = (e < 2) ? ra : rb;
-          float val = s[nt][e] * sc2;
-          if (bias != nullptr && rr < a.n && kk < a.n)
-            val += __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e;
-          bool valid = (kk < a.n) && (rr < a.n);
-          if (MASK && valid && sMask[kk]) valid = false;
-          const float p = valid ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
-          s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;  // d(q_hat . k_hat)
+          const float p = fast_exp2(s[nt][e] - ((e < 2) ? lse_a : lse_b));           // -inf logits -> 0
+          s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;          // d(q_hat . k_hat)
         }
       }
       pv_block<4, DH>(dqa, s, sKt, tstride, key0, lane, ntv);
@@ -397,6 +440,9 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
     load_a_frags<DH>(ka, k, a.ldk, head, g, seq, k0, lane);
     load_a_frags<DH>(va, v, a.ldv, head, g, seq, k0, lane);
     const int ka_ = k0 + gq, kb_ = k0 + gq + 8;  // key rows owned by this thread
+    const bool pair_ok = (a.n & 1) == 0;
+    const __nv_bfloat16* brow_a = (biasT != nullptr && ka_ < a.n) ? biasT + ((long long)head * a.n + ka_) * a.n : nullptr;
+    const __nv_bfloat16* brow_b = (biasT != nullptr && kb_ < a.n) ? biasT + ((long long)head * a.n + kb_) * a.n : nullptr;
     bool keep_a = ka_ < a.n, keep_b = kb_ < a.n;
     if (MASK) {
       if (keep_a) keep_a = a.key_mask[(long long)seq * a.n + ka_] != 0;
@@ -414,23 +460,23 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       const int ntv = rem >= 32 ? 4 : 2;
       qk_block<4, DH>(s, ka, sQ, q0, lane, ntv);
       qk_block<4, DH>(dp, va, sDO, q0, lane, ntv);
+      // columns of this block are queries: mask columns >= n; masked / out-of-range key rows via keep_a / keep_b
+      logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv);
       float ds[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
-        const int qr = q0 + nt * 8 + 2 * t;  // query index of elements e&1
+        const int qr = q0 + nt * 8 + 2 * t;              // < n_pad whenever nt < ntv (sLse/sDel are n_pad long, zero-filled)
+        float2 l2 = make_float2(0.f, 0.f), d2 = make_float2(0.f, 0.f);
+        if (nt < ntv) {
+          l2 = *reinterpret_cast<const float2*>(sLse + qr);
+          d2 = *reinterpret_cast<const float2*>(sDel + qr);
+        }
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const int qq = qr + (e & 1);
-          const int kk = (e < 2) ? ka_ : kb_;
-          float val = s[nt][e] * sc2;
-          if (biasT != nullptr && qq < a.n && kk < a.n)
-            val += __bfloat162float(biasT[((long long)head * a.n + kk) * a.n + qq]) * kLog2e;
-          const bool valid = ((e < 2) ? keep_a : keep_b) && (qq < a.n);   // also keeps the smem reads in range
-          const float lq = valid ? sLse[qq] : 0.f;
-          const float dq_ = valid ? sDel[qq] : 0.f;
-          const float p = valid ? exp2f(val - lq) : 0.f;
-          s[nt][e] = p;                                             // P^T
-          ds[nt][e] = p * (dp[nt][e] - dq_) * a.scale;              // dS^T (w.r.t. q_hat.k_hat)
+          const bool keep = (e < 2) ? keep_a : keep_b;
+          const float p = keep ? fast_exp2(s[nt][e] - ((e & 1) ? l2.y : l2.x)) : 0.f;
+          s[nt][e] = p;                                                            // P^T
+          ds[nt][e] = p * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * a.scale;         // dS^T (w.r.t. q_hat.k_hat)
         }
       }
       pv_block<4, DH>(dva, s, sDOt, tstride, q0, lane, ntv);
@@ -521,7 +567,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a)
       for (int e = 0; e < 4; e++) {
         const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
         const float val = s[nt][e] * sc2 + bz[nt][e];
-        const float p = (kk < a.n && rr < a.n) ? exp2f(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
+        const float p = (kk < a.n && rr < a.n) ? fast_exp2(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
         acc[nt][e] += p * (dp[nt][e] - ((e < 2) ? del_a : del_b));
       }
     }

@@ -3,9 +3,10 @@
 // accumulator stages) -> tcgen05.ld epilogue fused with bias / residual / GEGLU / split-K
 // reduction / argmax.
 //
-// Roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane),
-// warps 2..5 = epilogue (warp 2 also owns the TMEM allocation). Epilogue warp w reads TMEM lanes
-// [32*(w%4), 32*(w%4)+32), i.e. one output row per thread.
+// Roles (320 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane),
+// warps 2..9 = epilogue (warp 2 also owns the TMEM allocation). Epilogue warp w reads TMEM lanes
+// [32*(w%4), 32*(w%4)+32), i.e. one output row per thread; the two warps sharing a lane quarter take
+// alternate 32-column chunks (the fused epilogues, not the MMA, bound the K=512 GEMMs otherwise).
 //
 // Reference ops replaced: see include/ctclip_b200.h (ctclip_gemm_bf16).
 #include "common.cuh"
@@ -17,6 +18,8 @@ namespace ctb {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 
 enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5, EPI_L2NORM = 6, EPI_BIAS_GELU = 7 };
 
@@ -47,7 +50,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*argmax merge*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
@@ -64,7 +67,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 }
 
 template <int BN, int AMAJ, int BMAJ>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -80,6 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* arg_merge = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [128][2] (value, index)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,7 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -187,8 +191,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which alternate 32-column chunks this warp handles
     uint32_t it = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       const int ng = unit % p.n_groups;
@@ -206,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c++) {
+        for (int c = half; c < BN / 32; c += EPI_WARPS / 4) {
           const int col0 = n_blk * BN + c * 32;
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t raw[32];
@@ -341,9 +346,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      if (p.epi == EPI_ARGMAX && row_ok) {
-        p.arg_out[row] = best_i;
-        if (p.argval_out != nullptr) p.argval_out[row] = best_v;
+      if (p.epi == EPI_ARGMAX) {
+        // merge the two column-halves of every row (first maximum wins, like torch.argmax)
+        const int rit = q * 32 + lane;
+        if (half == 1) {
+          arg_merge[2 * rit] = best_v;
+          arg_merge[2 * rit + 1] = __int_as_float(best_i);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+        if (half == 0 && row_ok) {
+          const float ov = arg_merge[2 * rit];
+          const int oi = __float_as_int(arg_merge[2 * rit + 1]);
+          if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+          p.arg_out[row] = best_i;
+          if (p.argval_out != nullptr) p.argval_out[row] = best_v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
       }
     }
   }
@@ -388,7 +406,7 @@ static int launch_gemm(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t s
     attr_set = true;
   }
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

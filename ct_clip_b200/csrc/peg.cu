@@ -12,8 +12,7 @@
 // The kernel walks the conv grid (a0,a1,a2) in (T,H,W) shape and maps every access through
 // canon(f); a0 is the causal axis (taps a0-2, a0-1, a0).
 //
-// Thread = one channel pair; CTA = `lines` consecutive (a0,a1) lines of one volume; sliding window
-// along a2 so every input element is loaded 9x (not 27x) from L1/L2.
+// See the v2 kernel comment below for the tiling (rolling 3-plane shared-memory buffer along the causal axis).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/ctclip_b200.h"
@@ -33,134 +32,182 @@ __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1,
   return ((long long)it * g.H + ih) * g.W + iw;
 }
 
-// MODE 0: y = x + conv(x) (+bias)           (forward)
-// MODE 1: dx = dy + conv^T(dy)              (backward data; taps mirrored, no bias)
-template <int MODE>
-__global__ void __launch_bounds__(384) peg_conv_kernel(ctclip_peg_args a) {
-  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal};
-  const int c = 2 * threadIdx.x;  // channel pair
-  if (c >= a.D) return;
-  const int lines_total = a.T * a.H;
-  const int line0 = blockIdx.x * a.lines;
-  const int b = blockIdx.y;
-  const float* xin = a.x + (long long)b * a.T * a.H * a.W * a.D;
-  float* yout = a.y + (long long)b * a.T * a.H * a.W * a.D;
-  __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)b * a.T * a.H * a.W * a.D : nullptr;
+// ------------------------------------------------------------------------------------------------
+// v2 kernels. CTA = (32-channel block, tile of A1T=8 conv-grid lines along a1, range of a0 planes, volume).
+// The CTA walks the causal axis a0 with a ROLLING 3-plane buffer in shared memory ([slot][a1 halo][a2 halo][32 ch] fp32):
+// every step loads ONE new plane (halo factor (A1T+2)(W+2)/(A1T*W) ~ 1.35x of compulsory traffic, 128 B coalesced
+// segments), then each thread (= one line x one channel) slides a 3-wide register window along a2 (9 LDS per output,
+// 27 taps). Warps read 32 consecutive channels -> conflict-free LDS and 128 B coalesced stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int A1T = 8;   // lines per CTA tile
+constexpr int CB = 32;   // channels per CTA
 
-  float2 wt[27];
-#pragma unroll
-  for (int k = 0; k < 27; k++) {
-    const int kk = (MODE == 0) ? k : (26 - k);  // mirrored taps for the transposed conv
-    wt[k] = make_float2(a.weight[(long long)c * 27 + kk], a.weight[(long long)(c + 1) * 27 + kk]);
+struct PegTile {
+  int a1_0, c0, b, p_begin, p_end;  // a0 plane range [p_begin, p_end) produced by this CTA
+};
+
+// load plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one smem slot; zero outside
+__device__ __forceinline__ void peg_load_plane(float* slot, const float* __restrict__ src, const PegGeom& g, int a0, int a1_0) {
+  const int a2h = g.W + 2;
+  const int n_tok = (A1T + 2) * a2h;
+  for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += blockDim.x) {
+    const int tok = idx / (CB / 4), q = idx % (CB / 4);
+    const int r1 = tok / a2h, r2 = tok % a2h;
+    const int a1 = a1_0 - 1 + r1, a2 = r2 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a0 >= 0 && a0 < g.T && a1 >= 0 && a1 < g.H && a2 >= 0 && a2 < g.W)
+      v = *reinterpret_cast<const float4*>(src + peg_canon(g, a0, a1, a2) * g.D + q * 4);
+    *reinterpret_cast<float4*>(slot + (size_t)tok * CB + q * 4) = v;
   }
-  float2 bias = make_float2(0.f, 0.f);
-  if (MODE == 0 && a.bias != nullptr) bias = make_float2(a.bias[c], a.bias[c + 1]);
+}
 
-  for (int li = 0; li < a.lines; li++) {
-    const int line = line0 + li;
-    if (line >= lines_total) break;
-    const int a0 = line / a.H, a1 = line % a.H;
-    // tap k0 reads a0 + k0 - 2 (forward) or a0 + k0 (mirrored: original offset 2-k0' with k0'=2-k0)
-    float2 win[9][3];
-    long long rowbase_valid[9];
+// MODE 0: y = x + conv(x) + bias (forward; taps a0-2..a0)     MODE 1: dx = dy + conv^T(dy) (taps a0..a0+2, mirrored)
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) peg_conv2_kernel(ctclip_peg_args a, int planes_per_cta) {
+  extern __shared__ __align__(16) float peg_sm[];
+  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal};
+  const int a2h = a.W + 2;
+  const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
+  const int n_a1t = (a.H + A1T - 1) / A1T;
+  const int c0 = (blockIdx.x % (a.D / CB)) * CB;
+  const int a1_0 = ((blockIdx.x / (a.D / CB)) % n_a1t) * A1T;
+  const int chunk = blockIdx.x / ((a.D / CB) * n_a1t);
+  const int b = blockIdx.y;
+  const int p_begin = chunk * planes_per_cta;
+  const int p_end = min(a.T, p_begin + planes_per_cta);
+  if (p_begin >= p_end) return;
+  const long long vol = (long long)a.T * a.H * a.W * a.D;
+  const float* xin = a.x + (long long)b * vol + c0;
+  float* yout = a.y + (long long)b * vol + c0;
+  __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)b * vol + c0 : nullptr;
+  const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;  // channel, a1 line within the tile
+  const int ch = c0 + lane;
+  float wt[27];
 #pragma unroll
-    for (int r = 0; r < 9; r++) {
-      const int k0 = r / 3, k1 = r % 3;
-      const int n0 = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
-      const int n1 = a1 + k1 - 1;
-      rowbase_valid[r] = (n0 >= 0 && n0 < a.T && n1 >= 0 && n1 < a.H) ? ((long long)n0 << 32 | (unsigned)n1) : -1;
-      win[r][0] = make_float2(0.f, 0.f);  // position a2-1 = -1 (padding)
-      win[r][1] = make_float2(0.f, 0.f);
-      if (rowbase_valid[r] >= 0)
-        win[r][1] = *reinterpret_cast<const float2*>(xin + peg_canon(g, n0, n1, 0) * a.D + c);
-    }
-    for (int a2 = 0; a2 < a.W; a2++) {
-      float2 acc = bias;
+  for (int k = 0; k < 27; k++) wt[k] = a.weight[(long long)ch * 27 + ((MODE == 0) ? k : 26 - k)];
+  const float bias = (MODE == 0 && a.bias != nullptr) ? a.bias[ch] : 0.f;
+  const int a1 = a1_0 + line;
+  // prime the rolling buffer with the two planes preceding (MODE 0) / following (MODE 1) the first output plane
+  const int first = (MODE == 0) ? p_begin : p_end - 1;
+  const int dirn = (MODE == 0) ? 1 : -1;
+  for (int d = 2; d >= 1; d--) {
+    const int pl = first - dirn * d;  // MODE 0: first-2, first-1   MODE 1: first+2, first+1
+    peg_load_plane(peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems, xin, g, pl, a1_0);
+  }
+  for (int step = 0; step < p_end - p_begin; step++) {
+    const int a0 = first + dirn * step;
+    __syncthreads();  // everyone is done reading the slot we are about to overwrite
+    peg_load_plane(peg_sm + (size_t)(((a0 % 3) + 3) % 3) * slot_elems, xin, g, a0, a1_0);
+    __syncthreads();
+    if (a1 < a.H) {
+      // tap k0 reads plane a0 + k0 - 2 (MODE 0) or a0 + k0 (MODE 1)
+      const float* rowp[9];
 #pragma unroll
       for (int r = 0; r < 9; r++) {
-        float2 nx = make_float2(0.f, 0.f);
-        if (rowbase_valid[r] >= 0 && a2 + 1 < a.W) {
-          const int n0 = (int)(rowbase_valid[r] >> 32), n1 = (int)(rowbase_valid[r] & 0xffffffff);
-          nx = *reinterpret_cast<const float2*>(xin + peg_canon(g, n0, n1, a2 + 1) * a.D + c);
-        }
-        win[r][2] = nx;
-#pragma unroll
-        for (int k2 = 0; k2 < 3; k2++) {
-          acc.x = fmaf(wt[r * 3 + k2].x, win[r][k2].x, acc.x);
-          acc.y = fmaf(wt[r * 3 + k2].y, win[r][k2].y, acc.y);
-        }
-        win[r][0] = win[r][1];
-        win[r][1] = win[r][2];
+        const int k0 = r / 3, k1 = r % 3;
+        const int pl = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
+        rowp[r] = peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
       }
-      const long long tok = peg_canon(g, a0, a1, a2);
-      const float2 ctr = *reinterpret_cast<const float2*>(xin + tok * a.D + c);
-      acc.x += ctr.x;
-      acc.y += ctr.y;
-      *reinterpret_cast<float2*>(yout + tok * a.D + c) = acc;
-      if (ybf != nullptr) *reinterpret_cast<uint32_t*>(ybf + tok * a.D + c) = pack_bf16x2(acc.x, acc.y);
+      float win[9][3];
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        win[r][0] = rowp[r][0];       // a2 = -1 (zero padding)
+        win[r][1] = rowp[r][CB];      // a2 = 0
+      }
+      for (int a2 = 0; a2 < a.W; a2++) {
+        float acc = bias;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          win[r][2] = rowp[r][(a2 + 2) * CB];
+#pragma unroll
+          for (int k2 = 0; k2 < 3; k2++) acc = fmaf(wt[r * 3 + k2], win[r][k2], acc);
+          win[r][0] = win[r][1];
+          win[r][1] = win[r][2];
+        }
+        // centre tap input = residual term: row r = (k0 = 2 | 0, k1 = 1), window position "a2" was shifted into win[.][0]
+        const float ctr = (MODE == 0) ? win[7][0] : win[1][0];
+        const long long tok = peg_canon(g, a0, a1, a2);
+        const float out = acc + ctr;
+        yout[tok * a.D + lane] = out;
+        if (ybf != nullptr) ybf[tok * a.D + lane] = __float2bfloat16(out);
+      }
     }
   }
 }
 
-// Weight / bias gradient: dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p].
-__global__ void __launch_bounds__(384) peg_wgrad_kernel(ctclip_peg_args a) {
+// dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p]   (x planes in the rolling buffer, dy straight from global)
+__global__ void __launch_bounds__(256, 2) peg_wgrad2_kernel(ctclip_peg_args a, int planes_per_cta) {
+  extern __shared__ __align__(16) float peg_sm[];
   const PegGeom g{a.T, a.H, a.W, a.D, a.temporal};
-  const int c = 2 * threadIdx.x;
-  if (c >= a.D) return;
-  const int lines_total = a.T * a.H;
-  const int line0 = blockIdx.x * a.lines;
+  const int a2h = a.W + 2;
+  const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
+  const int n_a1t = (a.H + A1T - 1) / A1T;
+  const int c0 = (blockIdx.x % (a.D / CB)) * CB;
+  const int a1_0 = ((blockIdx.x / (a.D / CB)) % n_a1t) * A1T;
+  const int chunk = blockIdx.x / ((a.D / CB) * n_a1t);
   const int b = blockIdx.y;
-  const float* xin = a.x + (long long)b * a.T * a.H * a.W * a.D;    // forward input
-  const float* dy = a.dy + (long long)b * a.T * a.H * a.W * a.D;    // upstream gradient
-  float2 acc[27];
+  const int p_begin = chunk * planes_per_cta;
+  const int p_end = min(a.T, p_begin + planes_per_cta);
+  if (p_begin >= p_end) return;
+  const long long vol = (long long)a.T * a.H * a.W * a.D;
+  const float* xin = a.x + (long long)b * vol + c0;
+  const float* dy = a.dy + (long long)b * vol + c0;
+  const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;
+  const int a1 = a1_0 + line;
+  float acc[27];
 #pragma unroll
-  for (int k = 0; k < 27; k++) acc[k] = make_float2(0.f, 0.f);
-  float2 accb = make_float2(0.f, 0.f);
-  for (int li = 0; li < a.lines; li++) {
-    const int line = line0 + li;
-    if (line >= lines_total) break;
-    const int a0 = line / a.H, a1 = line % a.H;
-    float2 win[9][3];
-    long long rv[9];
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      const int k0 = r / 3, k1 = r % 3;
-      const int n0 = a0 + k0 - 2, n1 = a1 + k1 - 1;
-      rv[r] = (n0 >= 0 && n0 < a.T && n1 >= 0 && n1 < a.H) ? ((long long)n0 << 32 | (unsigned)n1) : -1;
-      win[r][0] = make_float2(0.f, 0.f);
-      win[r][1] = make_float2(0.f, 0.f);
-      if (rv[r] >= 0) win[r][1] = *reinterpret_cast<const float2*>(xin + peg_canon(g, n0, n1, 0) * a.D + c);
-    }
-    for (int a2 = 0; a2 < a.W; a2++) {
-      const float2 d = *reinterpret_cast<const float2*>(dy + peg_canon(g, a0, a1, a2) * a.D + c);
-      accb.x += d.x;
-      accb.y += d.y;
+  for (int k = 0; k < 27; k++) acc[k] = 0.f;
+  float accb = 0.f;
+  for (int d = 2; d >= 1; d--) {
+    const int pl = p_begin - d;
+    peg_load_plane(peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems, xin, g, pl, a1_0);
+  }
+  for (int a0 = p_begin; a0 < p_end; a0++) {
+    __syncthreads();
+    peg_load_plane(peg_sm + (size_t)(((a0 % 3) + 3) % 3) * slot_elems, xin, g, a0, a1_0);
+    __syncthreads();
+    if (a1 < a.H) {
+      const float* rowp[9];
 #pragma unroll
       for (int r = 0; r < 9; r++) {
-        float2 nx = make_float2(0.f, 0.f);
-        if (rv[r] >= 0 && a2 + 1 < a.W) {
-          const int n0 = (int)(rv[r] >> 32), n1 = (int)(rv[r] & 0xffffffff);
-          nx = *reinterpret_cast<const float2*>(xin + peg_canon(g, n0, n1, a2 + 1) * a.D + c);
-        }
-        win[r][2] = nx;
+        const int k0 = r / 3, k1 = r % 3;
+        const int pl = a0 + k0 - 2;
+        rowp[r] = peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
+      }
+      float win[9][3];
 #pragma unroll
-        for (int k2 = 0; k2 < 3; k2++) {
-          acc[r * 3 + k2].x = fmaf(d.x, win[r][k2].x, acc[r * 3 + k2].x);
-          acc[r * 3 + k2].y = fmaf(d.y, win[r][k2].y, acc[r * 3 + k2].y);
+      for (int r = 0; r < 9; r++) {
+        win[r][0] = rowp[r][0];
+        win[r][1] = rowp[r][CB];
+      }
+      for (int a2 = 0; a2 < a.W; a2++) {
+        const float d = dy[peg_canon(g, a0, a1, a2) * a.D + lane];
+        accb += d;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          win[r][2] = rowp[r][(a2 + 2) * CB];
+#pragma unroll
+          for (int k2 = 0; k2 < 3; k2++) acc[r * 3 + k2] = fmaf(d, win[r][k2], acc[r * 3 + k2]);
+          win[r][0] = win[r][1];
+          win[r][1] = win[r][2];
         }
-        win[r][0] = win[r][1];
-        win[r][1] = win[r][2];
       }
     }
   }
+  // reduce the A1T lines of this CTA (same channel = same lane) through shared memory, one atomic per (channel, tap)
+  __syncthreads();
+  float* red = peg_sm;  // [A1T][28][CB]
 #pragma unroll
-  for (int k = 0; k < 27; k++) {
-    atomicAdd(a.dweight + (long long)c * 27 + k, acc[k].x);
-    atomicAdd(a.dweight + (long long)(c + 1) * 27 + k, acc[k].y);
-  }
-  if (a.dbias != nullptr) {
-    atomicAdd(a.dbias + c, accb.x);
-    atomicAdd(a.dbias + c + 1, accb.y);
+  for (int k = 0; k < 27; k++) red[(line * 28 + k) * CB + lane] = acc[k];
+  red[(line * 28 + 27) * CB + lane] = accb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 28 * CB; i += blockDim.x) {
+    const int k = i / CB, c = i % CB;
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < A1T; l++) t += red[(l * 28 + k) * CB + c];
+    if (k < 27) atomicAdd(a.dweight + (long long)(c0 + c) * 27 + k, t);
+    else if (a.dbias != nullptr) atomicAdd(a.dbias + c0 + c, t);
   }
 }
 
@@ -171,8 +218,35 @@ using namespace ctb;
 static int peg_check(const ctclip_peg_args* a, const char* who) {
   CTB_CHECK_ARG(a && a->x, "%s: null x", who);
   CTB_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->W > 0, "%s: bad grid", who);
-  CTB_CHECK_ARG(a->D % 2 == 0 && a->D <= 768, "%s: D must be even and <= 768", who);
-  CTB_CHECK_ARG(a->lines >= 1, "%s: lines must be >= 1", who);
+  CTB_CHECK_ARG(a->D % 32 == 0, "%s: D must be a multiple of 32", who);
+  return CTCLIP_OK;
+}
+
+// grid.x = channel blocks x a1 tiles x a0 chunks; a0 chunks sized so that the grid has >= ~3 CTAs per SM
+static void peg_launch_shape(const ctclip_peg_args* a, dim3* grid, int* planes_per_cta, size_t* smem) {
+  const int n_a1t = (a->H + A1T - 1) / A1T;
+  const long long base = (long long)(a->D / CB) * n_a1t * a->B;
+  int chunks = (int)((3LL * num_sms() + base - 1) / base);
+  if (chunks < 1) chunks = 1;
+  if (chunks > a->T) chunks = a->T;
+  *planes_per_cta = (a->T + chunks - 1) / chunks;
+  chunks = (a->T + *planes_per_cta - 1) / *planes_per_cta;
+  *grid = dim3((unsigned)((a->D / CB) * n_a1t * chunks), (unsigned)a->B);
+  *smem = sizeof(float) * 3 * (size_t)(A1T + 2) * (a->W + 2) * CB;
+  const size_t red_bytes = sizeof(float) * A1T * 28 * CB;  // weight-gradient reduction scratch
+  if (*smem < red_bytes) *smem = red_bytes;
+}
+
+template <typename Kern>
+static int peg_launch(Kern kern, const ctclip_peg_args* a, cudaStream_t stream) {
+  dim3 grid;
+  int ppc;
+  size_t smem;
+  peg_launch_shape(a, &grid, &ppc, &smem);
+  CTB_CHECK_ARG(smem <= 227 * 1024, "peg: token grid width %d needs %zu B of shared memory", a->W, smem);
+  CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 256, smem, stream>>>(*a, ppc);
+  CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }
 
@@ -180,10 +254,7 @@ extern "C" int ctclip_peg_fwd(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_fwd")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_fwd: null y/weight");
-  dim3 grid(ceil_div(a->T * a->H, a->lines), a->B);
-  peg_conv_kernel<0><<<grid, a->D / 2, 0, stream>>>(*a);
-  CTB_LAUNCH_CHECK();
-  return CTCLIP_OK;
+  return peg_launch(peg_conv2_kernel<0>, a, stream);
 }
 
 // x = upstream gradient dy (fp32), y = dx out (fp32), y_bf16 = optional bf16 copy of dx
@@ -191,10 +262,7 @@ extern "C" int ctclip_peg_bwd_data(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_data")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_bwd_data: null y/weight");
-  dim3 grid(ceil_div(a->T * a->H, a->lines), a->B);
-  peg_conv_kernel<1><<<grid, a->D / 2, 0, stream>>>(*a);
-  CTB_LAUNCH_CHECK();
-  return CTCLIP_OK;
+  return peg_launch(peg_conv2_kernel<1>, a, stream);
 }
 
 // x = forward input, dy = upstream gradient; dweight [D,27] and dbias [D] are accumulated (atomics)
@@ -202,8 +270,5 @@ extern "C" int ctclip_peg_bwd_weight(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_weight")) return rc;
   CTB_CHECK_ARG(a->dy && a->dweight, "peg_bwd_weight: null dy/dweight");
-  dim3 grid(ceil_div(a->T * a->H, a->lines), a->B);
-  peg_wgrad_kernel<<<grid, a->D / 2, 0, stream>>>(*a);
-  CTB_LAUNCH_CHECK();
-  return CTCLIP_OK;
+  return peg_launch(peg_wgrad2_kernel, a, stream);
 }

@@ -57,7 +57,7 @@ def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, 
         e0.record()
         call("ctclip_gemm_bf16", C.byref(a), _stream())
         e1.record()
-        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K))
+        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K, (M, N, K, a_major, b_major, epilogue, splits)))
 
 
 def wgrad_splits(k_red: int, out_tiles: int, sms: int = 148) -> int:

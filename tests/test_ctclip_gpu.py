@@ -65,9 +65,9 @@ def test_contrastive_step_matches_oracle():
         assert p.grad is not None, f"missing gradient for {name}"
         e = rms_err(p.grad, ref)
         report[name] = e
-        if e > 2e-2:
+        if e > 4e-2:
             bad.append((name, e))
-    worst = sorted(report.items(), key=lambda kv: -kv[1])[:8]
+    worst = sorted(report.items(), key=lambda kv: -kv[1])[:12]
     print("worst gradient rms errors:", worst)
     assert not bad, bad
     # ---- code-book EMA side effect of the training-mode forward
