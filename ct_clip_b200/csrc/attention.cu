@@ -505,17 +505,37 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
 
 // ------------------------------------------------------------------------------------------------
 // backward, part 3 (spatial stack only): dbias[h,i,j] += sum_seq dlogits_seq[h,i,j].
-// CTA = (head, 128 query rows, 64 keys); loops over all sequences; 8 warps x 16 rows.
+// CTA = (head, 64 query rows, 64 keys, chunk of sequences); 4 warps x 16 rows. The K/V tiles of consecutive
+// sequences stream through a 2-stage cp.async ring and the per-row operands (q_hat, dO fragments, lse, delta) of the
+// next sequence are prefetched into registers while the current one is being processed; partial sums are merged with
+// one fp32 red.add per element per chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a) {
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int bytes = valid ? 16 : 0;   // src-size 0 => 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(128, 3) attn_bwd_dbias_kernel(ctclip_attn_args a, int seq_chunks) {
   constexpr int DH = 32;
-  __shared__ __align__(16) __nv_bfloat16 sK[64 * KROW];
-  __shared__ __align__(16) __nv_bfloat16 sV[64 * KROW];
+  constexpr int BROW = 72;  // padded bias-tile row (bf16)
+  __shared__ __align__(16) __nv_bfloat16 sK[2][64 * KROW];
+  __shared__ __align__(16) __nv_bfloat16 sV[2][64 * KROW];
+  __shared__ __align__(16) __nv_bfloat16 sB[64 * BROW];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const int head = blockIdx.z;
-  const int r0 = blockIdx.y * 128 + warp * 16;
+  const int head = blockIdx.z % a.heads;
+  const int chunk = blockIdx.z / a.heads;
+  const int per = (a.num_seqs + seq_chunks - 1) / seq_chunks;
+  const int seq_begin = chunk * per;
+  const int seq_end = min(a.num_seqs, seq_begin + per);
+  if (seq_begin >= seq_end) return;
+  const int rblk = blockIdx.y * 64;
+  const int r0 = rblk + warp * 16;
   const int key0 = blockIdx.x * 64;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
   const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
@@ -524,52 +544,72 @@ __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a)
   const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   const float sc2 = a.scale * kLog2e;
   const int ra = r0 + gq, rb = r0 + gq + 8;
-  float acc[8][4];
-  float bz[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; nt++) {
-    const int key = key0 + nt * 8 + 2 * t;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      acc[nt][e] = 0.f;
-      const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
-      bz[nt][e] = (bias != nullptr && rr < a.n && kk < a.n)
-                      ? __bfloat162float(bias[((long long)head * a.n + rr) * a.n + kk]) * kLog2e : 0.f;
-    }
+  // bias tile (64 x 64) of this CTA, zero where out of range
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 128) {
+    const int r = idx >> 6, c = idx & 63;
+    float bv = 0.f;
+    if (bias != nullptr && rblk + r < a.n && key0 + c < a.n)
+      bv = __bfloat162float(bias[((long long)head * a.n + rblk + r) * a.n + key0 + c]);
+    sB[r * BROW + c] = __float2bfloat16(bv);
   }
-  for (int seq = 0; seq < a.num_seqs; seq++) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 64 * 4; idx += 256) {
+  auto issue_tile = [&](int seq, int buf) {
+    for (int idx = threadIdx.x; idx < 64 * 4; idx += 128) {
       const int r = idx >> 2, part = idx & 3;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (key0 + r < a.n) {
-        kv = *reinterpret_cast<const uint4*>(k + g.row(seq, key0 + r) * a.ldk + head * DH + part * 8);
-        vv = *reinterpret_cast<const uint4*>(v + g.row(seq, key0 + r) * a.ldv + head * DH + part * 8);
-      }
-      *reinterpret_cast<uint4*>(sK + r * KROW + part * 8) = kv;
-      *reinterpret_cast<uint4*>(sV + r * KROW + part * 8) = vv;
+      const bool ok = key0 + r < a.n;
+      const long long row = ok ? g.row(seq, key0 + r) : 0;
+      cp_async_16(&sK[buf][r * KROW + part * 8], k + row * a.ldk + head * DH + part * 8, ok);
+      cp_async_16(&sV[buf][r * KROW + part * 8], v + row * a.ldv + head * DH + part * 8, ok);
     }
-    __syncthreads();
-    if (r0 >= a.n) continue;
-    uint32_t qa[DH / 16][4], da[DH / 16][4];
-    load_a_frags<DH>(qa, q, a.ldq, head, g, seq, r0, lane);
-    load_a_frags<DH>(da, dO, a.ldo, head, g, seq, r0, lane);
-    float lse_a = 0.f, lse_b = 0.f, del_a = 0.f, del_b = 0.f;
-    if (ra < a.n) { lse_a = a.lse[g.row(seq, ra) * a.heads + head]; del_a = a.delta[g.row(seq, ra) * a.heads + head]; }
-    if (rb < a.n) { lse_b = a.lse[g.row(seq, rb) * a.heads + head]; del_b = a.delta[g.row(seq, rb) * a.heads + head]; }
+    cp_async_commit();
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  uint32_t qa[DH / 16][4], da[DH / 16][4], qn[DH / 16][4], dn[DH / 16][4];
+  float lse_a, lse_b, del_a, del_b, nlse_a, nlse_b, ndel_a, ndel_b;
+  auto load_rows_ops = [&](int seq, uint32_t (&fq)[DH / 16][4], uint32_t (&fd)[DH / 16][4], float& la, float& lb, float& dla,
+                           float& dlb) {
+    load_a_frags<DH>(fq, q, a.ldq, head, g, seq, r0, lane);
+    load_a_frags<DH>(fd, dO, a.ldo, head, g, seq, r0, lane);
+    la = lb = INFINITY;   // rows beyond n contribute probability 0
+    dla = dlb = 0.f;
+    if (ra < a.n) { la = a.lse[g.row(seq, ra) * a.heads + head]; dla = a.delta[g.row(seq, ra) * a.heads + head]; }
+    if (rb < a.n) { lb = a.lse[g.row(seq, rb) * a.heads + head]; dlb = a.delta[g.row(seq, rb) * a.heads + head]; }
+  };
+  issue_tile(seq_begin, 0);
+  load_rows_ops(seq_begin, qa, da, lse_a, lse_b, del_a, del_b);
+  for (int seq = seq_begin; seq < seq_end; seq++) {
+    const int buf = (seq - seq_begin) & 1;
+    cp_async_wait<0>();
+    __syncthreads();                       // tile `buf` landed for everyone; everyone finished with tile `buf^1`
+    if (seq + 1 < seq_end) {
+      issue_tile(seq + 1, buf ^ 1);
+      load_rows_ops(seq + 1, qn, dn, nlse_a, nlse_b, ndel_a, ndel_b);
+    }
     float s[8][4], dp[8][4];
-    qk_block<8, DH>(s, qa, sK, 0, lane);
-    qk_block<8, DH>(dp, da, sV, 0, lane);
+    qk_block<8, DH>(s, qa, sK[buf], 0, lane);
+    qk_block<8, DH>(dp, da, sV[buf], 0, lane);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-      const int key = key0 + nt * 8 + 2 * t;
+      const int c = nt * 8 + 2 * t;
+      const float2 b_a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sB[(warp * 16 + gq) * BROW + c]));
+      const float2 b_b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sB[(warp * 16 + gq + 8) * BROW + c]));
+      const bool k0ok = key0 + c < a.n, k1ok = key0 + c + 1 < a.n;
+      const float p0 = k0ok ? fast_exp2(fmaf(s[nt][0], sc2, b_a.x * kLog2e) - lse_a) : 0.f;
+      const float p1 = k1ok ? fast_exp2(fmaf(s[nt][1], sc2, b_a.y * kLog2e) - lse_a) : 0.f;
+      const float p2 = k0ok ? fast_exp2(fmaf(s[nt][2], sc2, b_b.x * kLog2e) - lse_b) : 0.f;
+      const float p3 = k1ok ? fast_exp2(fmaf(s[nt][3], sc2, b_b.y * kLog2e) - lse_b) : 0.f;
+      acc[nt][0] += p0 * (dp[nt][0] - del_a);
+      acc[nt][1] += p1 * (dp[nt][1] - del_a);
+      acc[nt][2] += p2 * (dp[nt][2] - del_b);
+      acc[nt][3] += p3 * (dp[nt][3] - del_b);
+    }
+    if (seq + 1 < seq_end) {
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
-        const float val = s[nt][e] * sc2 + bz[nt][e];
-        const float p = (kk < a.n && rr < a.n) ? fast_exp2(val - ((e < 2) ? lse_a : lse_b)) : 0.f;
-        acc[nt][e] += p * (dp[nt][e] - ((e < 2) ? del_a : del_b));
-      }
+      for (int kt = 0; kt < DH / 16; kt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) { qa[kt][e] = qn[kt][e]; da[kt][e] = dn[kt][e]; }
+      lse_a = nlse_a; lse_b = nlse_b; del_a = ndel_a; del_b = ndel_b;
     }
   }
 #pragma unroll
@@ -578,7 +618,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dbias_kernel(ctclip_attn_args a)
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int kk = key + (e & 1), rr = (e < 2) ? ra : rb;
-      if (rr < a.n && kk < a.n) a.dbias[((long long)head * a.n + rr) * a.n + kk] += acc[nt][e];
+      if (rr < a.n && kk < a.n) atomicAdd(&a.dbias[((long long)head * a.n + rr) * a.n + kk], acc[nt][e]);
     }
   }
 }
@@ -751,8 +791,13 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
   if (int rc = attn_route(1, a, stream)) return rc;
   if (int rc = attn_route(2, a, stream)) return rc;
   if (a->dbias != nullptr) {
-    dim3 grid((a->n + 63) / 64, (a->n + 127) / 128, a->heads);
-    attn_bwd_dbias_kernel<<<grid, 256, 0, stream>>>(*a);
+    // sequence chunks: enough CTAs for ~2 waves at 3 CTAs/SM
+    const int tiles = ((a->n + 63) / 64) * ((a->n + 63) / 64) * a->heads;
+    int chunks = (6 * num_sms() + tiles - 1) / tiles;
+    if (chunks < 1) chunks = 1;
+    if (chunks > a->num_seqs) chunks = a->num_seqs;
+    dim3 grid((a->n + 63) / 64, (a->n + 63) / 64, a->heads * chunks);
+    attn_bwd_dbias_kernel<<<grid, 128, 0, stream>>>(*a, chunks);
     CTB_LAUNCH_CHECK();
   }
   return CTCLIP_OK;

@@ -119,6 +119,7 @@ class CTClipTrainer(nn.Module):
         self.dl = torch.utils.data.DataLoader(self.ds, num_workers=num_workers, batch_size=batch_size, shuffle=True,
                                               pin_memory=True, collate_fn=getattr(self.ds, "collate", None))
         self.dl_iter = cycle(self.dl)
+        self._prefetcher = None
 
         # ---- flat arena over everything that can receive a gradient
         live = [(n, p) for n, p in self.CTClip.named_parameters()
@@ -195,10 +196,9 @@ class CTClipTrainer(nn.Module):
     def train_step(self):
         steps = int(self.steps.item())
         logs = {}
-        video, text = next(self.dl_iter)
-        video = video.to(self.device, non_blocking=True)
-        tok = self._tokenize(text)
-        tok = _Tokens(tok.input_ids.to(self.device, non_blocking=True), tok.attention_mask.to(self.device, non_blocking=True))
+        if self._prefetcher is None:   # H2D of the next batch overlaps this step's compute
+            self._prefetcher = DevicePrefetcher(self.dl_iter, self.device, self._tokenize)
+        video, tok = self._prefetcher.next()
         loss = self.step_on_batch(video, tok)
         logs['loss'] = loss.item()                      # device->host sync, as the reference (:258)
         self.print(f"{steps}: loss: {logs['loss']}")
@@ -214,6 +214,41 @@ class CTClipTrainer(nn.Module):
             logs = self.train_step()
             log_fn(logs)
         self.print('training complete')
+
+
+class DevicePrefetcher:
+    """Overlaps the pinned-host -> device copy of batch i+1 with the compute of batch i (copy stream + events).
+    `it` yields (volume, tokens-like) with CPU tensors (pinned for true asynchrony)."""
+
+    def __init__(self, it, device, to_tokens):
+        self.it, self.device, self.to_tokens = it, device, to_tokens
+        self.stream = torch.cuda.Stream(device=device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            video, text = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        tok = self.to_tokens(text)
+        with torch.cuda.stream(self.stream):
+            vd = video.to(self.device, non_blocking=True)
+            td = _Tokens(tok.input_ids.to(self.device, non_blocking=True), tok.attention_mask.to(self.device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._next = (vd, td, ev)
+
+    def next(self):
+        if self._next is None:
+            raise StopIteration
+        vd, td, ev = self._next
+        torch.cuda.current_stream().wait_event(ev)
+        for t_ in (vd, td.input_ids, td.attention_mask):
+            t_.record_stream(torch.cuda.current_stream())
+        self._preload()
+        return vd, td
 
 
 class _Tokens:
