@@ -51,7 +51,7 @@ class PatchifyArgs(C.Structure):
 class PegArgs(C.Structure):
     _fields_ = [("x", P), ("dy", P), ("y", P), ("y_bf16", P), ("weight", P), ("bias", P), ("dweight", P),
                 ("dbias", P), ("B", I32), ("T", I32), ("H", I32), ("W", I32), ("D", I32), ("temporal", I32),
-                ("lines", I32)]
+                ("lines", I32), ("canon_table", P)]
 
 
 class AttnArgs(C.Structure):
@@ -60,7 +60,8 @@ class AttnArgs(C.Structure):
                 ("n", I32), ("heads", I32), ("dim_head", I32), ("num_seqs", I32), ("seq_inner", I32),
                 ("seq_outer_stride", I64), ("tok_stride", I64), ("scale", F32),
                 ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
-                ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P)]
+                ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P),
+                ("bias_frag", P), ("bias_t_frag", P)]
 
 
 class SgemmArgs(C.Structure):
@@ -95,6 +96,7 @@ SIGNATURES = {
     "ctclip_cpb_inputs": [P, I32, I32, P],
     "ctclip_cpb_expand": [P, I32, I32, I32, P, P, P],
     "ctclip_cpb_reduce": [P, I32, I32, I32, P, P],
+    "ctclip_cpb_expand_frag": [P, I32, I32, I32, P, P, P],
     "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
     "ctclip_vq_gather": [P, P, P, I64, I32, P],

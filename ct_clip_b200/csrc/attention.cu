@@ -140,10 +140,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // One 16 x 8*NT block of raw dot products -> log2-domain logits  s*sc2 + bias*log2(e);  columns >= n, masked keys and
 // tiles >= nt_valid become -inf (=> probability 0). brow_a / brow_b: bias rows of the two fragment rows (nullptr: none).
+// bfrag (optional): this thread's NT*4 bias values in MMA-fragment order (bf16, 8 bytes per n-tile) -- the layout
+// ctclip_cpb_expand writes so that a warp reads its whole 16 x 64 bias block with four fully coalesced 16-byte loads
+// per lane (the natural [h,i,j] layout costs 16 loads per lane at 25 % sector efficiency).
 template <int NT, bool MASK>
 __device__ __forceinline__ void logits_tile(float (&s)[NT][4], float sc2, const __nv_bfloat16* brow_a,
                                             const __nv_bfloat16* brow_b, int c0, int t, int n, bool cols_full, bool pair_ok,
-                                            const int* sMask, int nt_valid) {
+                                            const int* sMask, int nt_valid, const uint2* bfrag = nullptr) {
+  uint2 bf[NT];
+  if (bfrag != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NT / 2; i++) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
+      bf[2 * i] = make_uint2(u.x, u.y);
+      bf[2 * i + 1] = make_uint2(u.z, u.w);
+    }
+  }
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) {
     if (nt >= nt_valid) {
@@ -153,7 +165,10 @@ __device__ __forceinline__ void logits_tile(float (&s)[NT][4], float sc2, const 
     const int c = c0 + nt * 8 + 2 * t;
     const bool ok0 = cols_full || c < n, ok1 = cols_full || c + 1 < n;
     float ba0 = 0.f, ba1 = 0.f, bb0 = 0.f, bb1 = 0.f;
-    if (brow_a != nullptr) {
+    if (bfrag != nullptr) {
+      const float2 fa = unpack_bf16x2(bf[nt].x), fb = unpack_bf16x2(bf[nt].y);
+      ba0 = fa.x; ba1 = fa.y; bb0 = fb.x; bb1 = fb.y;
+    } else if (brow_a != nullptr) {
       if (ok1 && pair_ok) {
         const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(brow_a + c));
         ba0 = f.x; ba1 = f.y;
@@ -162,7 +177,7 @@ __device__ __forceinline__ void logits_tile(float (&s)[NT][4], float sc2, const 
         if (ok1) ba1 = __bfloat162float(brow_a[c + 1]);
       }
     }
-    if (brow_b != nullptr) {
+    if (bfrag == nullptr && brow_b != nullptr) {
       if (ok1 && pair_ok) {
         const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(brow_b + c));
         bb0 = f.x; bb1 = f.y;
@@ -230,6 +245,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   if (!active) return;
   const float sc2 = a.scale * kLog2e;
   const int row_tiles = n_pad / 16;
+  const int kblocks = (n_pad + 63) / 64;
+  const uint2* bias_frag = reinterpret_cast<const uint2*>(a.bias_frag);
   for (int rt = wig; rt < row_tiles; rt += WPG) {
     const int r0 = rt * 16;
     uint32_t qa[DH / 16][4];
@@ -247,7 +264,9 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       const int rem = n_pad - key0;  // multiple of 16
       const int ntv = rem >= 64 ? 8 : rem / 8;
       qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
-      logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv);
+      const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8
+                                   : nullptr;
+      logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv, bfr);
       float bm_a = -INFINITY, bm_b = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
@@ -342,6 +361,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
   if (!active) return;
   const float sc2 = a.scale * kLog2e;
   const int row_tiles = n_pad / 16;
+  const int kblocks = (n_pad + 63) / 64;
+  const uint2* bias_frag = reinterpret_cast<const uint2*>(a.bias_frag);
   for (int rt = wig; rt < row_tiles; rt += WPG) {
     const int r0 = rt * 16;
     uint32_t qa[DH / 16][4], da[DH / 16][4];
@@ -364,7 +385,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
       const int ntv = rem >= 32 ? 4 : 2;
       qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
       qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
-      logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv);
+      const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8 +
+                                         ((key0 >> 5) & 1) * 4
+                                   : nullptr;
+      logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv, bfr);
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
@@ -434,6 +458,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
   if (!active) return;
   const float sc2 = a.scale * kLog2e;
   const int key_tiles = n_pad / 16;
+  const int qblocks = (n_pad + 63) / 64;
+  const uint2* bias_t_frag = reinterpret_cast<const uint2*>(a.bias_t_frag);
   for (int kt_ = wig; kt_ < key_tiles; kt_ += WPG) {
     const int k0 = kt_ * 16;
     uint32_t ka[DH / 16][4], va[DH / 16][4];
@@ -461,7 +487,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       qk_block<4, DH>(s, ka, sQ, q0, lane, ntv);
       qk_block<4, DH>(dp, va, sDO, q0, lane, ntv);
       // columns of this block are queries: mask columns >= n; masked / out-of-range key rows via keep_a / keep_b
-      logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv);
+      const uint2* bfr = bias_t_frag ? bias_t_frag + ((((long long)head * key_tiles + kt_) * qblocks + (q0 >> 6)) * 32 + lane) * 8 +
+                                           ((q0 >> 5) & 1) * 4
+                                     : nullptr;
+      logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
       float ds[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
@@ -774,7 +803,9 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = attn_check(a, "attn_bwd")) return rc;
   CTB_CHECK_ARG(a->o && a->d_o && a->lse && a->delta && a->dq && a->dk && a->dv, "attn_bwd: null pointer");
-  CTB_CHECK_ARG(a->bias == nullptr || a->bias_t != nullptr, "attn_bwd: bias needs its transposed copy bias_t");
+  CTB_CHECK_ARG(a->bias == nullptr || a->bias_t != nullptr || a->bias_t_frag != nullptr,
+                "attn_bwd: bias needs its transposed copy (bias_t or bias_t_frag)");
+  CTB_CHECK_ARG((a->bias_frag == nullptr) == (a->bias_t_frag == nullptr), "attn_bwd: bias_frag and bias_t_frag come together");
   CTB_CHECK_ARG(a->dbias == nullptr || a->dim_head == 32, "attn_bwd: dbias is implemented for dim_head 32 only");
   const long long rows = a->total_rows;
   CTB_CHECK_ARG(rows > 0, "attn_bwd: total_rows must be set");

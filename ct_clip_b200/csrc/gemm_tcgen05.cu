@@ -207,6 +207,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int n_blk = ng * p.n_per_unit + j;
         const uint32_t acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        // RESID_F32: the residual tile is prefetched one chunk ahead (the first chunk while the MMAs of this tile are
+        // still in flight) -- these epilogues are HBM-latency-bound otherwise
+        const bool pf = (p.epi == EPI_RESID_F32) && row_ok && (p.N % 32 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.resid) | (uintptr_t)(p.ldr * 4)) & 15) == 0;
+        float4 rnext[8];
+        if (pf && n_blk * BN + half * 32 < p.N) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldr + n_blk * BN + half * 32);
+#pragma unroll
+          for (int i = 0; i < 8; i++) rnext[i] = rp[i];
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -216,15 +226,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t raw[32];
           tmem_ld_32x32(taddr + c * 32, raw);
+          float4 rcur[8];
+          if (pf) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) rcur[i] = rnext[i];
+            const int cn = c + EPI_WARPS / 4;
+            if (cn < BN / 32 && n_blk * BN + cn * 32 < p.N) {
+              const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldr + n_blk * BN + cn * 32);
+#pragma unroll
+              for (int i = 0; i < 8; i++) rnext[i] = rp[i];
+            }
+          }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = __uint_as_float(raw[i]);
           const int ncols = min(32, p.N - col0);
           if (p.bias != nullptr) {
+            const float* bp = p.bias + col0;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-              if (i < ncols) v[i] += __ldg(p.bias + col0 + i);
+              for (int i = 0; i < 8; i++) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
+                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (i < ncols) v[i] += __ldg(bp + i);
+            }
           }
           if (p.epi == EPI_ARGMAX) {
 #pragma unroll
@@ -252,7 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < 8; i++) {
                 float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 if (rs != nullptr) {
-                  const float4 r = *reinterpret_cast<const float4*>(rs + 4 * i);
+                  const float4 r = pf ? rcur[i] : *reinterpret_cast<const float4*>(rs + 4 * i);
                   o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
                 *reinterpret_cast<float4*>(dst + 4 * i) = o;

@@ -109,6 +109,34 @@ __global__ void cpb_expand_kernel(const float* __restrict__ table, int heads, in
     if (bias_t != nullptr) bias_t[((long long)hd * n + j) * n + i] = v;
   }
 }
+// fragment-ordered bias tables: out[hd][rt][cb][lane][nt][e] = bias[hd][row][col] (transposed table: bias[hd][col][row])
+// with row = rt*16 + lane/4 + 8*(e>>1), col = cb*64 + nt*8 + 2*(lane%4) + (e&1); zero outside the n x n grid
+__global__ void cpb_expand_frag_kernel(const float* __restrict__ table, int heads, int h, int w,
+                                       __nv_bfloat16* __restrict__ frag, __nv_bfloat16* __restrict__ frag_t) {
+  const int n = h * w;
+  const int n_pad = (n + 15) & ~15;
+  const int RT = n_pad / 16, CBk = (n_pad + 63) / 64;
+  const long long total = (long long)heads * RT * CBk * 32 * 32;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx & 3), nt = (int)((idx >> 2) & 7), lane = (int)((idx >> 5) & 31);
+    long long rest = idx >> 10;
+    const int cb = (int)(rest % CBk);
+    rest /= CBk;
+    const int rt = (int)(rest % RT);
+    const int hd = (int)(rest / RT);
+    const int row = rt * 16 + (lane >> 2) + 8 * (e >> 1);
+    const int col = cb * 64 + nt * 8 + 2 * (lane & 3) + (e & 1);
+    float v = 0.f, vt = 0.f;
+    if (row < n && col < n) {
+      const int r1 = ((row / w) - (col / w) + h - 1) * (2 * w - 1) + ((row % w) - (col % w) + w - 1);   // bias[row][col]
+      const int r2 = ((col / w) - (row / w) + h - 1) * (2 * w - 1) + ((col % w) - (row % w) + w - 1);   // bias[col][row]
+      v = table[(long long)r1 * heads + hd];
+      vt = table[(long long)r2 * heads + hd];
+    }
+    frag[idx] = __float2bfloat16(v);
+    frag_t[idx] = __float2bfloat16(vt);
+  }
+}
 // dtable[r][hd] = sum over (i,j) with rel(i,j) == r of dbias[hd][i][j]
 __global__ void cpb_reduce_kernel(const float* __restrict__ dbias, int heads, int h, int w, float* __restrict__ dtable) {
   const int r = blockIdx.x;
@@ -463,7 +491,7 @@ extern "C" int ctclip_sgemm_f32(const ctclip_sgemm_args* a, void* stream_) {
 extern "C" int ctclip_colsum(const void* x, int32_t is_bf16, int64_t ld, int64_t M, int32_t N, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(x && out && M > 0 && N > 0, "colsum: bad args");
-  const int rows_per_cta = 512;
+  const int rows_per_cta = M >= 16384 ? 512 : 32;   // few rows: spread them over more CTAs (latency-bound otherwise)
   dim3 grid(ceil_div(N, 256), ceil_div(M, rows_per_cta));
   if (is_bf16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, N, out, rows_per_cta);
   else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ld, M, N, out, rows_per_cta);
@@ -494,6 +522,17 @@ extern "C" int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, i
   const long long total = (long long)heads * h * w * h * w;
   cpb_expand_kernel<<<grid_for(total, 256), 256, 0, stream>>>(table, heads, h, w, reinterpret_cast<__nv_bfloat16*>(bias),
                                                             reinterpret_cast<__nv_bfloat16*>(bias_t));
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t w, void* bias_frag, void* bias_t_frag,
+                                      void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(table && bias_frag && bias_t_frag && heads > 0 && h > 0 && w > 0, "cpb_expand_frag: bad args");
+  const int n_pad = (h * w + 15) & ~15;
+  const long long total = (long long)heads * (n_pad / 16) * ((n_pad + 63) / 64) * 1024;
+  cpb_expand_frag_kernel<<<grid_for(total, 256), 256, 0, stream>>>(table, heads, h, w, reinterpret_cast<__nv_bfloat16*>(bias_frag),
+                                                                  reinterpret_cast<__nv_bfloat16*>(bias_t_frag));
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

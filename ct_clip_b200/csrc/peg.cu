@@ -21,11 +21,13 @@ namespace ctb {
 
 struct PegGeom {
   int T, H, W, D, temporal;
+  const int* table;   // optional precomputed canon(f) (avoids three integer divisions per access in the temporal stack)
 };
 
 __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1, int a2) {
   const int f = (a0 * g.H + a1) * g.W + a2;
   if (!g.temporal) return f;
+  if (g.table != nullptr) return __ldg(g.table + f);
   const int it = f % g.T;
   const int iw = (f / g.T) % g.W;
   const int ih = f / (g.T * g.W);
@@ -39,33 +41,84 @@ __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1,
 // segments), then each thread (= one line x one channel) slides a 3-wide register window along a2 (9 LDS per output,
 // 27 taps). Warps read 32 consecutive channels -> conflict-free LDS and 128 B coalesced stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int A1T = 8;   // lines per CTA tile
-constexpr int CB = 32;   // channels per CTA
+constexpr int A1T = 8;     // lines per CTA tile
+constexpr int CB = 32;     // channels per CTA
+constexpr int NSLOT = 4;   // ring of planes: 3 live + 1 being filled by cp.async while the current plane is computed
 
-struct PegTile {
-  int a1_0, c0, b, p_begin, p_end;  // a0 plane range [p_begin, p_end) produced by this CTA
-};
+__device__ __forceinline__ int peg_slot(int pl) { return ((pl % NSLOT) + NSLOT) % NSLOT; }
 
-// load plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one smem slot; zero outside
-__device__ __forceinline__ void peg_load_plane(float* slot, const float* __restrict__ src, const PegGeom& g, int a0, int a1_0) {
+__device__ __forceinline__ void peg_cp16(void* smem_dst, const void* gmem_src, bool valid) {
+  const int bytes = valid ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void peg_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void peg_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// async load of plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one ring slot
+__device__ __forceinline__ void peg_load_plane_async(float* slot, const float* __restrict__ src, const PegGeom& g, int a0,
+                                                     int a1_0) {
   const int a2h = g.W + 2;
   const int n_tok = (A1T + 2) * a2h;
   for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += blockDim.x) {
     const int tok = idx / (CB / 4), q = idx % (CB / 4);
     const int r1 = tok / a2h, r2 = tok % a2h;
     const int a1 = a1_0 - 1 + r1, a2 = r2 - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a0 >= 0 && a0 < g.T && a1 >= 0 && a1 < g.H && a2 >= 0 && a2 < g.W)
-      v = *reinterpret_cast<const float4*>(src + peg_canon(g, a0, a1, a2) * g.D + q * 4);
-    *reinterpret_cast<float4*>(slot + (size_t)tok * CB + q * 4) = v;
+    const bool ok = a0 >= 0 && a0 < g.T && a1 >= 0 && a1 < g.H && a2 >= 0 && a2 < g.W;
+    const float* p = ok ? src + peg_canon(g, a0, a1, a2) * g.D + q * 4 : src;
+    peg_cp16(slot + (size_t)tok * CB + q * 4, p, ok);
+  }
+}
+// async load of the upstream-gradient tile (A1T lines x W positions x CB channels) of plane a0
+__device__ __forceinline__ void peg_load_dy_async(float* buf, const float* __restrict__ dy, const PegGeom& g, int a0, int a1_0) {
+  const int n_tok = A1T * g.W;
+  for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += blockDim.x) {
+    const int tok = idx / (CB / 4), q = idx % (CB / 4);
+    const int a1 = a1_0 + tok / g.W, a2 = tok % g.W;
+    const bool ok = a0 >= 0 && a0 < g.T && a1 < g.H;
+    const float* p = ok ? dy + peg_canon(g, a0, a1, a2) * g.D + q * 4 : dy;
+    peg_cp16(buf + (size_t)tok * CB + q * 4, p, ok);
+  }
+}
+
+// One output position of the sliding window; the 3-wide window rotates through the register file (ROT) instead of
+// being shifted, so no register moves are issued. Window slot (ROT+2)%3 receives the new right-hand element.
+// Two independent accumulation chains keep the FMA pipe busy with only 8 warps per SM.
+template <int ROT>
+__device__ __forceinline__ float peg_step(float (&win)[9][3], const float* const (&rowp)[9], const float (&wt)[27],
+                                          int off, float init) {
+  constexpr int L = ROT % 3, C = (ROT + 1) % 3, R = (ROT + 2) % 3;
+  float acc0 = init, acc1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 9; r++) win[r][R] = rowp[r][off];
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    float& acc = (r & 1) ? acc1 : acc0;
+    acc = fmaf(wt[r * 3 + 0], win[r][L], acc);
+    acc = fmaf(wt[r * 3 + 1], win[r][C], acc);
+    acc = fmaf(wt[r * 3 + 2], win[r][R], acc);
+  }
+  return acc0 + acc1;
+}
+template <int ROT>
+__device__ __forceinline__ void peg_wstep(float (&win)[9][3], const float* const (&rowp)[9], float (&acc)[27], int off,
+                                          float d) {
+  constexpr int L = ROT % 3, C = (ROT + 1) % 3, R = (ROT + 2) % 3;
+#pragma unroll
+  for (int r = 0; r < 9; r++) win[r][R] = rowp[r][off];
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    acc[r * 3 + 0] = fmaf(d, win[r][L], acc[r * 3 + 0]);
+    acc[r * 3 + 1] = fmaf(d, win[r][C], acc[r * 3 + 1]);
+    acc[r * 3 + 2] = fmaf(d, win[r][R], acc[r * 3 + 2]);
   }
 }
 
 // MODE 0: y = x + conv(x) + bias (forward; taps a0-2..a0)     MODE 1: dx = dy + conv^T(dy) (taps a0..a0+2, mirrored)
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) peg_conv2_kernel(ctclip_peg_args a, int planes_per_cta) {
+__global__ void __launch_bounds__(256, 1) peg_conv2_kernel(ctclip_peg_args a, int planes_per_cta) {
   extern __shared__ __align__(16) float peg_sm[];
-  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal};
+  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table};
   const int a2h = a.W + 2;
   const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
   const int n_a1t = (a.H + A1T - 1) / A1T;
@@ -87,26 +140,32 @@ __global__ void __launch_bounds__(256, 2) peg_conv2_kernel(ctclip_peg_args a, in
   for (int k = 0; k < 27; k++) wt[k] = a.weight[(long long)ch * 27 + ((MODE == 0) ? k : 26 - k)];
   const float bias = (MODE == 0 && a.bias != nullptr) ? a.bias[ch] : 0.f;
   const int a1 = a1_0 + line;
-  // prime the rolling buffer with the two planes preceding (MODE 0) / following (MODE 1) the first output plane
+  // planes needed for output plane a0: a0-2, a0-1, a0 (MODE 0) / a0, a0+1, a0+2 (MODE 1). Walk a0 in direction `dirn`
+  // so that only ONE new plane enters per step; it is fetched (cp.async) while the previous plane is being computed.
   const int first = (MODE == 0) ? p_begin : p_end - 1;
   const int dirn = (MODE == 0) ? 1 : -1;
-  for (int d = 2; d >= 1; d--) {
-    const int pl = first - dirn * d;  // MODE 0: first-2, first-1   MODE 1: first+2, first+1
-    peg_load_plane(peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems, xin, g, pl, a1_0);
+  for (int d = 2; d >= 0; d--) {
+    const int pl = first - dirn * d;
+    peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
   }
-  for (int step = 0; step < p_end - p_begin; step++) {
+  peg_commit();
+  const int n_steps = p_end - p_begin;
+  for (int step = 0; step < n_steps; step++) {
     const int a0 = first + dirn * step;
-    __syncthreads();  // everyone is done reading the slot we are about to overwrite
-    peg_load_plane(peg_sm + (size_t)(((a0 % 3) + 3) % 3) * slot_elems, xin, g, a0, a1_0);
-    __syncthreads();
+    peg_wait_all();
+    __syncthreads();   // plane a0 landed for everyone; everyone finished computing plane a0 - dirn
+    if (step + 1 < n_steps) {   // prefetch the next plane into the slot released by plane a0 - 3*dirn
+      const int pl = a0 + dirn;
+      peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
+      peg_commit();
+    }
     if (a1 < a.H) {
-      // tap k0 reads plane a0 + k0 - 2 (MODE 0) or a0 + k0 (MODE 1)
       const float* rowp[9];
 #pragma unroll
       for (int r = 0; r < 9; r++) {
         const int k0 = r / 3, k1 = r % 3;
         const int pl = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
-        rowp[r] = peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
+        rowp[r] = peg_sm + (size_t)peg_slot(pl) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
       }
       float win[9][3];
 #pragma unroll
@@ -114,33 +173,37 @@ __global__ void __launch_bounds__(256, 2) peg_conv2_kernel(ctclip_peg_args a, in
         win[r][0] = rowp[r][0];       // a2 = -1 (zero padding)
         win[r][1] = rowp[r][CB];      // a2 = 0
       }
-      for (int a2 = 0; a2 < a.W; a2++) {
-        float acc = bias;
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-          win[r][2] = rowp[r][(a2 + 2) * CB];
-#pragma unroll
-          for (int k2 = 0; k2 < 3; k2++) acc = fmaf(wt[r * 3 + k2], win[r][k2], acc);
-          win[r][0] = win[r][1];
-          win[r][1] = win[r][2];
-        }
-        // centre tap input = residual term: row r = (k0 = 2 | 0, k1 = 1), window position "a2" was shifted into win[.][0]
-        const float ctr = (MODE == 0) ? win[7][0] : win[1][0];
+      constexpr int CR = (MODE == 0) ? 7 : 1;   // row of the centre tap (k0 = 2 | 0, k1 = 1): its centre element = residual
+      auto emit = [&](int a2, float val) {
         const long long tok = peg_canon(g, a0, a1, a2);
-        const float out = acc + ctr;
-        yout[tok * a.D + lane] = out;
-        if (ybf != nullptr) ybf[tok * a.D + lane] = __float2bfloat16(out);
+        yout[tok * a.D + lane] = val;
+        if (ybf != nullptr) ybf[tok * a.D + lane] = __float2bfloat16(val);
+      };
+      for (int a2 = 0; a2 < a.W; a2 += 3) {
+        const float o0 = peg_step<0>(win, rowp, wt, (a2 + 2) * CB, bias) + win[CR][1];
+        emit(a2, o0);
+        if (a2 + 1 < a.W) {
+          const float o1 = peg_step<1>(win, rowp, wt, (a2 + 3) * CB, bias) + win[CR][2];
+          emit(a2 + 1, o1);
+        }
+        if (a2 + 2 < a.W) {
+          const float o2 = peg_step<2>(win, rowp, wt, (a2 + 4) * CB, bias) + win[CR][0];
+          emit(a2 + 2, o2);
+        }
       }
     }
   }
 }
 
-// dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p]   (x planes in the rolling buffer, dy straight from global)
-__global__ void __launch_bounds__(256, 2) peg_wgrad2_kernel(ctclip_peg_args a, int planes_per_cta) {
+// dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p]
+// x planes in the 4-slot ring, the upstream-gradient tile of the same plane in a 2-slot ring, both prefetched with cp.async
+__global__ void __launch_bounds__(256, 1) peg_wgrad2_kernel(ctclip_peg_args a, int planes_per_cta, int dy_double) {
   extern __shared__ __align__(16) float peg_sm[];
-  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal};
+  const PegGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table};
   const int a2h = a.W + 2;
   const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
+  const size_t dy_elems = (size_t)A1T * a.W * CB;
+  float* sdy = peg_sm + NSLOT * slot_elems;   // [2][A1T][W][CB]
   const int n_a1t = (a.H + A1T - 1) / A1T;
   const int c0 = (blockIdx.x % (a.D / CB)) * CB;
   const int a1_0 = ((blockIdx.x / (a.D / CB)) % n_a1t) * A1T;
@@ -158,39 +221,48 @@ __global__ void __launch_bounds__(256, 2) peg_wgrad2_kernel(ctclip_peg_args a, i
 #pragma unroll
   for (int k = 0; k < 27; k++) acc[k] = 0.f;
   float accb = 0.f;
-  for (int d = 2; d >= 1; d--) {
+  for (int d = 2; d >= 0; d--) {
     const int pl = p_begin - d;
-    peg_load_plane(peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems, xin, g, pl, a1_0);
+    peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
   }
+  peg_load_dy_async(sdy, dy, g, p_begin, a1_0);
+  peg_commit();
   for (int a0 = p_begin; a0 < p_end; a0++) {
+    const int par = dy_double ? ((a0 - p_begin) & 1) : 0;
+    if (!dy_double && a0 > p_begin) {   // wide grids: a single gradient tile fits; fetch it without overlap
+      __syncthreads();
+      peg_load_dy_async(sdy, dy, g, a0, a1_0);
+      peg_commit();
+    }
+    peg_wait_all();
     __syncthreads();
-    peg_load_plane(peg_sm + (size_t)(((a0 % 3) + 3) % 3) * slot_elems, xin, g, a0, a1_0);
-    __syncthreads();
+    if (a0 + 1 < p_end) {
+      peg_load_plane_async(peg_sm + (size_t)peg_slot(a0 + 1) * slot_elems, xin, g, a0 + 1, a1_0);
+      if (dy_double) peg_load_dy_async(sdy + (size_t)(par ^ 1) * dy_elems, dy, g, a0 + 1, a1_0);
+      peg_commit();
+    }
     if (a1 < a.H) {
       const float* rowp[9];
 #pragma unroll
       for (int r = 0; r < 9; r++) {
         const int k0 = r / 3, k1 = r % 3;
-        const int pl = a0 + k0 - 2;
-        rowp[r] = peg_sm + (size_t)(((pl % 3) + 3) % 3) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
+        rowp[r] = peg_sm + (size_t)peg_slot(a0 + k0 - 2) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
       }
+      const float* dyl = sdy + (size_t)par * dy_elems + (size_t)(line * a.W) * CB + lane;
       float win[9][3];
 #pragma unroll
       for (int r = 0; r < 9; r++) {
         win[r][0] = rowp[r][0];
         win[r][1] = rowp[r][CB];
       }
-      for (int a2 = 0; a2 < a.W; a2++) {
-        const float d = dy[peg_canon(g, a0, a1, a2) * a.D + lane];
-        accb += d;
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-          win[r][2] = rowp[r][(a2 + 2) * CB];
-#pragma unroll
-          for (int k2 = 0; k2 < 3; k2++) acc[r * 3 + k2] = fmaf(d, win[r][k2], acc[r * 3 + k2]);
-          win[r][0] = win[r][1];
-          win[r][1] = win[r][2];
-        }
+      for (int a2 = 0; a2 < a.W; a2 += 3) {
+        const float d0 = dyl[a2 * CB];
+        const float d1 = (a2 + 1 < a.W) ? dyl[(a2 + 1) * CB] : 0.f;
+        const float d2 = (a2 + 2 < a.W) ? dyl[(a2 + 2) * CB] : 0.f;
+        accb += d0 + d1 + d2;
+        peg_wstep<0>(win, rowp, acc, (a2 + 2) * CB, d0);
+        if (a2 + 1 < a.W) peg_wstep<1>(win, rowp, acc, (a2 + 3) * CB, d1);
+        if (a2 + 2 < a.W) peg_wstep<2>(win, rowp, acc, (a2 + 4) * CB, d2);
       }
     }
   }
@@ -222,30 +294,59 @@ static int peg_check(const ctclip_peg_args* a, const char* who) {
   return CTCLIP_OK;
 }
 
-// grid.x = channel blocks x a1 tiles x a0 chunks; a0 chunks sized so that the grid has >= ~3 CTAs per SM
-static void peg_launch_shape(const ctclip_peg_args* a, dim3* grid, int* planes_per_cta, size_t* smem) {
+// grid.x = channel blocks x a1 tiles x a0 chunks (1 CTA per SM: ~133-182 KB of shared memory). The a0 range is
+// split into the chunk count that minimises  ceil(CTAs / SMs) * (planes per CTA + 2 priming planes).
+static void peg_launch_shape(const ctclip_peg_args* a, int dy_bufs, dim3* grid, int* planes_per_cta, size_t* smem) {
   const int n_a1t = (a->H + A1T - 1) / A1T;
   const long long base = (long long)(a->D / CB) * n_a1t * a->B;
-  int chunks = (int)((3LL * num_sms() + base - 1) / base);
-  if (chunks < 1) chunks = 1;
-  if (chunks > a->T) chunks = a->T;
-  *planes_per_cta = (a->T + chunks - 1) / chunks;
-  chunks = (a->T + *planes_per_cta - 1) / *planes_per_cta;
+  int best_chunks = 1;
+  long long best_cost = -1;
+  for (int chunks = 1; chunks <= 6 && chunks <= a->T; chunks++) {
+    const int ppc = (a->T + chunks - 1) / chunks;
+    const int real_chunks = (a->T + ppc - 1) / ppc;
+    const long long waves = (base * real_chunks + num_sms() - 1) / num_sms();
+    const long long cost = waves * (ppc + 2);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = real_chunks; }
+  }
+  *planes_per_cta = (a->T + best_chunks - 1) / best_chunks;
+  const int chunks = (a->T + *planes_per_cta - 1) / *planes_per_cta;
   *grid = dim3((unsigned)((a->D / CB) * n_a1t * chunks), (unsigned)a->B);
-  *smem = sizeof(float) * 3 * (size_t)(A1T + 2) * (a->W + 2) * CB;
+  *smem = sizeof(float) * NSLOT * (size_t)(A1T + 2) * (a->W + 2) * CB;
+  *smem += sizeof(float) * dy_bufs * (size_t)A1T * a->W * CB;
   const size_t red_bytes = sizeof(float) * A1T * 28 * CB;  // weight-gradient reduction scratch
   if (*smem < red_bytes) *smem = red_bytes;
 }
 
-template <typename Kern>
-static int peg_launch(Kern kern, const ctclip_peg_args* a, cudaStream_t stream) {
+static int peg_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream) {
   dim3 grid;
   int ppc;
   size_t smem;
-  peg_launch_shape(a, &grid, &ppc, &smem);
+  peg_launch_shape(a, 0, &grid, &ppc, &smem);
   CTB_CHECK_ARG(smem <= 227 * 1024, "peg: token grid width %d needs %zu B of shared memory", a->W, smem);
-  CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, 256, smem, stream>>>(*a, ppc);
+  if (mode == 0) {
+    CTB_CUDA(cudaFuncSetAttribute(peg_conv2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    peg_conv2_kernel<0><<<grid, 256, smem, stream>>>(*a, ppc);
+  } else {
+    CTB_CUDA(cudaFuncSetAttribute(peg_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    peg_conv2_kernel<1><<<grid, 256, smem, stream>>>(*a, ppc);
+  }
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+static int peg_launch_wgrad(const ctclip_peg_args* a, cudaStream_t stream) {
+  dim3 grid;
+  int ppc;
+  size_t smem;
+  int dy_bufs = 2;
+  peg_launch_shape(a, dy_bufs, &grid, &ppc, &smem);
+  if (smem > 227 * 1024) {
+    dy_bufs = 1;
+    peg_launch_shape(a, dy_bufs, &grid, &ppc, &smem);
+  }
+  CTB_CHECK_ARG(smem <= 227 * 1024, "peg: token grid width %d needs %zu B of shared memory", a->W, smem);
+  CTB_CUDA(cudaFuncSetAttribute(peg_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  peg_wgrad2_kernel<<<grid, 256, smem, stream>>>(*a, ppc, dy_bufs == 2);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }
@@ -254,7 +355,7 @@ extern "C" int ctclip_peg_fwd(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_fwd")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_fwd: null y/weight");
-  return peg_launch(peg_conv2_kernel<0>, a, stream);
+  return peg_launch_conv(0, a, stream);
 }
 
 // x = upstream gradient dy (fp32), y = dx out (fp32), y_bf16 = optional bf16 copy of dx
@@ -262,7 +363,7 @@ extern "C" int ctclip_peg_bwd_data(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_data")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_bwd_data: null y/weight");
-  return peg_launch(peg_conv2_kernel<1>, a, stream);
+  return peg_launch_conv(1, a, stream);
 }
 
 // x = forward input, dy = upstream gradient; dweight [D,27] and dbias [D] are accumulated (atomics)
@@ -270,5 +371,5 @@ extern "C" int ctclip_peg_bwd_weight(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_weight")) return rc;
   CTB_CHECK_ARG(a->dy && a->dweight, "peg_bwd_weight: null dy/dweight");
-  return peg_launch(peg_wgrad2_kernel, a, stream);
+  return peg_launch_wgrad(a, stream);
 }

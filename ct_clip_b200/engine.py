@@ -92,6 +92,16 @@ class CTViTEngine:
         R = (2 * g.H - 1) * (2 * g.W - 1)
         self.cpb_x = torch.empty(R, 2, device=device)
         ops.cpb_inputs(self.cpb_x, g.H, g.W)
+        self._canon = {}
+
+    def _canon_table(self, T):
+        """canon(f) of the temporal stack's PEG (SURVEY trap T1) as an int32 lookup table (index prep, built once per T)."""
+        if T not in self._canon:
+            g = self.g
+            f = torch.arange(T * g.H * g.W, dtype=torch.int64)
+            it, iw, ih = f % T, (f // T) % g.W, f // (T * g.W)
+            self._canon[T] = ((it * g.H + ih) * g.W + iw).to(torch.int32).to(self.device)
+        return self._canon[T]
 
     # ------------------------------------------------------------------------------------------
     def _alloc_weights(self):
@@ -150,10 +160,13 @@ class CTViTEngine:
         ops.sgemm(self.cpb_x, P[pre + "0.0.weight"], h1, M=R, N=g.dim, K=2, trans_b=True, bias=P[pre + "0.0.bias"], act=1)
         ops.sgemm(h1, P[pre + "1.0.weight"], h2, M=R, N=g.dim, K=g.dim, trans_b=True, bias=P[pre + "1.0.bias"], act=1)
         ops.sgemm(h2, P[pre + "2.weight"], tab, M=R, N=g.heads, K=g.dim, trans_b=True, bias=P[pre + "2.bias"])
-        bias = torch.empty(g.heads, g.S, g.S, dtype=torch.bfloat16, device=dev)
-        bias_t = torch.empty_like(bias) if save else None
-        ops.cpb_expand(tab, g.heads, g.H, g.W, bias, bias_t)
-        return bias, bias_t, (h1, h2)
+        bias = torch.empty(g.heads, g.S, g.S, dtype=torch.bfloat16, device=dev)     # natural layout: dbias kernel, taps
+        ops.cpb_expand(tab, g.heads, g.H, g.W, bias, None)
+        nfrag = ops.frag_elems(g.heads, g.S)
+        bias_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)             # MMA-fragment order (fwd / dQ)
+        bias_t_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)           # transposed, fragment order (dK/dV)
+        ops.cpb_expand_frag(tab, g.heads, g.H, g.W, bias_frag, bias_t_frag)
+        return bias, (bias_frag, bias_t_frag), (h1, h2)
 
     def _cpb_backward(self, P, G, dbias, hs):
         g, dev = self.g, self.device
@@ -175,7 +188,7 @@ class CTViTEngine:
         ops.colsum(dh1, G[pre + "0.0.bias"], M=R, N=g.dim)
 
     # ------------------------------------------------------------------------------------------
-    def _layer_forward(self, x, P, pre, lw, b, T, temporal, bias, save):
+    def _layer_forward(self, x, P, pre, lw, b, T, temporal, bias, save, frags=None):
         """x: fp32 stream [M, D] (consumed). Returns (new stream, saved-or-None)."""
         g, dev = self.g, self.device
         M, D, I, Fp = x.shape[0], g.dim, g.inner, g.ff_pad
@@ -183,7 +196,7 @@ class CTViTEngine:
         sv = _Saved() if save else None
         x1 = torch.empty_like(x)
         ops.peg_fwd(x, x1, P[pre + "0.dsconv.weight"], P[pre + "0.dsconv.bias"], B=b, T=T, H=g.H, W=g.W, D=D,
-                    temporal=temporal)
+                    temporal=temporal, canon_table=self._canon_table(T) if temporal else None)
         xhat1 = torch.empty(M, D, **bf)
         xb1 = torch.empty(M, D, **bf)
         rstd1 = torch.empty(M, device=dev) if save else None
@@ -199,7 +212,8 @@ class CTViTEngine:
         o = torch.empty(M, I, **bf)
         lse = torch.empty(M, g.heads, device=dev) if save else None
         v = kv_raw[:, I:]
-        ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, **self._attn_geom(b, T, temporal))
+        ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, bias_frag=frags[0] if frags else None,
+                     bias_t_frag=frags[1] if frags else None, **self._attn_geom(b, T, temporal))
         ops.gemm(o, lw.wo, M=M, N=D, K=I, epilogue=ops.EPI_RESID_F32, C_out=x1, resid=x1)          # x2 (in place)
         xhat2 = torch.empty(M, D, **bf)
         rstd2 = torch.empty(M, device=dev) if save else None
@@ -243,7 +257,7 @@ class CTViTEngine:
         ctx.update(bias=bias, bias_t=bias_t, cpb_h=cpb_h if save else None)
         saved_s, saved_t = [], []
         for i, lw in enumerate(self.spatial_w):
-            x, sv = self._layer_forward(x, P, f"enc_spatial_transformer.layers.{i}.", lw, b, T, False, bias, save)
+            x, sv = self._layer_forward(x, P, f"enc_spatial_transformer.layers.{i}.", lw, b, T, False, bias, save, frags=bias_t)
             saved_s.append(sv)
             if taps is not None:
                 taps[f"spatial.{i}"] = x.clone()
@@ -325,7 +339,8 @@ class CTViTEngine:
         dkv = torch.empty(M, 2 * I, **bf)       # [dk_hat | dv]
         delta = torch.empty(M, g.heads, device=dev)
         ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
-                     ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias, bias_t=bias_t,
+                     ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias,
+                     bias_frag=bias_t[0] if bias_t else None, bias_t_frag=bias_t[1] if bias_t else None,
                      dbias=dbias, **self._attn_geom(b, T, temporal))
         # ---- l2norm * scale backward (attention.py:152-154); dq/dk overwritten with raw-projection gradients
         ops.l2norm_bwd(dqh, I, sv.q_raw, I, P[a + "q_scale"], dqh, I, G[a + "q_scale"], M, g.heads)
@@ -340,10 +355,12 @@ class CTViTEngine:
         ops.ln_bwd(M, D, g_bf16=dxh, xhat=sv.xhat1, rstd=sv.rstd1, dres_in=dres, dx_f32=dres)
         ops.gemm(dkv, lw.wkv, M=M, N=D, K=2 * I, b_major=1, epilogue=ops.EPI_RESID_F32, C_out=dres, resid=dres)
         # ---- PEG: x1 = x0 + conv(x0)
+        ct = self._canon_table(T) if temporal else None
         ops.peg_bwd_weight(sv.x_in, dres, G[pre + "0.dsconv.weight"], G[pre + "0.dsconv.bias"], B=b, T=T, H=g.H, W=g.W,
-                           D=D, temporal=temporal)
+                           D=D, temporal=temporal, canon_table=ct)
         dx0 = torch.empty_like(dres)
-        ops.peg_bwd_data(dres, dx0, P[pre + "0.dsconv.weight"], dx_bf16=dxb, B=b, T=T, H=g.H, W=g.W, D=D, temporal=temporal)
+        ops.peg_bwd_data(dres, dx0, P[pre + "0.dsconv.weight"], dx_bf16=dxb, B=b, T=T, H=g.H, W=g.W, D=D, temporal=temporal,
+                         canon_table=ct)
         return dx0, dxb
 
     def backward(self, ctx, dtok, P, G):

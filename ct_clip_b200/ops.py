@@ -103,11 +103,12 @@ def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
 
 
 def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
-              dbias=None, lines=4):
+              dbias=None, lines=4, canon_table=None):
     a = PegArgs()
     a.x, a.dy, a.y, a.y_bf16 = x.data_ptr(), _ptr(dy), _ptr(y), _ptr(y_bf16)
     a.weight, a.bias, a.dweight, a.dbias = _ptr(weight), _ptr(bias), _ptr(dweight), _ptr(dbias)
     a.B, a.T, a.H, a.W, a.D, a.temporal, a.lines = B, T, H, W, D, int(temporal), lines
+    a.canon_table = _ptr(canon_table) if temporal else None
     return a
 
 
@@ -124,7 +125,7 @@ def peg_bwd_weight(x, dy, dweight, dbias, **kw):
 
 
 def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
-               bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None):
+               bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None, bias_frag=None, bias_t_frag=None):
     a = AttnArgs()
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv
     a.o, a.ldo, a.lse = o.data_ptr(), ldo, _ptr(lse)
@@ -132,6 +133,7 @@ def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_i
     a.n, a.heads, a.dim_head, a.num_seqs, a.seq_inner = n, heads, dim_head, num_seqs, seq_inner
     a.seq_outer_stride, a.tok_stride, a.scale = seq_outer_stride, tok_stride, scale
     a.key_mask = _ptr(key_mask)
+    a.bias_frag, a.bias_t_frag = _ptr(bias_frag), _ptr(bias_t_frag)
     return a
 
 
@@ -181,6 +183,16 @@ def cpb_inputs(X, h, w):
 
 def cpb_expand(table, heads, h, w, bias, bias_t=None):
     call("ctclip_cpb_expand", table.data_ptr(), heads, h, w, bias.data_ptr(), _ptr(bias_t), _stream())
+
+
+def cpb_expand_frag(table, heads, h, w, bias_frag, bias_t_frag):
+    call("ctclip_cpb_expand_frag", table.data_ptr(), heads, h, w, bias_frag.data_ptr(), bias_t_frag.data_ptr(), _stream())
+
+
+def frag_elems(heads, n):
+    """number of bf16 elements of a fragment-ordered bias table"""
+    n_pad = (n + 15) // 16 * 16
+    return heads * (n_pad // 16) * ((n_pad + 63) // 64) * 32 * 32
 
 
 def cpb_reduce(dbias, heads, h, w, dtable):

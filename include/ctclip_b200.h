@@ -163,7 +163,9 @@ typedef struct {
   float* dbias;
   int32_t B, T, H, W, D;
   int32_t temporal;
-  int32_t lines;       /* (a0,a1) lines per CTA */
+  int32_t lines;       /* unused (kept for ABI stability) */
+  const int32_t* canon_table; /* optional, temporal only: canon_table[f] = canonical token of conv-grid index
+                                 f = (a0*H + a1)*W + a2, i.e. ((f % T)*H + f / (T*W))*W + (f / T) % W */
 } ctclip_peg_args;
 int ctclip_peg_fwd(const ctclip_peg_args* args, void* stream);
 int ctclip_peg_bwd_data(const ctclip_peg_args* args, void* stream);
@@ -198,6 +200,11 @@ typedef struct {
   float* dbias;
   int64_t total_rows;
   const int32_t* key_mask; /* optional [num_seqs, n]: non-zero = key may be attended (BERT padding mask) */
+  /* optional: the same bias (and its transpose) re-ordered per MMA fragment by ctclip_cpb_expand_frag:
+   * bf16 [heads, ceil16(n)/16, ceil64(n)/64, 32 lanes, 8 n-tiles, 4]; when given they replace bias / bias_t in the
+   * forward, dQ and dK/dV kernels (fully coalesced 16-byte loads). */
+  const uint16_t* bias_frag;
+  const uint16_t* bias_t_frag;
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
@@ -235,6 +242,9 @@ int ctclip_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int ctclip_cpb_inputs(float* X, int32_t h, int32_t w, void* stream);
 int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, int32_t w, void* bias, void* bias_t, void* stream);
 int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream);
+/* fragment-ordered copies of the bias and of its transpose (see ctclip_attn_args.bias_frag) */
+int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t w, void* bias_frag, void* bias_t_frag,
+                           void* stream);
 
 /* GEGLU backward (attention.py:39-42) on the interleaved pre-activation h bf16 [M, 2*n_pairs] (in place):
  * h[:,2j] <- dg[:,j]*gelu(gate_j), h[:,2j+1] <- dg[:,j]*value_j*gelu'(gate_j); colsum[2*n_pairs] += column sums. */

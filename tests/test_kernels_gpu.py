@@ -66,6 +66,9 @@ def test_peg_fwd_bwd(temporal, T, H, W):
     bias = 0.1 * _randn(D, seed=9)
     y = torch.empty_like(x)
     kw = dict(B=b, T=T, H=H, W=W, D=D, temporal=temporal)
+    if temporal and T == 6:     # also exercise the precomputed canon(f) table
+        f = torch.arange(T * H * W)
+        kw["canon_table"] = (((f % T) * H + f // (T * W)) * W + (f // T) % W).to(torch.int32).to(DEV)
     ops.peg_fwd(x.view(-1, D), y.view(-1, D), w.view(D, 27), bias, **kw)
 
     def ref(xc, wc, bc):
@@ -101,9 +104,31 @@ def _attn_ref(q, k, v, bias, scale=8.0):
     return sim.softmax(-1) @ v
 
 
+def _to_frag(bias):
+    """dense [heads, n, n] -> MMA-fragment order [heads, n_pad/16, ceil(n_pad/64), 32 lanes, 8 n-tiles, 4] (zero padded)."""
+    heads, n, _ = bias.shape
+    n_pad = (n + 15) // 16 * 16
+    RT, CB = n_pad // 16, (n_pad + 63) // 64
+    big = torch.zeros(heads, RT * 16, CB * 64, dtype=bias.dtype, device=bias.device)
+    big[:, :n, :n] = bias
+    lane = torch.arange(32, device=bias.device)
+    e = torch.arange(4, device=bias.device)
+    nt = torch.arange(8, device=bias.device)
+    row_in = (lane[:, None, None] // 4) + 8 * (e[None, None, :] // 2)                       # [32,1,4]
+    col_in = nt[None, :, None] * 8 + 2 * (lane[:, None, None] % 4) + (e[None, None, :] % 2)   # [32,8,4]
+    rows = (torch.arange(RT, device=bias.device)[:, None, None, None, None] * 16 + row_in[None, None])    # [RT,1,32,1,4]
+    cols = (torch.arange(CB, device=bias.device)[None, :, None, None, None] * 64 + col_in[None, None])   # [1,CB,32,8,4]
+    rows = rows.expand(RT, CB, 32, 8, 4)
+    cols = cols.expand(RT, CB, 32, 8, 4)
+    return big[:, rows, cols].contiguous().view(-1)
+
+
 @pytest.mark.parametrize("mode,b,T,S", [("spatial", 2, 3, 16), ("spatial", 1, 2, 576), ("spatial", 1, 2, 100),
+                                        ("spatial_frag", 1, 2, 576), ("spatial_frag", 2, 2, 100),
                                         ("temporal", 2, 24, 16), ("temporal", 1, 5, 8)])
 def test_attention_fwd_bwd(mode, b, T, S):
+    use_frag = mode == "spatial_frag"
+    mode = "spatial" if use_frag else mode
     from ct_clip_b200 import ops
     heads, dh = 8, 32
     I = heads * dh
@@ -138,6 +163,10 @@ def test_attention_fwd_bwd(mode, b, T, S):
 
     o = torch.empty(M, I, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(M, heads, device=DEV)
+    if use_frag:    # fragment-ordered bias tables (what the encoder uses); the dense table still feeds the dbias kernel
+        geom["bias_frag"] = _to_frag(bias)
+        geom["bias_t_frag"] = _to_frag(bias_t)
+        bias_t = None
     ops.attn_fwd(q, k, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, **geom)
     qs, ks, vs = (to_seq(t).requires_grad_(True) for t in (q, k, v))
     bref = bias.float().clone().requires_grad_(True) if bias is not None else None
