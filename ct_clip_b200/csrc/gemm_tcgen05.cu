@@ -306,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             __nv_bfloat16* gdst = reinterpret_cast<__nv_bfloat16*>(p.C2) + row * p.ldc2 + (col0 >> 1);
             float g[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) g[i] = gelu_erf(v[2 * i + 1]) * v[2 * i];
+            for (int i = 0; i < 16; i++) g[i] = gelu_erf_fast(v[2 * i + 1]) * v[2 * i];
             if (ncols == 32 && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0)) {
               uint4* d4 = reinterpret_cast<uint4*>(gdst);
 #pragma unroll
@@ -347,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 32; i++) v[i] = gelu_erf_fast(v[i]);
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
             if (ncols == 32) store_bf16x32(dst, v);
             else {

@@ -150,8 +150,15 @@ __global__ void __launch_bounds__(256, 1) peg_conv2_kernel(ctclip_peg_args a, in
   }
   peg_commit();
   const int n_steps = p_end - p_begin;
+  // canonical token index of every output of the current plane ([2][A1T][W], double-buffered by step parity): one
+  // canon() per thread per plane instead of one per output inside the sliding loop
+  int* s_tok = reinterpret_cast<int*>(peg_sm + NSLOT * slot_elems);
   for (int step = 0; step < n_steps; step++) {
     const int a0 = first + dirn * step;
+    for (int i = threadIdx.x; i < A1T * a.W; i += blockDim.x) {
+      const int l1 = a1_0 + i / a.W;
+      s_tok[(step & 1) * A1T * a.W + i] = (l1 < a.H) ? (int)peg_canon(g, a0, l1, i % a.W) : 0;
+    }
     peg_wait_all();
     __syncthreads();   // plane a0 landed for everyone; everyone finished computing plane a0 - dirn
     if (step + 1 < n_steps) {   // prefetch the next plane into the slot released by plane a0 - 3*dirn
@@ -174,10 +181,11 @@ __global__ void __launch_bounds__(256, 1) peg_conv2_kernel(ctclip_peg_args a, in
         win[r][1] = rowp[r][CB];      // a2 = 0
       }
       constexpr int CR = (MODE == 0) ? 7 : 1;   // row of the centre tap (k0 = 2 | 0, k1 = 1): its centre element = residual
+      const int* tokl = s_tok + (step & 1) * A1T * a.W + line * a.W;
       auto emit = [&](int a2, float val) {
-        const long long tok = peg_canon(g, a0, a1, a2);
-        yout[tok * a.D + lane] = val;
-        if (ybf != nullptr) ybf[tok * a.D + lane] = __float2bfloat16(val);
+        const long long off = (long long)tokl[a2] * a.D + lane;
+        yout[off] = val;
+        if (ybf != nullptr) ybf[off] = __float2bfloat16(val);
       };
       for (int a2 = 0; a2 < a.W; a2 += 3) {
         const float o0 = peg_step<0>(win, rowp, wt, (a2 + 2) * CB, bias) + win[CR][1];
@@ -312,6 +320,7 @@ static void peg_launch_shape(const ctclip_peg_args* a, int dy_bufs, dim3* grid, 
   const int chunks = (a->T + *planes_per_cta - 1) / *planes_per_cta;
   *grid = dim3((unsigned)((a->D / CB) * n_a1t * chunks), (unsigned)a->B);
   *smem = sizeof(float) * NSLOT * (size_t)(A1T + 2) * (a->W + 2) * CB;
+  if (dy_bufs == 0) *smem += sizeof(int) * 2 * (size_t)A1T * a->W;   // token-index table of the conv kernels
   *smem += sizeof(float) * dy_bufs * (size_t)A1T * a->W * CB;
   const size_t red_bytes = sizeof(float) * A1T * 28 * CB;  // weight-gradient reduction scratch
   if (*smem < red_bytes) *smem = red_bytes;

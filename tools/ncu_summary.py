@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Print the headline metrics of every launch in an .ncu-rep (read here without a GPU): ncu -i rep --page raw --csv"""
+import csv
+import subprocess
+import sys
+
+WANT = [("gpu__time_duration.sum", "time"), ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+        ("launch__block_size", "block"),
+        ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+        ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("smsp__inst_executed.sum", "warp_inst"),
+        ("lts__t_sector_hit_rate.pct", "l2hit%"), ("l1tex__t_sector_hit_rate.pct", "l1hit%"),
+        ("lts__t_bytes.sum", "l2_bytes"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long_sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short_sb"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_barrier"),
+        ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "st_mio"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "st_lg"),
+        ("smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "st_sleep"),
+        ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "st_membar"),
+        ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "st_tex")]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")][:90]
+        print("==", name)
+        for key, short in WANT:
+            if key in hdr:
+                print(f"   {short:14s} {r[hdr.index(key)]} {units[hdr.index(key)]}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
