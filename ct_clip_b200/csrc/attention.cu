@@ -90,29 +90,42 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[DH / 16][4], const __
     a[kt][3] = rb < g.n ? *reinterpret_cast<const uint32_t*>(pb + kt * 16 + 2 * t + 8) : 0u;
   }
 }
-// C[16 x 8*NT] = A[16 x DH] * rows(tile)[key0 .. key0+8*NT)^T  with tile row-major [key][KROW]
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
+// C[16 x 8*NT] = A[16 x DH] * rows(tile)[key0 .. key0+8*NT)^T  with tile row-major [key][KROW].
+// B fragments via ldmatrix.x4: one instruction yields (b0,b1) of two consecutive 16-wide k-steps of one n-tile.
 template <int NT, int DH>
 __device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[DH / 16][4],
                                          const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
-  const int gq = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) {
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
     if (nt >= nt_valid) continue;  // warp-uniform; tiles beyond the padded sequence stay zero
-    const __nv_bfloat16* kr = tile + (key0 + nt * 8 + gq) * KROW + 2 * t;
+    const __nv_bfloat16* base = tile + (key0 + nt * 8 + (lane & 7)) * KROW + (lane >> 3) * 8;
 #pragma unroll
-    for (int kt = 0; kt < DH / 16; kt++) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kt * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kt * 16 + 8);
-      mma_16816(s[nt], a[kt], b0, b1);
+    for (int kp = 0; kp < DH / 32; kp++) {
+      uint32_t b[4];
+      ldsm_x4(b, base + kp * 32);
+      mma_16816(s[nt], a[2 * kp], b[0], b[1]);
+      mma_16816(s[nt], a[2 * kp + 1], b[2], b[3]);
     }
   }
 }
-// acc[16 x DH] += P[16 x 8*NT] * X[key0.., :]  with X given transposed: xt[d][tstride] (keys contiguous)
+// acc[16 x DH] += P[16 x 8*NT] * X[key0 .. key0+8*NT, :]  with X row-major [key][KROW] (the same tile layout as above):
+// ldmatrix.x4.trans delivers the (k = key, n = d) B fragments straight from the row-major tile, so no transposed copy of
+// V / K / Q / dO is kept in shared memory.
 template <int NT, int DH>
 __device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&p)[NT][4],
-                                         const __nv_bfloat16* xt, int tstride, int key0, int lane, int nt_valid = NT) {
-  const int gq = lane >> 2, t = lane & 3;
+                                         const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
 #pragma unroll
   for (int kk = 0; kk < NT / 2; kk++) {
     if (2 * kk >= nt_valid) continue;
@@ -121,16 +134,17 @@ __device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&
     a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
     a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
     a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    const int mi = lane >> 3;
+    const __nv_bfloat16* base = tile + (key0 + kk * 16 + (mi & 1) * 8 + (lane & 7)) * KROW + (mi >> 1) * 8;
 #pragma unroll
-    for (int dt = 0; dt < DH / 8; dt++) {
-      const __nv_bfloat16* vr = xt + (dt * 8 + gq) * tstride + key0 + kk * 16 + 2 * t;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
-      mma_16816(acc[dt], a, b0, b1);
+    for (int dp = 0; dp < DH / 16; dp++) {
+      uint32_t b[4];
+      ldsm_x4_trans(b, base + dp * 16);
+      mma_16816(acc[2 * dp], a, b[0], b[1]);
+      mma_16816(acc[2 * dp + 1], a, b[2], b[3]);
     }
   }
 }
-
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -222,10 +236,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   const int group = warp / WPG, wig = warp % WPG;
   const int gq = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * GROUPS + group;
-  const size_t group_bytes = (size_t)(n_pad * KROW + DH * tstride) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
-  __nv_bfloat16* sVt = sK + n_pad * KROW;
-  int* sMask = reinterpret_cast<int*>(sVt + DH * tstride);   // 1 = key is masked out (only when MASK)
+  __nv_bfloat16* sV = sK + n_pad * KROW;
+  int* sMask = reinterpret_cast<int*>(sV + n_pad * KROW);   // 1 = key is masked out (only when MASK)
   const bool active = item < (long long)a.num_seqs * a.heads;
   const int head = active ? (int)(item % a.heads) : 0;
   const int seq = active ? (int)(item / a.heads) : 0;
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.o);
   if (active) {
     load_rows<DH>(sK, k, a.ldk, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
-    load_rows_t<DH>(sVt, tstride, v, a.ldv, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
+    load_rows<DH>(sV, v, a.ldv, head, g, seq, n_pad, wig * 32 + lane, WPG * 32);
     if (MASK)
       for (int i = wig * 32 + lane; i < n_pad; i += WPG * 32)
         sMask[i] = (i < a.n && a.key_mask[(long long)seq * a.n + i] != 0) ? 0 : 1;
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
         oacc[dt][2] *= corr_b; oacc[dt][3] *= corr_b;
       }
       // masked / beyond-n_pad keys carry p == 0 and V^T rows are zero-filled there
-      pv_block<8, DH>(oacc, s, sVt, tstride, key0, lane, ntv);
+      pv_block<8, DH>(oacc, s, sV, key0, lane, ntv);
     }
     l_a = quad_sum(l_a);
     l_b = quad_sum(l_b);
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
 // backward, part 1 (query-row parallel): dq_hat.   dlogits = P * (dP - delta), dq = scale * dlogits K
 // ------------------------------------------------------------------------------------------------
 template <int DH, int WPG, int GROUPS, bool MASK>
-__global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_attn_args a) {
+__global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1) attn_bwd_dq_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
   const int n_pad = (a.n + 15) & ~15;
@@ -334,11 +348,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
   const int group = warp / WPG, wig = warp % WPG;
   const int gq = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * GROUPS + group;
-  const size_t group_bytes = (size_t)(2 * n_pad * KROW + DH * tstride) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW) * 2 + (MASK ? (size_t)n_pad * 4 : 0);
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
   __nv_bfloat16* sV = sK + n_pad * KROW;
-  __nv_bfloat16* sKt = sV + n_pad * KROW;
-  int* sMask = reinterpret_cast<int*>(sKt + DH * tstride);
+  int* sMask = reinterpret_cast<int*>(sV + n_pad * KROW);
   const bool active = item < (long long)a.num_seqs * a.heads;
   const int head = active ? (int)(item % a.heads) : 0;
   const int seq = active ? (int)(item / a.heads) : 0;
@@ -352,7 +365,6 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
     const int tid = wig * 32 + lane;
     load_rows<DH>(sK, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
     load_rows<DH>(sV, v, a.ldv, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t<DH>(sKt, tstride, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
     if (MASK)
       for (int i = tid; i < n_pad; i += WPG * 32)
         sMask[i] = (i < a.n && a.key_mask[(long long)seq * a.n + i] != 0) ? 0 : 1;
@@ -397,7 +409,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dq_kernel(ctclip_at
           s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;          // d(q_hat . k_hat)
         }
       }
-      pv_block<4, DH>(dqa, s, sKt, tstride, key0, lane, ntv);
+      pv_block<4, DH>(dqa, s, sK, key0, lane, ntv);
     }
     if (ra < a.n) {
       __nv_bfloat16* orow = dq + g.row(seq, ra) * a.ld_dq + head * DH + 2 * t;
@@ -426,12 +438,10 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
   const int group = warp / WPG, wig = warp % WPG;
   const int gq = lane >> 2, t = lane & 3;
   const long long item = (long long)blockIdx.x * GROUPS + group;
-  const size_t group_bytes = (size_t)(2 * n_pad * KROW + 2 * DH * tstride) * 2 + (size_t)n_pad * 8;
+  const size_t group_bytes = (size_t)(2 * n_pad * KROW) * 2 + (size_t)n_pad * 8;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn + group * group_bytes);
   __nv_bfloat16* sDO = sQ + n_pad * KROW;
-  __nv_bfloat16* sQt = sDO + n_pad * KROW;
-  __nv_bfloat16* sDOt = sQt + DH * tstride;
-  float* sLse = reinterpret_cast<float*>(sDOt + DH * tstride);
+  float* sLse = reinterpret_cast<float*>(sDO + n_pad * KROW);
   float* sDel = sLse + n_pad;
   const bool active = item < (long long)a.num_seqs * a.heads;
   const int head = active ? (int)(item % a.heads) : 0;
@@ -447,8 +457,6 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
     const int tid = wig * 32 + lane;
     load_rows<DH>(sQ, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
     load_rows<DH>(sDO, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t<DH>(sQt, tstride, q, a.ldq, head, g, seq, n_pad, tid, WPG * 32);
-    load_rows_t<DH>(sDOt, tstride, dO, a.ldo, head, g, seq, n_pad, tid, WPG * 32);
     for (int i = tid; i < n_pad; i += WPG * 32) {
       sLse[i] = i < a.n ? a.lse[g.row(seq, i) * a.heads + head] : 0.f;
       sDel[i] = i < a.n ? a.delta[g.row(seq, i) * a.heads + head] : 0.f;
@@ -508,8 +516,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
           ds[nt][e] = p * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * a.scale;         // dS^T (w.r.t. q_hat.k_hat)
         }
       }
-      pv_block<4, DH>(dva, s, sDOt, tstride, q0, lane, ntv);
-      pv_block<4, DH>(dka, ds, sQt, tstride, q0, lane, ntv);
+      pv_block<4, DH>(dva, s, sDO, q0, lane, ntv);
+      pv_block<4, DH>(dka, ds, sQ, q0, lane, ntv);
     }
     if (ka_ < a.n) {
       __nv_bfloat16* r1 = dk + g.row(seq, ka_) * a.ld_dk + head * DH + 2 * t;
@@ -766,11 +774,10 @@ static int launch_grouped(Kern kern, const ctclip_attn_args* a, size_t group_byt
 template <int DH, bool MASK>
 static int attn_dispatch(int which, const ctclip_attn_args* a, cudaStream_t stream) {
   const int n_pad = (a->n + 15) & ~15;
-  const int ts = n_pad + 8;
   const size_t mk = MASK ? (size_t)n_pad * 4 : 0;
-  const size_t gb_fwd = (size_t)(n_pad * (DH + 8) + DH * ts) * 2 + mk;
-  const size_t gb_dq = (size_t)(2 * n_pad * (DH + 8) + DH * ts) * 2 + mk;
-  const size_t gb_dkv = (size_t)(2 * n_pad * (DH + 8) + 2 * DH * ts) * 2 + (size_t)n_pad * 8;
+  const size_t gb_fwd = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk;
+  const size_t gb_dq = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk;
+  const size_t gb_dkv = (size_t)(2 * n_pad * (DH + 8)) * 2 + (size_t)n_pad * 8;
   if (a->n <= 64) {
     if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 1, 8, MASK>, a, gb_fwd, 1, 8, stream);
     if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 1, 8, MASK>, a, gb_dq, 1, 8, stream);
@@ -781,8 +788,8 @@ static int attn_dispatch(int which, const ctclip_attn_args* a, cudaStream_t stre
     if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 4, 2, MASK>, a, gb_dq, 4, 2, stream);
     return launch_grouped(attn_bwd_dkv_kernel<DH, 4, 2, MASK>, a, gb_dkv, 4, 2, stream);
   }
-  if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 9, 1, MASK>, a, gb_fwd, 9, 1, stream);
-  if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 12, 1, MASK>, a, gb_dq, 12, 1, stream);
+  if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 8, 1, MASK>, a, gb_fwd, 8, 1, stream);   // 128 regs, 2 CTAs / SM
+  if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 8, 1, MASK>, a, gb_dq, 8, 1, stream);   // 2 CTAs / SM
   return launch_grouped(attn_bwd_dkv_kernel<DH, 12, 1, MASK>, a, gb_dkv, 12, 1, stream);
 }
 
