@@ -257,16 +257,18 @@ def run_b200(args):
 def cpu_baseline(args, sample_volumes=1, timed_steps=1, sample_frames=None):
     """The reference algorithm's CPU PyTorch path (oracle port: the Python reference itself cannot travel to the GPU
     box) on the host cores: forward + loss + backward. BOUNDED SAMPLE: `sample_volumes` slabs of `sample_frames` frames
-    (default: 4 token planes = 1/6 of a 240-frame volume) through the full-width, full-depth model; every per-token cost
+    (default: 2 token planes = 1/12 of a 240-frame volume) through the full-width, full-depth model; every per-token cost
     (patch embed, PEG, spatial attention over the complete 24x24 grid, feed-forward, VQ) is exercised at full size, only
     the temporal extent is cropped, and the result is scaled to whole volumes."""
     from oracle import ctclip_oracle as O
-    cores = os.cpu_count() or 1
+    # torch's CPU eager kernels stop scaling (and then regress) beyond a few tens of threads on these shapes: measured on
+    # the 128-core bench host, the 128-thread run was 3x slower than an 8-thread run. Use min(cores, 32) threads and say so.
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     p = args.image // 24 if args.image % 24 == 0 else 16
     pt = args.frames // 24 if args.frames % 24 == 0 else 8
     if sample_frames is None:
-        sample_frames = min(args.frames, 4 * pt)
+        sample_frames = min(args.frames, 2 * pt)
     cfg = O.CTCLIPConfig(vit=O.CTViTConfig(image_size=args.image, patch_size=p, temporal_patch_size=pt, spatial_depth=args.depth,
                                            temporal_depth=args.depth), bert=O.BertConfigLite(layers=args.bert_layers))
     shapes = oracle_shapes(cfg)
@@ -340,7 +342,7 @@ def run_reference(args):
         sample = r["sample"]
     ms = 1e3 * sum(t_all) / len(t_all)
     val = sum(vals) / len(vals)
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)
     out = {"impl": "reference", "metric": "CT volumes/sec contrastive step @ 480x480x240, bs8/GPU", "value": val,
            "unit": "volumes/s", "n_gpus": args.gpus, "steps": len(t_all), "warmup": min(args.warmup, 1), "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

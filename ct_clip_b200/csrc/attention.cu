@@ -103,13 +103,13 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
 
 // C[16 x 8*NT] = A[16 x DH] * rows(tile)[key0 .. key0+8*NT)^T  with tile row-major [key][KROW].
 // B fragments via ldmatrix.x4: one instruction yields (b0,b1) of two consecutive 16-wide k-steps of one n-tile.
-template <int NT, int DH>
+template <int NT, int DH, bool FULL = false>
 __device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[DH / 16][4],
                                          const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) {
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    if (nt >= nt_valid) continue;  // warp-uniform; tiles beyond the padded sequence stay zero
+    if (!FULL && nt >= nt_valid) continue;  // warp-uniform; tiles beyond the padded sequence stay zero
     const __nv_bfloat16* base = tile + (key0 + nt * 8 + (lane & 7)) * KROW + (lane >> 3) * 8;
 #pragma unroll
     for (int kp = 0; kp < DH / 32; kp++) {
@@ -123,12 +123,12 @@ __device__ __forceinline__ void qk_block(float (&s)[NT][4], const uint32_t (&a)[
 // acc[16 x DH] += P[16 x 8*NT] * X[key0 .. key0+8*NT, :]  with X row-major [key][KROW] (the same tile layout as above):
 // ldmatrix.x4.trans delivers the (k = key, n = d) B fragments straight from the row-major tile, so no transposed copy of
 // V / K / Q / dO is kept in shared memory.
-template <int NT, int DH>
+template <int NT, int DH, bool FULL = false>
 __device__ __forceinline__ void pv_block(float (&acc)[DH / 8][4], const float (&p)[NT][4],
                                          const __nv_bfloat16* tile, int key0, int lane, int nt_valid = NT) {
 #pragma unroll
   for (int kk = 0; kk < NT / 2; kk++) {
-    if (2 * kk >= nt_valid) continue;
+    if (!FULL && 2 * kk >= nt_valid) continue;
     uint32_t a[4];
     a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
     a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
@@ -214,6 +214,32 @@ __device__ __forceinline__ void logits_tile(float (&s)[NT][4], float sc2, const 
   }
 }
 
+// Branch-free variant for blocks that lie completely inside the sequence and carry no key mask (every block of the
+// 576-token spatial sequences): logits = s*sc2 (+ fragment-ordered bias * log2 e).
+template <int NT>
+__device__ __forceinline__ void logits_tile_full(float (&s)[NT][4], float sc2, const uint2* bfrag) {
+  if (bfrag != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NT / 2; i++) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
+      const float2 a0 = unpack_bf16x2(u.x), b0 = unpack_bf16x2(u.y), a1 = unpack_bf16x2(u.z), b1 = unpack_bf16x2(u.w);
+      s[2 * i][0] = fmaf(s[2 * i][0], sc2, a0.x * kLog2e);
+      s[2 * i][1] = fmaf(s[2 * i][1], sc2, a0.y * kLog2e);
+      s[2 * i][2] = fmaf(s[2 * i][2], sc2, b0.x * kLog2e);
+      s[2 * i][3] = fmaf(s[2 * i][3], sc2, b0.y * kLog2e);
+      s[2 * i + 1][0] = fmaf(s[2 * i + 1][0], sc2, a1.x * kLog2e);
+      s[2 * i + 1][1] = fmaf(s[2 * i + 1][1], sc2, a1.y * kLog2e);
+      s[2 * i + 1][2] = fmaf(s[2 * i + 1][2], sc2, b1.x * kLog2e);
+      s[2 * i + 1][3] = fmaf(s[2 * i + 1][3], sc2, b1.y * kLog2e);
+    }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      s[nt][0] *= sc2; s[nt][1] *= sc2; s[nt][2] *= sc2; s[nt][3] *= sc2;
+    }
+  }
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -277,10 +303,16 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       float s[8][4];
       const int rem = n_pad - key0;  // multiple of 16
       const int ntv = rem >= 64 ? 8 : rem / 8;
-      qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
       const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8
                                    : nullptr;
-      logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv, bfr);
+      const bool full = !MASK && (key0 + 64 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
+      if (full) {
+        qk_block<8, DH, true>(s, qa, sK, key0, lane);
+        logits_tile_full<8>(s, sc2, bfr);
+      } else {
+        qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
+        logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv, bfr);
+      }
       float bm_a = -INFINITY, bm_b = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
@@ -313,7 +345,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
         oacc[dt][2] *= corr_b; oacc[dt][3] *= corr_b;
       }
       // masked / beyond-n_pad keys carry p == 0 and V^T rows are zero-filled there
-      pv_block<8, DH>(oacc, s, sV, key0, lane, ntv);
+      if (full) pv_block<8, DH, true>(oacc, s, sV, key0, lane);
+      else pv_block<8, DH>(oacc, s, sV, key0, lane, ntv);
     }
     l_a = quad_sum(l_a);
     l_b = quad_sum(l_b);
@@ -395,12 +428,19 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
       float s[4][4], dp[4][4];
       const int rem = n_pad - key0;
       const int ntv = rem >= 32 ? 4 : 2;
-      qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
-      qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
       const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8 +
                                          ((key0 >> 5) & 1) * 4
                                    : nullptr;
-      logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv, bfr);
+      const bool full = !MASK && (key0 + 32 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
+      if (full) {
+        qk_block<4, DH, true>(s, qa, sK, key0, lane);
+        qk_block<4, DH, true>(dp, da, sV, key0, lane);
+        logits_tile_full<4>(s, sc2, bfr);
+      } else {
+        qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
+        qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
+        logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv, bfr);
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
@@ -409,7 +449,8 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
           s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b)) * a.scale;          // d(q_hat . k_hat)
         }
       }
-      pv_block<4, DH>(dqa, s, sK, key0, lane, ntv);
+      if (full) pv_block<4, DH, true>(dqa, s, sK, key0, lane);
+      else pv_block<4, DH>(dqa, s, sK, key0, lane, ntv);
     }
     if (ra < a.n) {
       __nv_bfloat16* orow = dq + g.row(seq, ra) * a.ld_dq + head * DH + 2 * t;
@@ -492,13 +533,20 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       float s[4][4], dp[4][4];
       const int rem = n_pad - q0;
       const int ntv = rem >= 32 ? 4 : 2;
-      qk_block<4, DH>(s, ka, sQ, q0, lane, ntv);
-      qk_block<4, DH>(dp, va, sDO, q0, lane, ntv);
+      const bool full = (q0 + 32 <= a.n) && (biasT == nullptr || bias_t_frag != nullptr);   // warp-uniform
+      if (full) {
+        qk_block<4, DH, true>(s, ka, sQ, q0, lane);
+        qk_block<4, DH, true>(dp, va, sDO, q0, lane);
+      } else {
+        qk_block<4, DH>(s, ka, sQ, q0, lane, ntv);
+        qk_block<4, DH>(dp, va, sDO, q0, lane, ntv);
+      }
       // columns of this block are queries: mask columns >= n; masked / out-of-range key rows via keep_a / keep_b
       const uint2* bfr = bias_t_frag ? bias_t_frag + ((((long long)head * key_tiles + kt_) * qblocks + (q0 >> 6)) * 32 + lane) * 8 +
                                            ((q0 >> 5) & 1) * 4
                                      : nullptr;
-      logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
+      if (full) logits_tile_full<4>(s, sc2, bfr);
+      else logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
       float ds[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
@@ -516,8 +564,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
           ds[nt][e] = p * (dp[nt][e] - ((e & 1) ? d2.y : d2.x)) * a.scale;         // dS^T (w.r.t. q_hat.k_hat)
         }
       }
-      pv_block<4, DH>(dva, s, sDO, q0, lane, ntv);
-      pv_block<4, DH>(dka, ds, sQ, q0, lane, ntv);
+      if (full) {
+        pv_block<4, DH, true>(dva, s, sDO, q0, lane);
+        pv_block<4, DH, true>(dka, ds, sQ, q0, lane);
+      } else {
+        pv_block<4, DH>(dva, s, sDO, q0, lane, ntv);
+        pv_block<4, DH>(dka, ds, sQ, q0, lane, ntv);
+      }
     }
     if (ka_ < a.n) {
       __nv_bfloat16* r1 = dk + g.row(seq, ka_) * a.ld_dk + head * DH + 2 * t;

@@ -42,6 +42,7 @@ struct GemmKParams {
   float* argval_out;
   int norm_cols;
   const float* norm_scale;
+  int fast_store;  // all output / residual rows are 16-byte aligned: staged, fully coalesced epilogue stores
 };
 
 template <int BN>
@@ -50,7 +51,8 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*argmax merge*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*argmax merge*/ +
+                                    EPI_WARPS * 2048 /*epilogue store staging*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
@@ -64,6 +66,105 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
     u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
     d4[i] = u;
   }
+}
+
+// ---- epilogue store staging -------------------------------------------------------------------------------------
+// After tcgen05.ld every thread owns ONE row (32 consecutive columns). Storing that directly makes each warp-wide
+// 16-byte store touch 32 different rows = 32 half-filled 32-byte sectors, and the L2 write path (not the MMA) bounds
+// the K=512 GEMMs. Each epilogue warp therefore bounces its 32 x 64 B block through a private 2 KB shared-memory
+// buffer (16-byte pieces XOR-swizzled so that both directions are bank-conflict free) and writes it back with 4
+// consecutive lanes covering 64 contiguous bytes of one row: full sectors, 8 rows per instruction.
+__device__ __forceinline__ void stage_put(uint8_t* st, int lane, int piece, const uint4& u) {
+  *reinterpret_cast<uint4*>(st + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)) = u;
+}
+__device__ __forceinline__ uint4 stage_get(const uint8_t* st, int r, int piece) {
+  return *reinterpret_cast<const uint4*>(st + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
+}
+// 32 rows x 32 bf16: base -> element (first row of the warp, col0); ld in elements
+__device__ __forceinline__ void staged_store_bf16(uint8_t* st, int lane, const float (&v)[32], __nv_bfloat16* base,
+                                                  long long ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    stage_put(st, lane, i, u);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const int r = it * 8 + (lane >> 2), pc = lane & 3;
+    const uint4 u = stage_get(st, r, pc);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(base + (long long)r * ld + pc * 8) = u;
+  }
+  __syncwarp();
+}
+// 32 rows x 16 bf16 (32 B per row): two lanes per row
+__device__ __forceinline__ void staged_store_bf16_half(uint8_t* st, int lane, const float (&g)[16], __nv_bfloat16* base,
+                                                       long long ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    uint4 u;
+    u.x = pack_bf16x2(g[8 * i + 0], g[8 * i + 1]);
+    u.y = pack_bf16x2(g[8 * i + 2], g[8 * i + 3]);
+    u.z = pack_bf16x2(g[8 * i + 4], g[8 * i + 5]);
+    u.w = pack_bf16x2(g[8 * i + 6], g[8 * i + 7]);
+    stage_put(st, lane, i, u);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int r = it * 16 + (lane >> 1), pc = lane & 1;
+    const uint4 u = stage_get(st, r, pc);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(base + (long long)r * ld + pc * 8) = u;
+  }
+  __syncwarp();
+}
+// 32 rows x 32 fp32 (+ optional residual), in two 16-column halves. rbuf: residual values already loaded in the
+// transposed ownership (rbuf[h*4 + it] belongs to row it*8 + lane/4, columns h*16 + (lane%4)*4 ..), or nullptr to load here.
+__device__ __forceinline__ void staged_store_f32(uint8_t* st, int lane, const float (&v)[32], float* base, long long ld,
+                                                 const float* rbase, long long ldr, const float4* rbuf, int rows_valid) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 u;
+      u.x = __float_as_uint(v[16 * h + 4 * i + 0]);
+      u.y = __float_as_uint(v[16 * h + 4 * i + 1]);
+      u.z = __float_as_uint(v[16 * h + 4 * i + 2]);
+      u.w = __float_as_uint(v[16 * h + 4 * i + 3]);
+      stage_put(st, lane, i, u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int r = it * 8 + (lane >> 2), pc = lane & 3;
+      const uint4 u = stage_get(st, r, pc);
+      float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+      if (r < rows_valid) {
+        if (rbase != nullptr) {
+          const float4 rr = (rbuf != nullptr) ? rbuf[h * 4 + it]
+                                              : *reinterpret_cast<const float4*>(rbase + (long long)r * ldr + h * 16 + pc * 4);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(base + (long long)r * ld + h * 16 + pc * 4) = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+// residual prefetch in the transposed ownership used by staged_store_f32
+__device__ __forceinline__ void resid_prefetch(float4 (&buf)[8], const float* rbase, long long ldr, int lane, int rows_valid) {
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int r = it * 8 + (lane >> 2), pc = lane & 3;
+      buf[h * 4 + it] = (r < rows_valid) ? *reinterpret_cast<const float4*>(rbase + (long long)r * ldr + h * 16 + pc * 4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 template <int BN, int AMAJ, int BMAJ>
@@ -84,6 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* arg_merge = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [128][2] (value, index)
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(bars) + 256 + 1024;                     // [EPI_WARPS][2048]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,6 +303,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int m_blk = rest % p.m_blks;
       const long long row = (long long)m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      const long long row0 = (long long)m_blk * BM + q * 32;   // first row of this warp
+      const int rows_valid = (int)max(0LL, min(32LL, (long long)p.M - row0));
+      uint8_t* st = stage_all + (warp - 2) * 2048;
       float best_v = -INFINITY;
       int best_i = 0;
       for (int j = 0; j < p.n_per_unit; j++, it++) {
@@ -209,14 +314,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t acc_phase = (it >> 1) & 1;
         // RESID_F32: the residual tile is prefetched one chunk ahead (the first chunk while the MMAs of this tile are
         // still in flight) -- these epilogues are HBM-latency-bound otherwise
-        const bool pf = (p.epi == EPI_RESID_F32) && row_ok && (p.N % 32 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.resid) | (uintptr_t)(p.ldr * 4)) & 15) == 0;
+        // staged (coalesced) stores need 16-byte aligned rows and whole 32-column chunks
+        const bool fast = p.fast_store && (p.N % 32 == 0);
+        const bool pf = (p.epi == EPI_RESID_F32) && fast;
         float4 rnext[8];
-        if (pf && n_blk * BN + half * 32 < p.N) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldr + n_blk * BN + half * 32);
-#pragma unroll
-          for (int i = 0; i < 8; i++) rnext[i] = rp[i];
-        }
+        if (pf && n_blk * BN + half * 32 < p.N)
+          resid_prefetch(rnext, p.resid + row0 * p.ldr + n_blk * BN + half * 32, p.ldr, lane, rows_valid);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -231,11 +334,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; i++) rcur[i] = rnext[i];
             const int cn = c + EPI_WARPS / 4;
-            if (cn < BN / 32 && n_blk * BN + cn * 32 < p.N) {
-              const float4* rp = reinterpret_cast<const float4*>(p.resid + row * p.ldr + n_blk * BN + cn * 32);
-#pragma unroll
-              for (int i = 0; i < 8; i++) rnext[i] = rp[i];
-            }
+            if (cn < BN / 32 && n_blk * BN + cn * 32 < p.N)
+              resid_prefetch(rnext, p.resid + row0 * p.ldr + n_blk * BN + cn * 32, p.ldr, lane, rows_valid);
           }
           tmem_ld_wait();
           float v[32];
@@ -262,6 +362,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (i < ncols && v[i] > best_v) { best_v = v[i]; best_i = col0 + i; }
             continue;
           }
+          if (fast) {   // warp-uniform: every lane takes part in the shared-memory bounce
+            if (p.epi == EPI_BF16) {
+              staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+            } else if (p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+              staged_store_f32(st, lane, v, reinterpret_cast<float*>(p.C) + row0 * p.ldc + col0, p.ldc,
+                               (p.epi == EPI_RESID_F32) ? p.resid + row0 * p.ldr + col0 : nullptr, p.ldr, pf ? rcur : nullptr,
+                               rows_valid);
+            } else if (p.epi == EPI_GEGLU) {
+              if (p.C != nullptr)
+                staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+              float g[16];
+#pragma unroll
+              for (int i = 0; i < 16; i++) g[i] = gelu_erf_fast(v[2 * i + 1]) * v[2 * i];
+              staged_store_bf16_half(st, lane, g, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + (col0 >> 1), p.ldc2,
+                                     rows_valid);
+            } else if (p.epi == EPI_L2NORM) {
+              if (p.C != nullptr)
+                staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+              if (col0 < p.norm_cols) {
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i++) ss += v[i] * v[i];
+                const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = v[i] * inv * __ldg(p.norm_scale + i);
+                staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + col0, p.ldc2, rows_valid);
+              }
+            } else if (p.epi == EPI_BIAS_GELU) {
+              if (p.C2 != nullptr)
+                staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + col0, p.ldc2, rows_valid);
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] = gelu_erf_fast(v[i]);
+              staged_store_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+            }
+            if (p.epi != EPI_ATOMIC_F32) continue;
+          }
           if (!row_ok) continue;
           if (p.epi == EPI_BF16) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
@@ -282,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < 8; i++) {
                 float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 if (rs != nullptr) {
-                  const float4 r = pf ? rcur[i] : *reinterpret_cast<const float4*>(rs + 4 * i);
+                  const float4 r = *reinterpret_cast<const float4*>(rs + 4 * i);
                   o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
                 *reinterpret_cast<float4*>(dst + 4 * i) = o;
@@ -481,6 +617,16 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   p.C2 = a->C2; p.ldc2 = a->ldc2;
   p.arg_out = a->arg_out; p.argval_out = a->argval_out;
   p.norm_cols = a->norm_cols; p.norm_scale = a->norm_scale;
+  {
+    const bool out_f32 = (a->epilogue == EPI_F32 || a->epilogue == EPI_RESID_F32);
+    const int esz = out_f32 ? 4 : 2;
+    bool ok = a->epilogue != EPI_ARGMAX && a->epilogue != EPI_ATOMIC_F32;
+    if (ok && a->C != nullptr) ok = ((uintptr_t)a->C % 16 == 0) && ((a->ldc * esz) % 16 == 0);
+    if (ok && a->C2 != nullptr) ok = ((uintptr_t)a->C2 % 16 == 0) && ((a->ldc2 * 2) % 16 == 0);
+    if (ok && a->epilogue == EPI_RESID_F32) ok = ((uintptr_t)a->resid % 16 == 0) && ((a->ldr * 4) % 16 == 0);
+    if (ok && a->epilogue == EPI_GEGLU) ok = (a->N % 64 == 0);   // 16-column halves of C2 stay 16-byte aligned
+    p.fast_store = ok ? 1 : 0;
+  }
 
   // Tile-N selection: 256 where it divides N (fewest B re-reads per MMA), else 128, 64 for tiny N.
   int bn;

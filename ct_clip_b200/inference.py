@@ -70,15 +70,15 @@ class CTClipInference(nn.Module):
     @torch.no_grad()
     def infer(self, log_fn=lambda logs: None):
         self.CTClip.eval()
+        from . import ops
         text_lat = self.CTClip.encode_text_latents(self._bank())              # (36, L), once
-        temp = self.CTClip.temperature.exp()
         predicted, real, names = [], [], []
         for batch in self.dl:
             vol = batch[0].to(self.device, non_blocking=True)
             img_lat = self.CTClip.encode_image_latents(vol)                     # (b, L), one image pass per volume
-            sims = (img_lat @ text_lat.t()) * temp                              # (b, 36): tiny epilogue on the latents
-            probs = sims.view(-1, len(PATHOLOGIES), 2).softmax(dim=-1)[..., 0]  # zero_shot.py:140-143
-            predicted.append(probs.float().cpu().numpy())
+            probs = torch.empty(vol.shape[0], len(PATHOLOGIES), device=self.device)
+            ops.zero_shot_probs(img_lat, text_lat, self.CTClip.temperature, probs)   # sims * exp(T) + pair softmax (zero_shot.py:140-143)
+            predicted.append(probs.cpu().numpy())
             if len(batch) > 2:
                 real.append(np.asarray(batch[2]).reshape(vol.shape[0], -1))
             if len(batch) > 3:

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Data-parallel parity check on real GPUs (launch with torchrun --nproc-per-node W):
+every rank trains one step on its shard of a global batch through CTClipTrainer (NCCL all-gather of latents, SUM
+all-reduce of the gradient arena, EMA statistics all-reduce); rank 0 then repeats the step single-process on the
+whole global batch with identically initialised weights and compares loss and updated parameters."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+
+
+def build(seed=0):
+    from transformers import BertConfig, BertModel
+
+    from ct_clip_b200 import CTCLIP, CTViT
+    from oracle import ctclip_oracle as O
+    vit = CTViT(dim=512, codebook_size=1024, image_size=64, patch_size=16, temporal_patch_size=8, spatial_depth=1, temporal_depth=1,
+                dim_head=32, heads=8)
+    bert = BertModel(BertConfig(num_hidden_layers=1, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=16 * 512, dim_latent=512)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in clip.state_dict().items()}, seed)
+    clip.load_state_dict(sd, strict=True)
+    return clip
+
+
+def main():
+    from ct_clip_b200.data import SyntheticCTReportDataset
+    from ct_clip_b200.trainer import CTClipTrainer, _Tokens
+    from oracle import ctclip_oracle as O
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    b = 2
+    hu, ids, mask = O.synth_inputs(world * b, 32, 64, 32)
+    ds = SyntheticCTReportDataset(8, frames=32, image=64, n_text=32)
+    tr = CTClipTrainer(build(), num_train_steps=1, batch_size=b, train_dataset=ds, num_workers=0, lr=1e-3, save_model_every=0,
+                       results_folder="/tmp/dpcheck")
+    dev = tr.device
+    sl = slice(rank * b, (rank + 1) * b)
+    loss = tr.step_on_batch(hu[sl].to(dev), _Tokens(ids[sl].to(dev), mask[sl].to(dev)))
+    torch.cuda.synchronize()
+    after_dp = {k: v.detach().clone() for k, v in tr.CTClip.named_parameters()}
+    emb_dp = tr.CTClip.visual_transformer.vq._codebook.embed.detach().clone()
+    loss_dp = loss.item()
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        os.environ["WORLD_SIZE"], os.environ["RANK"] = "1", "0"
+        tr1 = CTClipTrainer(build(), num_train_steps=1, batch_size=world * b, train_dataset=ds, num_workers=0, lr=1e-3,
+                            save_model_every=0, results_folder="/tmp/dpcheck1")
+        tr1.world, tr1.CTClip.dp_world = 1, 1
+        loss1 = tr1.step_on_batch(hu.to(dev), _Tokens(ids.to(dev), mask.to(dev)))
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k, v in tr1.CTClip.named_parameters():
+            d = (v.detach() - after_dp[k]).abs().max().item()
+            worst = max(worst, d)
+        emb_d = (tr1.CTClip.visual_transformer.vq._codebook.embed - emb_dp).abs().max().item()
+        print(f"dp_check world={world}: loss dp {loss_dp:.6f} vs single {loss1.item():.6f}; max |param diff| after one step "
+              f"{worst:.3e} (lr 1e-3); code-book EMA max diff {emb_d:.3e}")
+        # Adam's first step moves every element by ~lr*sign(g): sign flips of near-zero gradients are the only differences
+        ok = abs(loss_dp - loss1.item()) < 2e-3 * abs(loss1.item()) and worst <= 2.1e-3 and emb_d < 1e-2
+        print("DP_CHECK", "PASS" if ok else "FAIL")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
