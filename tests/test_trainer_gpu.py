@@ -25,7 +25,9 @@ def test_trainer_step_matches_oracle_adam(tmp_path):
     sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
     out["loss"].backward()
-    live = [k for k, v in sdp.items() if v.is_floating_point() and v.grad is not None and not k.endswith("_extra.weight")]
+    trainable = {k for k, _ in clip.named_parameters()}     # buffers (LayerNorm.beta, attention.py:32; code-book) are not trained
+    live = [k for k, v in sdp.items() if v.is_floating_point() and v.grad is not None and not k.endswith("_extra.weight")
+            and k in trainable]
     ps = [torch.nn.Parameter(sd[k].clone()) for k in live]
     for p_, k in zip(ps, live):
         p_.grad = sdp[k].grad.clone()
