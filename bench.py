@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--text-len", type=int, default=128)
     ap.add_argument("--bert-layers", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the per-stage roofline pass (one extra untimed step)")
     ap.add_argument("--cpu-sample-volumes", type=int, default=2)
     return ap.parse_args()
 
@@ -94,6 +95,39 @@ class ClockSampler:
         sm.sort()
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None), reasons=sorted(reasons),
                     samples=len(sm))
+
+
+def stage_table(rec, peaks):
+    """Aggregate (entry point, tag) -> [stage, launches, ms, bound, achieved, unit, frac] from one instrumented step.
+    HBM-bound stages are rated against the measured copy bandwidth, tensor stages against the measured sustained bf16 rate."""
+    agg = {}
+    for name, tag, work, e0, e1 in rec:
+        key = (name.replace("ctclip_", ""), tag or "", work[0] if work else "")
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+        a[2] += work[1] if work else 0.0
+    rows = []
+    for (name, tag, kind), (n, t_ms, w) in agg.items():
+        if kind == "B":
+            ach, unit, peak, bound = w / (t_ms * 1e-3) / 1e9, "GB/s", peaks["hbm"], "hbm"
+        elif kind == "F":
+            ach, unit, peak, bound = w / (t_ms * 1e-3) / 1e12, "TFLOP/s", peaks["tf_sus"], "tensor"
+        else:
+            ach, unit, peak, bound = 0.0, "", 1.0, "latency"
+        rows.append([f"{name} [{tag}]" if tag else name, n, t_ms, bound, ach, unit, ach / peak if peak else 0.0])
+    rows.sort(key=lambda r: -r[2])
+    return rows
+
+
+def write_stage_table(path, rows, step_ms):
+    tot = sum(r[2] for r in rows)
+    with open(path, "w") as f:
+        f.write(f"# per-stage roofline, one instrumented step (CUDA events around every C-ABI call; sum {tot:.1f} ms, "
+                f"un-instrumented step {step_ms:.1f} ms)\n")
+        f.write("| stage (entry point [tag]) | launches | ms/step | share | bound | achieved | of measured peak |\n|---|---|---|---|---|---|---|\n")
+        for r in rows:
+            f.write(f"| {r[0]} | {r[1]} | {r[2]:.3f} | {100 * r[2] / tot:.1f}% | {r[3]} | {r[4]:.1f} {r[5]} | {100 * r[6]:.1f}% |\n")
 
 
 def flops_per_volume(cfgd):
@@ -162,8 +196,10 @@ def run_b200(args):
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for s in range(args.steps):
         loss = trainer.step_on_batch(*dev[s % 2])
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / max(1, args.steps)   # CPU time to enqueue one step (no sync)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -193,6 +229,17 @@ def run_b200(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # ---- per-stage pass (untimed for the headline): CUDA events around every C-ABI call of ONE extra step
+    stage_rows = None
+    if rank == 0 and not args.no_stages:
+        rec = []
+        _lib.STAGE_TIMER = rec
+        trainer.step_on_batch(*dev[0])
+        torch.cuda.synchronize()
+        _lib.STAGE_TIMER = None
+        stage_rows = stage_table(rec, load_peaks())
+        if os.environ.get("CTCLIP_BENCH_STAGE_TABLE"):
+            write_stage_table(os.environ["CTCLIP_BENCH_STAGE_TABLE"], stage_rows, ms / args.steps)
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -217,6 +264,13 @@ def run_b200(args):
                 f.write(f"{shp} | {c_} {t_:.3f} {fl_ / (t_ * 1e-3) / 1e12 if t_ > 0 else 0:.1f}\n")
     peaks = load_peaks()
     achieved = (gflops / (gsum_ms * 1e-3) / 1e12) if gsum_ms > 0 else 0.0
+    # dominant kernel = the GEMM shape with the largest share of the step (the GEGLU feed-forward GEMM at configs[1])
+    dom_shape, (dom_n, dom_ms, dom_fl) = max(by_shape.items(), key=lambda kv: kv[1][1]) if by_shape else (None, (0, 0.0, 0.0))
+    dom_achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = ROOT / "profiles" / "ncu_traffic.json"
+    if tpath.exists() and dom_shape is not None:
+        traffic = json.loads(tpath.read_text()).get("x".join(str(v) for v in dom_shape[:3]))
     vit = clip.visual_transformer
     g = vit.geom
     T = args.frames // g.temporal_patch
@@ -236,19 +290,28 @@ def run_b200(args):
                                f"BERT-base({args.bert_layers}L, random init), bs{args.batch}/GPU",
                    "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "two alternating input batches of 885 MB each (> 126 MB L2); activations of a step exceed L2 by >100x",
-                   "text_tower": "HF BertModel executed by PyTorch (not yet on the native kernels)",
+                   "text_tower": "BERT-base on the native kernels (ct_clip_b200/bert.py), weights from the injected HF BertModel",
                    "step_tflop_per_volume_algorithmic": step_flops / 1e12},
         "e2e": {"value": vols / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "loss": loss_val,
         "clocks": clocks,
-        "roofline": {"kernel": "gemm_tc_kernel (tcgen05/TMA GEMM family, all instantiations)", "bound": "tensor",
-                     "achieved": achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tf_sus"] if peaks["tf_sus"] else None, "traffic": None,
-                     "peak_source": f"{peaks['src']} bf16_tflops_sustained", "launches_per_step": n_g // max(1, args.steps),
-                     "share_of_step": gsum_ms / ms if ms > 0 else None},
+        "roofline": {"kernel": f"gemm_tc_kernel M,N,K,a_major,b_major,epilogue,splits={dom_shape} (dominant launch shape of the "
+                               "tcgen05/TMA GEMM family)", "bound": "tensor",
+                     "achieved": dom_achieved, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                     "frac": dom_achieved / peaks["tf_sus"] if peaks["tf_sus"] else None, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per launch from profiles/ncu_traffic.json (ncu --set full capture)",
+                     "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches_per_step": dom_n // max(1, args.steps), "share_of_step": dom_ms / ms if ms > 0 else None,
+                     "gemm_family": {"achieved": achieved, "frac": achieved / peaks["tf_sus"] if peaks["tf_sus"] else None,
+                                     "launches_per_step": n_g // max(1, args.steps),
+                                     "share_of_step": gsum_ms / ms if ms > 0 else None}},
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "model_tflops": step_flops * vols / (ms * 1e-3) / 1e12,
     }
+    if stage_rows is not None:
+        out["stages"] = [dict(stage=r[0], launches=r[1], ms=round(r[2], 3), bound=r[3], achieved=round(r[4], 1), unit=r[5],
+                              frac=round(r[6], 3)) for r in stage_rows[:16]]
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_volumes=max(2, args.cpu_sample_volumes), timed_steps=1)
     print(json.dumps(out), flush=True)

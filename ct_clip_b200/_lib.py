@@ -139,10 +139,23 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def call(name: str, *args) -> None:
+# bench.py sets this to a list to collect (entry point, tag, work, start_event, end_event) per call (per-stage roofline
+# table); work = ("B", algorithmic bytes) | ("F", algorithmic flops) | None. Never enabled inside a timed region.
+STAGE_TIMER = None
+
+
+def call(name: str, *args, tag=None, work=None) -> None:
     """Invoke an entry point; raise CtclipError with the library's message on failure."""
     global launch_count
-    rc = getattr(lib(), name)(*args)
+    if STAGE_TIMER is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        STAGE_TIMER.append((name, tag, work, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     launch_count += 1
     if rc != 0:
         msg = lib().ctclip_last_error().decode(errors="replace")

@@ -9,6 +9,7 @@
 // alternate 32-column chunks (the fused epilogues, not the MMA, bound the K=512 GEMMs otherwise).
 //
 // Reference ops replaced: see include/ctclip_b200.h (ctclip_gemm_bf16).
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/ctclip_b200.h"
@@ -43,6 +44,7 @@ struct GemmKParams {
   int norm_cols;
   const float* norm_scale;
   int fast_store;  // all output / residual rows are 16-byte aligned: staged, fully coalesced epilogue stores
+  int fast_epi;    // use the specialised epilogue loops (fast_store && N % 32 == 0 && not ARGMAX / ATOMIC)
 };
 
 template <int BN>
@@ -165,6 +167,222 @@ __device__ __forceinline__ void resid_prefetch(float4 (&buf)[8], const float* rb
       buf[h * 4 + it] = (r < rows_valid) ? *reinterpret_cast<const float4*>(rbase + (long long)r * ldr + h * 16 + pc * 4)
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+
+// ---- fast epilogue (v2) ------------------------------------------------------------------------------------------
+// One specialised loop per epilogue kind (compile-time EPI), entered once per kernel: no per-chunk dispatch, explicit
+// shared-space staging (st/ld.shared with 32-bit addresses; the generic-pointer version compiled to generic LD/ST), the
+// TMEM load of chunk i+1 in flight while chunk i is processed, and the bias row of a chunk fetched ONE chunk ahead by a
+// single coalesced load per warp and broadcast through 128 B of shared memory (v1 issued eight dependent
+// ld.global.nc.v4 per thread right before their first use; that long-scoreboard stall was the top stall of the K=512
+// GEMMs).
+constexpr int EPI_NONE_DEBUG = 8;   // probe: drain the accumulator without storing (mainloop ceiling)
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  return u;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t stg_put_addr(uint32_t st, int lane, int piece) {
+  return st + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint32_t stg_get_addr(uint32_t st, int r, int piece) {
+  return st + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4);
+}
+// make the compiler treat the asynchronously written tcgen05.ld destination registers as redefined here
+__device__ __forceinline__ void reg_fence32(uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i++) asm volatile("" : "+r"(v[i]));
+}
+// 32 rows x 32 bf16 (64 B per row) from one row per thread to 4 lanes per row
+__device__ __forceinline__ void fstore_bf16(uint32_t st, int lane, const float (&v)[32], __nv_bfloat16* base, long long ld,
+                                            int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    sts128(stg_put_addr(st, lane, i), u);
+  }
+  __syncwarp();
+  __nv_bfloat16* dst = base + (long long)(lane >> 2) * ld + (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const int r = it * 8 + (lane >> 2);
+    const uint4 u = lds128(stg_get_addr(st, r, lane & 3));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(dst) = u;
+    dst += 8 * ld;
+  }
+  __syncwarp();
+}
+// 32 rows x 16 bf16 (32 B per row): two lanes per row
+__device__ __forceinline__ void fstore_bf16_half(uint32_t st, int lane, const float (&g)[16], __nv_bfloat16* base,
+                                                 long long ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    uint4 u;
+    u.x = pack_bf16x2(g[8 * i + 0], g[8 * i + 1]);
+    u.y = pack_bf16x2(g[8 * i + 2], g[8 * i + 3]);
+    u.z = pack_bf16x2(g[8 * i + 4], g[8 * i + 5]);
+    u.w = pack_bf16x2(g[8 * i + 6], g[8 * i + 7]);
+    sts128(stg_put_addr(st, lane, i), u);
+  }
+  __syncwarp();
+  __nv_bfloat16* dst = base + (long long)(lane >> 1) * ld + (lane & 1) * 8;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int r = it * 16 + (lane >> 1);
+    const uint4 u = lds128(stg_get_addr(st, r, lane & 1));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(dst) = u;
+    dst += 16 * ld;
+  }
+  __syncwarp();
+}
+// 32 rows x 32 fp32 in two 16-column halves, optional residual already prefetched in the transposed ownership
+template <bool RESID>
+__device__ __forceinline__ void fstore_f32(uint32_t st, int lane, const float (&v)[32], float* base, long long ld,
+                                           const float4 (&rbuf)[8], int rows_valid) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 u;
+      u.x = __float_as_uint(v[16 * h + 4 * i + 0]);
+      u.y = __float_as_uint(v[16 * h + 4 * i + 1]);
+      u.z = __float_as_uint(v[16 * h + 4 * i + 2]);
+      u.w = __float_as_uint(v[16 * h + 4 * i + 3]);
+      sts128(stg_put_addr(st, lane, i), u);
+    }
+    __syncwarp();
+    float* dst = base + (long long)(lane >> 2) * ld + h * 16 + (lane & 3) * 4;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int r = it * 8 + (lane >> 2);
+      const uint4 u = lds128(stg_get_addr(st, r, lane & 3));
+      float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+      if (RESID) {
+        const float4 rr = rbuf[h * 4 + it];
+        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+      }
+      if (r < rows_valid) *reinterpret_cast<float4*>(dst) = o;
+      dst += 8 * ld;
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t st, uint32_t sb, int warp, int lane) {
+  constexpr int NCH = (BN / 32 + 1) / 2;        // 32-column chunks per warp and tile (chunks half, half+2, ...)
+  constexpr bool kResid = (EPI == EPI_RESID_F32);
+  constexpr bool kTmemPrefetch = !kResid;       // RESID keeps its registers for the residual prefetch instead
+  const int q = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const bool has_bias = p.bias != nullptr;
+  uint32_t it = 0;
+  for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, it++) {
+    const int n_blk = unit % p.n_groups;
+    const int m_blk = (unit / p.n_groups) % p.m_blks;
+    const long long row0 = (long long)m_blk * BM + q * 32;
+    const int rows_valid = (int)max(0LL, min(32LL, (long long)p.M - row0));
+    const uint32_t acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const int colbase = n_blk * BN + half * 32;
+    float bnext = 0.f;
+    if (has_bias && colbase < p.N) bnext = __ldg(p.bias + colbase + lane);
+    float4 rnext[8], rcur[8];
+    if (kResid && colbase < p.N) resid_prefetch(rnext, p.resid + row0 * p.ldr + colbase, p.ldr, lane, rows_valid);
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 32;
+    uint32_t raw[2][32];
+    if (colbase < p.N) tmem_ld_32x32(taddr, raw[0]);
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      const int col0 = colbase + i * 64;
+      if (col0 >= p.N) break;   // warp-uniform
+      constexpr int kCurMask = kTmemPrefetch ? 1 : 0;
+      uint32_t(&cur)[32] = raw[i & kCurMask];
+      tmem_ld_wait();
+      reg_fence32(cur);
+      const bool has_next = (i + 1 < NCH) && (col0 + 64 < p.N);
+      if (kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * 64, raw[(i + 1) & 1]);
+      float v[32];
+      if (has_bias) {
+        sts32(sb + lane * 4, bnext);
+        __syncwarp();
+        if (has_next) bnext = __ldg(p.bias + col0 + 64 + lane);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint4 b = lds128(sb + k * 16);
+          v[4 * k + 0] = __uint_as_float(cur[4 * k + 0]) + __uint_as_float(b.x);
+          v[4 * k + 1] = __uint_as_float(cur[4 * k + 1]) + __uint_as_float(b.y);
+          v[4 * k + 2] = __uint_as_float(cur[4 * k + 2]) + __uint_as_float(b.z);
+          v[4 * k + 3] = __uint_as_float(cur[4 * k + 3]) + __uint_as_float(b.w);
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = __uint_as_float(cur[k]);
+      }
+      if (kResid) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) rcur[k] = rnext[k];
+        if (has_next) resid_prefetch(rnext, p.resid + row0 * p.ldr + col0 + 64, p.ldr, lane, rows_valid);
+      }
+      if (!kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * 64, raw[0]);   // v[] holds this chunk already
+      if (EPI == EPI_BF16) {
+        fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+      } else if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
+        fstore_f32<kResid>(st, lane, v, reinterpret_cast<float*>(p.C) + row0 * p.ldc + col0, p.ldc, rcur, rows_valid);
+      } else if (EPI == EPI_GEGLU) {
+        if (p.C != nullptr)
+          fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+        float g[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) g[k] = gelu_erf_fast(v[2 * k + 1]) * v[2 * k];
+        fstore_bf16_half(st, lane, g, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + (col0 >> 1), p.ldc2, rows_valid);
+      } else if (EPI == EPI_L2NORM) {
+        if (p.C != nullptr)
+          fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+        if (col0 < p.norm_cols) {
+          float ss = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; k++) ss = fmaf(v[k], v[k], ss);
+          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.norm_scale) + k);
+            v[4 * k + 0] = v[4 * k + 0] * inv * sc.x;
+            v[4 * k + 1] = v[4 * k + 1] * inv * sc.y;
+            v[4 * k + 2] = v[4 * k + 2] * inv * sc.z;
+            v[4 * k + 3] = v[4 * k + 3] * inv * sc.w;
+          }
+          fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + col0, p.ldc2, rows_valid);
+        }
+      } else if (EPI == EPI_BIAS_GELU) {
+        if (p.C2 != nullptr)
+          fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C2) + row0 * p.ldc2 + col0, p.ldc2, rows_valid);
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = gelu_erf_fast(v[k]);
+        fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
+      }
+    }
+    tmem_ld_wait();
+    // release this accumulator stage back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+  }
 }
 
 template <int BN, int AMAJ, int BMAJ>
@@ -294,6 +512,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
+    if (p.fast_epi) {   // kernel-uniform: specialised loops (fast_store shapes, one N tile per unit)
+      const uint32_t st32 = smem_u32(stage_all + (warp - 2) * 2048);
+      const uint32_t sb32 = smem_u32(arg_merge) + (warp - 2) * 128;   // per-warp bias broadcast buffer (argmax scratch is free here)
+      switch (p.epi) {
+        case EPI_BF16: epilogue_fast<BN, EPI_BF16>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        case EPI_F32: epilogue_fast<BN, EPI_F32>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        case EPI_RESID_F32: epilogue_fast<BN, EPI_RESID_F32>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        case EPI_GEGLU: epilogue_fast<BN, EPI_GEGLU>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        case EPI_L2NORM: epilogue_fast<BN, EPI_L2NORM>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        case EPI_BIAS_GELU: epilogue_fast<BN, EPI_BIAS_GELU>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        default: epilogue_fast<BN, EPI_NONE_DEBUG>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+      }
+    } else {
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which alternate 32-column chunks this warp handles
     uint32_t it = 0;
@@ -530,6 +761,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -626,6 +858,12 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
     if (ok && a->epilogue == EPI_RESID_F32) ok = ((uintptr_t)a->resid % 16 == 0) && ((a->ldr * 4) % 16 == 0);
     if (ok && a->epilogue == EPI_GEGLU) ok = (a->N % 64 == 0);   // 16-column halves of C2 stay 16-byte aligned
     p.fast_store = ok ? 1 : 0;
+    // debug / probing knobs (read once): CTCLIP_GEMM_OLD_EPI=1 keeps the v1 generic epilogue, CTCLIP_GEMM_EPI_NONE=1 drains
+    // accumulators without storing (mainloop ceiling; results are garbage), CTCLIP_GEMM_BN=64|128|256 forces the N tile
+    static const int old_epi = getenv("CTCLIP_GEMM_OLD_EPI") ? atoi(getenv("CTCLIP_GEMM_OLD_EPI")) : 0;
+    static const int epi_none = getenv("CTCLIP_GEMM_EPI_NONE") ? atoi(getenv("CTCLIP_GEMM_EPI_NONE")) : 0;
+    p.fast_epi = (ok && (a->N % 32 == 0) && !old_epi) ? 1 : 0;
+    if (epi_none && p.fast_epi) p.epi = EPI_NONE_DEBUG;
   }
 
   // Tile-N selection: 256 where it divides N (fewest B re-reads per MMA), else 128, 64 for tiny N.
@@ -636,6 +874,8 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   // keep at least ~1 wave of work for mid-sized problems
   if (bn == 256 && a->epilogue != EPI_ARGMAX &&
       (long long)ceil_div(a->M, BM) * (a->N / 256) * p.splits < num_sms() && a->N % 128 == 0) bn = 128;
+  static const int force_bn = getenv("CTCLIP_GEMM_BN") ? atoi(getenv("CTCLIP_GEMM_BN")) : 0;
+  if ((force_bn == 64 || force_bn == 128 || force_bn == 256) && a->epilogue != EPI_ARGMAX) bn = force_bn;
 
 #define CTB_DISPATCH(BN_)                                                                    \
   do {                                                                                       \

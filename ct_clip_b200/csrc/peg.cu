@@ -12,7 +12,7 @@
 // The kernel walks the conv grid (a0,a1,a2) in (T,H,W) shape and maps every access through
 // canon(f); a0 is the causal axis (taps a0-2, a0-1, a0).
 //
-// See the v2 kernel comment below for the tiling (rolling 3-plane shared-memory buffer along the causal axis).
+// See the v4 kernel comment below for the tiling (rolling plane ring in shared memory along the causal axis).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/ctclip_b200.h"
@@ -24,6 +24,13 @@ struct PegGeom {
   const int* table;   // optional precomputed canon(f) (avoids three integer divisions per access in the temporal stack)
 };
 
+// canonical token of conv-grid flat index f of the temporal stack, without the lookup table
+__device__ __forceinline__ long long peg_canon_f(const PegGeom& g, int f) {
+  const int it = f % g.T;
+  const int iw = (f / g.T) % g.W;
+  const int ih = f / (g.T * g.W);
+  return ((long long)it * g.H + ih) * g.W + iw;
+}
 __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1, int a2) {
   const int f = (a0 * g.H + a1) * g.W + a2;
   if (!g.temporal) return f;
@@ -35,15 +42,23 @@ __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1,
 }
 
 // ------------------------------------------------------------------------------------------------
-// v2 kernels. CTA = (32-channel block, tile of A1T=8 conv-grid lines along a1, range of a0 planes, volume).
-// The CTA walks the causal axis a0 with a ROLLING 3-plane buffer in shared memory ([slot][a1 halo][a2 halo][32 ch] fp32):
-// every step loads ONE new plane (halo factor (A1T+2)(W+2)/(A1T*W) ~ 1.35x of compulsory traffic, 128 B coalesced
-// segments), then each thread (= one line x one channel) slides a 3-wide register window along a2 (9 LDS per output,
-// 27 taps). Warps read 32 consecutive channels -> conflict-free LDS and 128 B coalesced stores.
+// v4 kernels. Work unit = one plane-step of a COLUMN = (volume, tile of A1T=8 conv-grid lines along a1, 32-channel
+// block); a column is walked along the causal axis a0 with a ROLLING ring of planes in shared memory
+// ([slot][a1 halo][a2 halo][32 ch] fp32): every step loads ONE new plane with cp.async (halo factor
+// (A1T+2)(W+2)/(A1T*W) ~ 1.35x of compulsory traffic, 128 B coalesced segments) while the previous one is computed.
+// Each thread (= one line x one channel) slides a register window along a2: 9 LDS + 27 FFMA per output, the window
+// rotates through FOUR register columns so that the loads of output i+1 are issued before the FMAs of output i, and
+// all shared-memory addresses are [running 32-bit offset + immediate] (v2/v3 spent 2/3 of their issue slots on 64-bit
+// address arithmetic and on the integer divisions of the plane loader; the loader's (line, column) decomposition is now
+// done once per column and kept in registers).
+// The grid is PERSISTENT: all (column, plane) steps are linearised and cut into gridDim.x equal contiguous ranges, so
+// every SM gets the same number of plane-steps (the former one-CTA-per-column grid ran 2.6 waves = 3 wave times).
 // ------------------------------------------------------------------------------------------------
-constexpr int A1T = 8;     // lines per CTA tile
-constexpr int CB = 32;     // channels per CTA
-constexpr int NSLOT = 4;   // ring of planes: 3 live + 1 being filled by cp.async while the current plane is computed
+constexpr int A1T = 8;          // lines per column tile
+constexpr int CB = 32;          // channels per column
+constexpr int NSLOT = 4;        // ring of planes: 3 live + 1 being filled by cp.async while the current plane is computed
+constexpr int PEG_THREADS = 256;
+constexpr int PEG_MAXIT = 14;   // cp.async items per thread and plane: (A1T+2)(W+2)(CB/4)/256 <= 14  <=>  W <= 42
 
 __device__ __forceinline__ int peg_slot(int pl) { return ((pl % NSLOT) + NSLOT) % NSLOT; }
 
@@ -55,42 +70,88 @@ __device__ __forceinline__ void peg_cp16(void* smem_dst, const void* gmem_src, b
 __device__ __forceinline__ void peg_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void peg_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// async load of plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one ring slot
-__device__ __forceinline__ void peg_load_plane_async(float* slot, const float* __restrict__ src, const PegGeom& g, int a0,
-                                                     int a1_0) {
-  const int a2h = g.W + 2;
-  const int n_tok = (A1T + 2) * a2h;
-  for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += blockDim.x) {
-    const int tok = idx / (CB / 4), q = idx % (CB / 4);
-    const int r1 = tok / a2h, r2 = tok % a2h;
-    const int a1 = a1_0 - 1 + r1, a2 = r2 - 1;
-    const bool ok = a0 >= 0 && a0 < g.T && a1 >= 0 && a1 < g.H && a2 >= 0 && a2 < g.W;
-    const float* p = ok ? src + peg_canon(g, a0, a1, a2) * g.D + q * 4 : src;
-    peg_cp16(slot + (size_t)tok * CB + q * 4, p, ok);
+struct PegCol {
+  int b, a1_0, c0;
+};
+__device__ __forceinline__ PegCol peg_column(int col, int n_cb, int n_a1t) {
+  PegCol c;
+  c.c0 = (col % n_cb) * CB;
+  c.a1_0 = ((col / n_cb) % n_a1t) * A1T;
+  c.b = col / (n_cb * n_a1t);
+  return c;
+}
+
+// Per-thread loader table of the current column: item idx = tid + it*256 copies 16 bytes (4 channels) of halo token
+// idx/8 = (r1, r2); inpl[it] = in-plane conv-grid offset a1*W + a2 of that token, -1 for zero-filled halo, -2 for
+// "beyond the slot".
+__device__ __forceinline__ void peg_loader_setup(int (&inpl)[PEG_MAXIT], int nit, int n_items, int a2h, int a1_0, int H,
+                                                 int W) {
+#pragma unroll
+  for (int it = 0; it < PEG_MAXIT; it++) {
+    const int idx = threadIdx.x + it * PEG_THREADS;
+    int v = -2;
+    if (it < nit && idx < n_items) {
+      const int tok = idx >> 3;
+      const int r1 = tok / a2h, r2 = tok - r1 * a2h;
+      const int a1 = a1_0 - 1 + r1, a2 = r2 - 1;
+      v = (a1 >= 0 && a1 < H && a2 >= 0 && a2 < W) ? a1 * W + a2 : -1;
+    }
+    inpl[it] = v;
   }
 }
-// async load of the upstream-gradient tile (A1T lines x W positions x CB channels) of plane a0
-__device__ __forceinline__ void peg_load_dy_async(float* buf, const float* __restrict__ dy, const PegGeom& g, int a0, int a1_0) {
+// async load of plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one ring slot
+__device__ __forceinline__ void peg_load_plane4(float* slot, const float* __restrict__ src, const PegGeom& g, int a0,
+                                                const int (&inpl)[PEG_MAXIT], int nit) {
+  const bool pl_ok = a0 >= 0 && a0 < g.T;
+  const int fbase = a0 * g.H * g.W;
+  const int q4 = (threadIdx.x & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < PEG_MAXIT; it++) {
+    if (it < nit) {
+      const int v = inpl[it];
+      if (v != -2) {
+        const bool ok = pl_ok && v >= 0;
+        long long tok = 0;
+        if (ok) {
+          const int f = fbase + v;
+          tok = !g.temporal ? f : (g.table != nullptr ? __ldg(g.table + f) : (int)peg_canon_f(g, f));
+        }
+        peg_cp16(slot + (size_t)(threadIdx.x + it * PEG_THREADS) * 4, src + tok * g.D + q4, ok);
+      }
+    }
+  }
+}
+// async load of the upstream-gradient tile (A1T lines x W positions x CB channels) of plane a0 (always inside [0,T))
+__device__ __forceinline__ void peg_load_dy4(float* buf, const float* __restrict__ dy, const PegGeom& g, int a0, int a1_0) {
   const int n_tok = A1T * g.W;
-  for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += blockDim.x) {
-    const int tok = idx / (CB / 4), q = idx % (CB / 4);
-    const int a1 = a1_0 + tok / g.W, a2 = tok % g.W;
-    const bool ok = a0 >= 0 && a0 < g.T && a1 < g.H;
-    const float* p = ok ? dy + peg_canon(g, a0, a1, a2) * g.D + q * 4 : dy;
-    peg_cp16(buf + (size_t)tok * CB + q * 4, p, ok);
+  const int n_valid = min(A1T, g.H - a1_0) * g.W;
+  const int fbase = (a0 * g.H + a1_0) * g.W;
+  const int q4 = (threadIdx.x & 7) * 4;
+  for (int idx = threadIdx.x; idx < n_tok * (CB / 4); idx += PEG_THREADS) {
+    const int tok = idx >> 3;
+    const bool ok = tok < n_valid;
+    long long ctok = 0;
+    if (ok) {
+      const int f = fbase + tok;
+      ctok = !g.temporal ? f : (g.table != nullptr ? __ldg(g.table + f) : (int)peg_canon_f(g, f));
+    }
+    peg_cp16(buf + (size_t)idx * 4, dy + ctok * g.D + q4, ok);
   }
 }
 
-// One output position of the sliding window; the 3-wide window rotates through the register file (ROT) instead of
-// being shifted, so no register moves are issued. Window slot (ROT+2)%3 receives the new right-hand element.
-// Two independent accumulation chains keep the FMA pipe busy with only 8 warps per SM.
+// shared-memory window loads: [32-bit running byte offset + immediate column offset]
+#define PEG_LD(smb, po, r, col) (*reinterpret_cast<const float*>((smb) + (po)[r] + (col) * (CB * 4)))
+
+// One output of the sliding window. The window holds FOUR columns per row; output ROT uses columns
+// (ROT, ROT+1, ROT+2) mod 4 as (left, centre, right) while column (ROT+3) mod 4 receives the right-hand element of
+// the NEXT output, so those loads are in flight during this output's FMAs. Two accumulation chains.
 template <int ROT>
-__device__ __forceinline__ float peg_step(float (&win)[9][3], const float* const (&rowp)[9], const float (&wt)[27],
-                                          int off, float init) {
-  constexpr int L = ROT % 3, C = (ROT + 1) % 3, R = (ROT + 2) % 3;
-  float acc0 = init, acc1 = 0.f;
+__device__ __forceinline__ float peg_out(float (&win)[9][4], const char* smb, const uint32_t (&po)[9],
+                                         const float (&wt)[27], float init) {
+  constexpr int L = ROT % 4, C = (ROT + 1) % 4, R = (ROT + 2) % 4, N = (ROT + 3) % 4;
 #pragma unroll
-  for (int r = 0; r < 9; r++) win[r][R] = rowp[r][off];
+  for (int r = 0; r < 9; r++) win[r][N] = PEG_LD(smb, po, r, ROT + 3);
+  float acc0 = init, acc1 = 0.f;
 #pragma unroll
   for (int r = 0; r < 9; r++) {
     float& acc = (r & 1) ? acc1 : acc0;
@@ -101,11 +162,11 @@ __device__ __forceinline__ float peg_step(float (&win)[9][3], const float* const
   return acc0 + acc1;
 }
 template <int ROT>
-__device__ __forceinline__ void peg_wstep(float (&win)[9][3], const float* const (&rowp)[9], float (&acc)[27], int off,
-                                          float d) {
-  constexpr int L = ROT % 3, C = (ROT + 1) % 3, R = (ROT + 2) % 3;
+__device__ __forceinline__ void peg_wout(float (&win)[9][4], const char* smb, const uint32_t (&po)[9], float (&acc)[27],
+                                         float d) {
+  constexpr int L = ROT % 4, C = (ROT + 1) % 4, R = (ROT + 2) % 4, N = (ROT + 3) % 4;
 #pragma unroll
-  for (int r = 0; r < 9; r++) win[r][R] = rowp[r][off];
+  for (int r = 0; r < 9; r++) win[r][N] = PEG_LD(smb, po, r, ROT + 3);
 #pragma unroll
   for (int r = 0; r < 9; r++) {
     acc[r * 3 + 0] = fmaf(d, win[r][L], acc[r * 3 + 0]);
@@ -116,178 +177,199 @@ __device__ __forceinline__ void peg_wstep(float (&win)[9][3], const float* const
 
 // MODE 0: y = x + conv(x) + bias (forward; taps a0-2..a0)     MODE 1: dx = dy + conv^T(dy) (taps a0..a0+2, mirrored)
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) peg_conv2_kernel(ctclip_peg_args a, int planes_per_cta) {
+__global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_args a, int steps_per_cta) {
   extern __shared__ __align__(16) float peg_sm[];
   const PegGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table};
   const int a2h = a.W + 2;
-  const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
-  const int n_a1t = (a.H + A1T - 1) / A1T;
-  const int c0 = (blockIdx.x % (a.D / CB)) * CB;
-  const int a1_0 = ((blockIdx.x / (a.D / CB)) % n_a1t) * A1T;
-  const int chunk = blockIdx.x / ((a.D / CB) * n_a1t);
-  const int b = blockIdx.y;
-  const int p_begin = chunk * planes_per_cta;
-  const int p_end = min(a.T, p_begin + planes_per_cta);
-  if (p_begin >= p_end) return;
+  const int slot_elems = (A1T + 2) * a2h * CB;
+  const int n_items = (A1T + 2) * a2h * (CB / 4);
+  const int nit = (n_items + PEG_THREADS - 1) / PEG_THREADS;
+  const int n_a1t = (a.H + A1T - 1) / A1T, n_cb = a.D / CB;
+  const int total = n_cb * n_a1t * a.B * a.T;
+  const int s_begin = blockIdx.x * steps_per_cta;
+  const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
-  const float* xin = a.x + (long long)b * vol + c0;
-  float* yout = a.y + (long long)b * vol + c0;
-  __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)b * vol + c0 : nullptr;
   const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;  // channel, a1 line within the tile
-  const int ch = c0 + lane;
-  float wt[27];
+  int* s_tok = reinterpret_cast<int*>(peg_sm + (size_t)NSLOT * slot_elems);   // [2][A1T][W] canonical token of every output
+  const char* smb = reinterpret_cast<const char*>(peg_sm);
+  int inpl[PEG_MAXIT];
+  int par = 0;
+  for (int s = s_begin; s < s_end;) {
+    const int col = s / a.T;
+    const int p_begin = s - col * a.T;
+    const int p_end = min(a.T, p_begin + (s_end - s));
+    const PegCol cc = peg_column(col, n_cb, n_a1t);
+    const float* xin = a.x + (long long)cc.b * vol + cc.c0;
+    float* yout = a.y + (long long)cc.b * vol + cc.c0;
+    __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)cc.b * vol + cc.c0 : nullptr;
+    const int ch = cc.c0 + lane;
+    float wt[27];
 #pragma unroll
-  for (int k = 0; k < 27; k++) wt[k] = a.weight[(long long)ch * 27 + ((MODE == 0) ? k : 26 - k)];
-  const float bias = (MODE == 0 && a.bias != nullptr) ? a.bias[ch] : 0.f;
-  const int a1 = a1_0 + line;
-  // planes needed for output plane a0: a0-2, a0-1, a0 (MODE 0) / a0, a0+1, a0+2 (MODE 1). Walk a0 in direction `dirn`
-  // so that only ONE new plane enters per step; it is fetched (cp.async) while the previous plane is being computed.
-  const int first = (MODE == 0) ? p_begin : p_end - 1;
-  const int dirn = (MODE == 0) ? 1 : -1;
-  for (int d = 2; d >= 0; d--) {
-    const int pl = first - dirn * d;
-    peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
-  }
-  peg_commit();
-  const int n_steps = p_end - p_begin;
-  // canonical token index of every output of the current plane ([2][A1T][W], double-buffered by step parity): one
-  // canon() per thread per plane instead of one per output inside the sliding loop
-  int* s_tok = reinterpret_cast<int*>(peg_sm + NSLOT * slot_elems);
-  for (int step = 0; step < n_steps; step++) {
-    const int a0 = first + dirn * step;
-    for (int i = threadIdx.x; i < A1T * a.W; i += blockDim.x) {
-      const int l1 = a1_0 + i / a.W;
-      s_tok[(step & 1) * A1T * a.W + i] = (l1 < a.H) ? (int)peg_canon(g, a0, l1, i % a.W) : 0;
+    for (int k = 0; k < 27; k++) wt[k] = __ldg(a.weight + (long long)ch * 27 + ((MODE == 0) ? k : 26 - k));
+    const float bias = (MODE == 0 && a.bias != nullptr) ? __ldg(a.bias + ch) : 0.f;
+    const int a1 = cc.a1_0 + line;
+    __syncthreads();   // the previous column's last plane (ring + token table) is fully consumed
+    peg_loader_setup(inpl, nit, n_items, a2h, cc.a1_0, a.H, a.W);
+    // planes needed for output plane a0: a0-2, a0-1, a0 (MODE 0) / a0, a0+1, a0+2 (MODE 1). Walk a0 in direction `dirn`
+    // so that only ONE new plane enters per step.
+    const int first = (MODE == 0) ? p_begin : p_end - 1;
+    const int dirn = (MODE == 0) ? 1 : -1;
+    for (int d = 2; d >= 0; d--) {
+      const int pl = first - dirn * d;
+      peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
     }
-    peg_wait_all();
-    __syncthreads();   // plane a0 landed for everyone; everyone finished computing plane a0 - dirn
-    if (step + 1 < n_steps) {   // prefetch the next plane into the slot released by plane a0 - 3*dirn
-      const int pl = a0 + dirn;
-      peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
-      peg_commit();
-    }
-    if (a1 < a.H) {
-      const float* rowp[9];
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        const int k0 = r / 3, k1 = r % 3;
-        const int pl = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
-        rowp[r] = peg_sm + (size_t)peg_slot(pl) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
+    peg_commit();
+    const int n_steps = p_end - p_begin;
+    for (int step = 0; step < n_steps; step++, par ^= 1) {
+      const int a0 = first + dirn * step;
+      for (int i = threadIdx.x; i < A1T * a.W; i += PEG_THREADS) {
+        const int l1 = cc.a1_0 + i / a.W;
+        s_tok[par * A1T * a.W + i] = (l1 < a.H) ? (int)peg_canon(g, a0, l1, i % a.W) : 0;
       }
-      float win[9][3];
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        win[r][0] = rowp[r][0];       // a2 = -1 (zero padding)
-        win[r][1] = rowp[r][CB];      // a2 = 0
+      peg_wait_all();
+      __syncthreads();   // plane a0 landed for everyone; everyone finished computing the previous plane
+      if (step + 1 < n_steps) {   // prefetch the next plane into the slot released by plane a0 - 3*dirn
+        const int pl = a0 + dirn;
+        peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
+        peg_commit();
       }
-      constexpr int CR = (MODE == 0) ? 7 : 1;   // row of the centre tap (k0 = 2 | 0, k1 = 1): its centre element = residual
-      const int* tokl = s_tok + (step & 1) * A1T * a.W + line * a.W;
-      auto emit = [&](int a2, float val) {
-        const long long off = (long long)tokl[a2] * a.D + lane;
-        yout[off] = val;
-        if (ybf != nullptr) ybf[off] = __float2bfloat16(val);
-      };
-      for (int a2 = 0; a2 < a.W; a2 += 3) {
-        const float o0 = peg_step<0>(win, rowp, wt, (a2 + 2) * CB, bias) + win[CR][1];
-        emit(a2, o0);
-        if (a2 + 1 < a.W) {
-          const float o1 = peg_step<1>(win, rowp, wt, (a2 + 3) * CB, bias) + win[CR][2];
-          emit(a2 + 1, o1);
+      if (a1 < a.H) {
+        uint32_t po[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const int k0 = r / 3, k1 = r % 3;
+          const int pl = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
+          po[r] = (uint32_t)(peg_slot(pl) * slot_elems + (line + k1) * a2h * CB + lane) * 4u;
         }
-        if (a2 + 2 < a.W) {
-          const float o2 = peg_step<2>(win, rowp, wt, (a2 + 4) * CB, bias) + win[CR][0];
-          emit(a2 + 2, o2);
+        float win[9][4];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          win[r][0] = PEG_LD(smb, po, r, 0);   // a2 = -1 (zero padding)
+          win[r][1] = PEG_LD(smb, po, r, 1);   // a2 = 0
+          win[r][2] = PEG_LD(smb, po, r, 2);   // a2 = 1
+        }
+        constexpr int CR = (MODE == 0) ? 7 : 1;   // row of the centre tap (k0 = 2 | 0, k1 = 1): its centre element = residual
+        const int* tokl = s_tok + par * A1T * a.W + line * a.W;
+        auto emit = [&](int a2, float val) {
+          const long long off = (long long)tokl[a2] * a.D + lane;
+          yout[off] = val;
+          if (ybf != nullptr) ybf[off] = __float2bfloat16(val);
+        };
+        for (int a2 = 0; a2 < a.W; a2 += 4) {
+          emit(a2, peg_out<0>(win, smb, po, wt, bias) + win[CR][1]);
+          if (a2 + 1 < a.W) emit(a2 + 1, peg_out<1>(win, smb, po, wt, bias) + win[CR][2]);
+          if (a2 + 2 < a.W) emit(a2 + 2, peg_out<2>(win, smb, po, wt, bias) + win[CR][3]);
+          if (a2 + 3 < a.W) emit(a2 + 3, peg_out<3>(win, smb, po, wt, bias) + win[CR][0]);
+#pragma unroll
+          for (int r = 0; r < 9; r++) po[r] += 4 * CB * 4;
         }
       }
     }
+    s += n_steps;
   }
 }
 
 // dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p]
-// x planes in the 4-slot ring, the upstream-gradient tile of the same plane in a 2-slot ring, both prefetched with cp.async
-__global__ void __launch_bounds__(256, 1) peg_wgrad2_kernel(ctclip_peg_args a, int planes_per_cta, int dy_double) {
+// x planes in the 4-slot ring, the upstream-gradient tile of the same plane in a 2-slot ring, both prefetched with cp.async.
+// Same persistent (column, plane) ranges as the conv kernel; the 27+1 partial sums of a thread are reduced across the 8
+// lines of the CTA through shared memory at the end of every column segment -> one atomic per (channel, tap).
+__global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_args a, int steps_per_cta, int dy_double) {
   extern __shared__ __align__(16) float peg_sm[];
   const PegGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table};
   const int a2h = a.W + 2;
-  const size_t slot_elems = (size_t)(A1T + 2) * a2h * CB;
-  const size_t dy_elems = (size_t)A1T * a.W * CB;
-  float* sdy = peg_sm + NSLOT * slot_elems;   // [2][A1T][W][CB]
-  const int n_a1t = (a.H + A1T - 1) / A1T;
-  const int c0 = (blockIdx.x % (a.D / CB)) * CB;
-  const int a1_0 = ((blockIdx.x / (a.D / CB)) % n_a1t) * A1T;
-  const int chunk = blockIdx.x / ((a.D / CB) * n_a1t);
-  const int b = blockIdx.y;
-  const int p_begin = chunk * planes_per_cta;
-  const int p_end = min(a.T, p_begin + planes_per_cta);
-  if (p_begin >= p_end) return;
+  const int slot_elems = (A1T + 2) * a2h * CB;
+  const int dy_elems = A1T * a.W * CB;
+  const int n_items = (A1T + 2) * a2h * (CB / 4);
+  const int nit = (n_items + PEG_THREADS - 1) / PEG_THREADS;
+  float* sdy = peg_sm + (size_t)NSLOT * slot_elems;   // [2][A1T][W][CB]
+  const int n_a1t = (a.H + A1T - 1) / A1T, n_cb = a.D / CB;
+  const int total = n_cb * n_a1t * a.B * a.T;
+  const int s_begin = blockIdx.x * steps_per_cta;
+  const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
-  const float* xin = a.x + (long long)b * vol + c0;
-  const float* dy = a.dy + (long long)b * vol + c0;
   const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;
-  const int a1 = a1_0 + line;
-  float acc[27];
+  const char* smb = reinterpret_cast<const char*>(peg_sm);
+  int inpl[PEG_MAXIT];
+  for (int s = s_begin; s < s_end;) {
+    const int col = s / a.T;
+    const int p_begin = s - col * a.T;
+    const int p_end = min(a.T, p_begin + (s_end - s));
+    const PegCol cc = peg_column(col, n_cb, n_a1t);
+    const float* xin = a.x + (long long)cc.b * vol + cc.c0;
+    const float* dy = a.dy + (long long)cc.b * vol + cc.c0;
+    const int a1 = cc.a1_0 + line;
+    float acc[27];
 #pragma unroll
-  for (int k = 0; k < 27; k++) acc[k] = 0.f;
-  float accb = 0.f;
-  for (int d = 2; d >= 0; d--) {
-    const int pl = p_begin - d;
-    peg_load_plane_async(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, a1_0);
-  }
-  peg_load_dy_async(sdy, dy, g, p_begin, a1_0);
-  peg_commit();
-  for (int a0 = p_begin; a0 < p_end; a0++) {
-    const int par = dy_double ? ((a0 - p_begin) & 1) : 0;
-    if (!dy_double && a0 > p_begin) {   // wide grids: a single gradient tile fits; fetch it without overlap
+    for (int k = 0; k < 27; k++) acc[k] = 0.f;
+    float accb = 0.f;
+    __syncthreads();   // previous column: reduction scratch / ring fully consumed
+    peg_loader_setup(inpl, nit, n_items, a2h, cc.a1_0, a.H, a.W);
+    for (int d = 2; d >= 0; d--) {
+      const int pl = p_begin - d;
+      peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
+    }
+    peg_load_dy4(sdy, dy, g, p_begin, cc.a1_0);
+    peg_commit();
+    for (int a0 = p_begin; a0 < p_end; a0++) {
+      const int par = dy_double ? ((a0 - p_begin) & 1) : 0;
+      if (!dy_double && a0 > p_begin) {   // wide grids: a single gradient tile fits; fetch it without overlap
+        __syncthreads();
+        peg_load_dy4(sdy, dy, g, a0, cc.a1_0);
+        peg_commit();
+      }
+      peg_wait_all();
       __syncthreads();
-      peg_load_dy_async(sdy, dy, g, a0, a1_0);
-      peg_commit();
+      if (a0 + 1 < p_end) {
+        peg_load_plane4(peg_sm + (size_t)peg_slot(a0 + 1) * slot_elems, xin, g, a0 + 1, inpl, nit);
+        if (dy_double) peg_load_dy4(sdy + (size_t)(par ^ 1) * dy_elems, dy, g, a0 + 1, cc.a1_0);
+        peg_commit();
+      }
+      if (a1 < a.H) {
+        uint32_t po[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const int k0 = r / 3, k1 = r % 3;
+          po[r] = (uint32_t)(peg_slot(a0 + k0 - 2) * slot_elems + (line + k1) * a2h * CB + lane) * 4u;
+        }
+        const float* dyl = sdy + (size_t)par * dy_elems + (size_t)(line * a.W) * CB + lane;
+        float win[9][4];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          win[r][0] = PEG_LD(smb, po, r, 0);
+          win[r][1] = PEG_LD(smb, po, r, 1);
+          win[r][2] = PEG_LD(smb, po, r, 2);
+        }
+        for (int a2 = 0; a2 < a.W; a2 += 4) {
+          const float d0 = dyl[a2 * CB];
+          const float d1 = (a2 + 1 < a.W) ? dyl[(a2 + 1) * CB] : 0.f;
+          const float d2 = (a2 + 2 < a.W) ? dyl[(a2 + 2) * CB] : 0.f;
+          const float d3 = (a2 + 3 < a.W) ? dyl[(a2 + 3) * CB] : 0.f;
+          accb += (d0 + d1) + (d2 + d3);
+          peg_wout<0>(win, smb, po, acc, d0);
+          if (a2 + 1 < a.W) peg_wout<1>(win, smb, po, acc, d1);
+          if (a2 + 2 < a.W) peg_wout<2>(win, smb, po, acc, d2);
+          if (a2 + 3 < a.W) peg_wout<3>(win, smb, po, acc, d3);
+#pragma unroll
+          for (int r = 0; r < 9; r++) po[r] += 4 * CB * 4;
+        }
+      }
     }
-    peg_wait_all();
+    // reduce the A1T lines of this CTA (same channel = same lane) through shared memory, one atomic per (channel, tap)
     __syncthreads();
-    if (a0 + 1 < p_end) {
-      peg_load_plane_async(peg_sm + (size_t)peg_slot(a0 + 1) * slot_elems, xin, g, a0 + 1, a1_0);
-      if (dy_double) peg_load_dy_async(sdy + (size_t)(par ^ 1) * dy_elems, dy, g, a0 + 1, a1_0);
-      peg_commit();
+    float* red = peg_sm;  // [A1T][28][CB]
+#pragma unroll
+    for (int k = 0; k < 27; k++) red[(line * 28 + k) * CB + lane] = acc[k];
+    red[(line * 28 + 27) * CB + lane] = accb;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * CB; i += PEG_THREADS) {
+      const int k = i / CB, c = i % CB;
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < A1T; l++) t += red[(l * 28 + k) * CB + c];
+      if (k < 27) atomicAdd(a.dweight + (long long)(cc.c0 + c) * 27 + k, t);
+      else if (a.dbias != nullptr) atomicAdd(a.dbias + cc.c0 + c, t);
     }
-    if (a1 < a.H) {
-      const float* rowp[9];
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        const int k0 = r / 3, k1 = r % 3;
-        rowp[r] = peg_sm + (size_t)peg_slot(a0 + k0 - 2) * slot_elems + (size_t)((line + k1) * a2h) * CB + lane;
-      }
-      const float* dyl = sdy + (size_t)par * dy_elems + (size_t)(line * a.W) * CB + lane;
-      float win[9][3];
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        win[r][0] = rowp[r][0];
-        win[r][1] = rowp[r][CB];
-      }
-      for (int a2 = 0; a2 < a.W; a2 += 3) {
-        const float d0 = dyl[a2 * CB];
-        const float d1 = (a2 + 1 < a.W) ? dyl[(a2 + 1) * CB] : 0.f;
-        const float d2 = (a2 + 2 < a.W) ? dyl[(a2 + 2) * CB] : 0.f;
-        accb += d0 + d1 + d2;
-        peg_wstep<0>(win, rowp, acc, (a2 + 2) * CB, d0);
-        if (a2 + 1 < a.W) peg_wstep<1>(win, rowp, acc, (a2 + 3) * CB, d1);
-        if (a2 + 2 < a.W) peg_wstep<2>(win, rowp, acc, (a2 + 4) * CB, d2);
-      }
-    }
-  }
-  // reduce the A1T lines of this CTA (same channel = same lane) through shared memory, one atomic per (channel, tap)
-  __syncthreads();
-  float* red = peg_sm;  // [A1T][28][CB]
-#pragma unroll
-  for (int k = 0; k < 27; k++) red[(line * 28 + k) * CB + lane] = acc[k];
-  red[(line * 28 + 27) * CB + lane] = accb;
-  __syncthreads();
-  for (int i = threadIdx.x; i < 28 * CB; i += blockDim.x) {
-    const int k = i / CB, c = i % CB;
-    float t = 0.f;
-#pragma unroll
-    for (int l = 0; l < A1T; l++) t += red[(l * 28 + k) * CB + c];
-    if (k < 27) atomicAdd(a.dweight + (long long)(c0 + c) * 27 + k, t);
-    else if (a.dbias != nullptr) atomicAdd(a.dbias + c0 + c, t);
+    s += p_end - p_begin;
   }
 }
 
@@ -299,63 +381,56 @@ static int peg_check(const ctclip_peg_args* a, const char* who) {
   CTB_CHECK_ARG(a && a->x, "%s: null x", who);
   CTB_CHECK_ARG(a->B > 0 && a->T > 0 && a->H > 0 && a->W > 0, "%s: bad grid", who);
   CTB_CHECK_ARG(a->D % 32 == 0, "%s: D must be a multiple of 32", who);
+  CTB_CHECK_ARG(a->W <= 42, "%s: token grid width %d > 42 is not supported by the shared-memory plane ring", who, a->W);
+  CTB_CHECK_ARG((long long)a->B * a->T * a->H * a->W < (1ll << 31) / 64, "%s: token count too large", who);
   return CTCLIP_OK;
 }
 
-// grid.x = channel blocks x a1 tiles x a0 chunks (1 CTA per SM: ~133-182 KB of shared memory). The a0 range is
-// split into the chunk count that minimises  ceil(CTAs / SMs) * (planes per CTA + 2 priming planes).
-static void peg_launch_shape(const ctclip_peg_args* a, int dy_bufs, dim3* grid, int* planes_per_cta, size_t* smem) {
+// Persistent launch: all (column, plane) steps are cut into one contiguous range per SM (1 CTA per SM: 133-182 KB of
+// shared memory).
+static void peg_launch_shape(const ctclip_peg_args* a, int dy_bufs, int* grid, int* steps_per_cta, size_t* smem) {
   const int n_a1t = (a->H + A1T - 1) / A1T;
-  const long long base = (long long)(a->D / CB) * n_a1t * a->B;
-  int best_chunks = 1;
-  long long best_cost = -1;
-  for (int chunks = 1; chunks <= 6 && chunks <= a->T; chunks++) {
-    const int ppc = (a->T + chunks - 1) / chunks;
-    const int real_chunks = (a->T + ppc - 1) / ppc;
-    const long long waves = (base * real_chunks + num_sms() - 1) / num_sms();
-    const long long cost = waves * (ppc + 2);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = real_chunks; }
-  }
-  *planes_per_cta = (a->T + best_chunks - 1) / best_chunks;
-  const int chunks = (a->T + *planes_per_cta - 1) / *planes_per_cta;
-  *grid = dim3((unsigned)((a->D / CB) * n_a1t * chunks), (unsigned)a->B);
+  const long long total = (long long)(a->D / CB) * n_a1t * a->B * a->T;
+  long long ctas = num_sms();
+  if (ctas > total) ctas = total;
+  *steps_per_cta = (int)((total + ctas - 1) / ctas);
+  *grid = (int)((total + *steps_per_cta - 1) / *steps_per_cta);
   *smem = sizeof(float) * NSLOT * (size_t)(A1T + 2) * (a->W + 2) * CB;
   if (dy_bufs == 0) *smem += sizeof(int) * 2 * (size_t)A1T * a->W;   // token-index table of the conv kernels
   *smem += sizeof(float) * dy_bufs * (size_t)A1T * a->W * CB;
+  *smem += 1024;   // the rotating window reads up to 6 columns past the end of the last row
   const size_t red_bytes = sizeof(float) * A1T * 28 * CB;  // weight-gradient reduction scratch
   if (*smem < red_bytes) *smem = red_bytes;
 }
 
 static int peg_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream) {
-  dim3 grid;
-  int ppc;
+  int grid, spc;
   size_t smem;
-  peg_launch_shape(a, 0, &grid, &ppc, &smem);
+  peg_launch_shape(a, 0, &grid, &spc, &smem);
   CTB_CHECK_ARG(smem <= 227 * 1024, "peg: token grid width %d needs %zu B of shared memory", a->W, smem);
   if (mode == 0) {
-    CTB_CUDA(cudaFuncSetAttribute(peg_conv2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    peg_conv2_kernel<0><<<grid, 256, smem, stream>>>(*a, ppc);
+    CTB_CUDA(cudaFuncSetAttribute(peg_conv4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    peg_conv4_kernel<0><<<grid, PEG_THREADS, smem, stream>>>(*a, spc);
   } else {
-    CTB_CUDA(cudaFuncSetAttribute(peg_conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    peg_conv2_kernel<1><<<grid, 256, smem, stream>>>(*a, ppc);
+    CTB_CUDA(cudaFuncSetAttribute(peg_conv4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    peg_conv4_kernel<1><<<grid, PEG_THREADS, smem, stream>>>(*a, spc);
   }
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }
 
 static int peg_launch_wgrad(const ctclip_peg_args* a, cudaStream_t stream) {
-  dim3 grid;
-  int ppc;
+  int grid, spc;
   size_t smem;
   int dy_bufs = 2;
-  peg_launch_shape(a, dy_bufs, &grid, &ppc, &smem);
+  peg_launch_shape(a, dy_bufs, &grid, &spc, &smem);
   if (smem > 227 * 1024) {
     dy_bufs = 1;
-    peg_launch_shape(a, dy_bufs, &grid, &ppc, &smem);
+    peg_launch_shape(a, dy_bufs, &grid, &spc, &smem);
   }
   CTB_CHECK_ARG(smem <= 227 * 1024, "peg: token grid width %d needs %zu B of shared memory", a->W, smem);
-  CTB_CUDA(cudaFuncSetAttribute(peg_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  peg_wgrad2_kernel<<<grid, 256, smem, stream>>>(*a, ppc, dy_bufs == 2);
+  CTB_CUDA(cudaFuncSetAttribute(peg_wgrad4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  peg_wgrad4_kernel<<<grid, PEG_THREADS, smem, stream>>>(*a, spc, dy_bufs == 2);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

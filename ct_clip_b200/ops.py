@@ -51,7 +51,8 @@ def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, 
     a.norm_cols = norm_cols
     a.norm_scale = _ptr(norm_scale)
     if GEMM_TIMER is None:
-        call("ctclip_gemm_bf16", C.byref(a), _stream())
+        call("ctclip_gemm_bf16", C.byref(a), _stream(), tag=f"{M}x{N}x{K} a{a_major}b{b_major} epi{epilogue} s{splits}",
+             work=("F", 2.0 * M * N * K))
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -72,7 +73,8 @@ def ln_fwd(x, M, D, *, eps=1e-5, gamma=None, beta=None, xhat=None, raw=None, y_f
     a.x, a.M, a.D, a.eps = x.data_ptr(), M, D, eps
     a.gamma, a.beta = _ptr(gamma), _ptr(beta)
     a.xhat_bf16, a.raw_bf16, a.y_f32, a.y_bf16, a.rstd_out = _ptr(xhat), _ptr(raw), _ptr(y_f32), _ptr(y_bf16), _ptr(rstd)
-    call("ctclip_ln_fwd", C.byref(a), _stream())
+    per_elem = 4 + 2 * (xhat is not None) + 2 * (raw is not None) + 4 * (y_f32 is not None) + 2 * (y_bf16 is not None)
+    call("ctclip_ln_fwd", C.byref(a), _stream(), tag=f"D{D} {per_elem}B/elem", work=("B", float(M) * D * per_elem))
 
 
 def ln_bwd(M, D, *, g_f32=None, g_bf16=None, gamma=None, xhat, rstd, dres_in=None, add_bf16=None, dx_f32=None,
@@ -83,7 +85,9 @@ def ln_bwd(M, D, *, g_f32=None, g_bf16=None, gamma=None, xhat, rstd, dres_in=Non
     a.xhat, a.rstd = xhat.data_ptr(), rstd.data_ptr()
     a.dres_in, a.add_bf16 = _ptr(dres_in), _ptr(add_bf16)
     a.dx_f32, a.dx_bf16, a.dgamma, a.dbeta = _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta)
-    call("ctclip_ln_bwd", C.byref(a), _stream())
+    per_elem = (2 + 4 * (g_f32 is not None) + 2 * (g_bf16 is not None) + 4 * (dres_in is not None) + 2 * (add_bf16 is not None)
+                + 4 * (dx_f32 is not None) + 2 * (dx_bf16 is not None))
+    call("ctclip_ln_bwd", C.byref(a), _stream(), tag=f"D{D} {per_elem}B/elem", work=("B", float(M) * D * per_elem))
 
 
 def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
@@ -99,7 +103,8 @@ def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
     a.pt, a.p1, a.p2, a.eps = pt, p1, p2, eps
     a.xhat = xhat.data_ptr()
     a.ld_out = ld_out if ld_out is not None else xhat.stride(0)
-    call("ctclip_patchify", C.byref(a), _stream())
+    call("ctclip_patchify", C.byref(a), _stream(), tag=str(video.dtype).replace("torch.", ""),
+         work=("B", float(video.numel()) * (video.element_size() + 2)))
 
 
 def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
@@ -112,16 +117,23 @@ def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_b
     return a
 
 
+def _peg_tag(kw):
+    return "temporal" if kw.get("temporal") else "spatial"
+
+
 def peg_fwd(x, y, weight, bias, **kw):
-    call("ctclip_peg_fwd", C.byref(_peg_args(x, y=y, weight=weight, bias=bias, **kw)), _stream())
+    call("ctclip_peg_fwd", C.byref(_peg_args(x, y=y, weight=weight, bias=bias, **kw)), _stream(), tag=_peg_tag(kw),
+         work=("B", 8.0 * x.numel()))
 
 
 def peg_bwd_data(dy, dx, weight, dx_bf16=None, **kw):
-    call("ctclip_peg_bwd_data", C.byref(_peg_args(dy, y=dx, y_bf16=dx_bf16, weight=weight, **kw)), _stream())
+    call("ctclip_peg_bwd_data", C.byref(_peg_args(dy, y=dx, y_bf16=dx_bf16, weight=weight, **kw)), _stream(),
+         tag=_peg_tag(kw), work=("B", (8.0 + 2 * (dx_bf16 is not None)) * dy.numel()))
 
 
 def peg_bwd_weight(x, dy, dweight, dbias, **kw):
-    call("ctclip_peg_bwd_weight", C.byref(_peg_args(x, dy=dy, dweight=dweight, dbias=dbias, **kw)), _stream())
+    call("ctclip_peg_bwd_weight", C.byref(_peg_args(x, dy=dy, dweight=dweight, dbias=dbias, **kw)), _stream(),
+         tag=_peg_tag(kw), work=("B", 8.0 * x.numel()))
 
 
 def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
@@ -137,8 +149,14 @@ def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_i
     return a
 
 
+def _attn_flops(kw):
+    """QK^T + PV of every (sequence, head): 4 n^2 dh"""
+    return 4.0 * kw["num_seqs"] * kw["heads"] * kw["n"] * kw["n"] * kw.get("dim_head", 32)
+
+
 def attn_fwd(q, k, v, o, lse, **kw):
-    call("ctclip_attn_fwd", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream())
+    call("ctclip_attn_fwd", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream(), tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}",
+         work=("F", _attn_flops(kw)))
 
 
 def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, **kw):
@@ -147,12 +165,14 @@ def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, to
     a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = dq.data_ptr(), ld_dq, dk.data_ptr(), ld_dk, dv.data_ptr(), ld_dv
     a.dbias = _ptr(dbias)
     a.total_rows = total_rows
-    call("ctclip_attn_bwd", C.byref(a), _stream())
+    # algorithmic backward = 5 contractions (S, dP, dV, dQ, dK) = 2.5x the forward (the three kernels recompute S/dP)
+    call("ctclip_attn_bwd", C.byref(a), _stream(), tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}" + (" +dbias" if dbias is not None else ""),
+         work=("F", 2.5 * _attn_flops(kw)))
 
 
 def l2norm_bwd(dxh, ld_dxh, xraw, ld_x, scale, dx, ld_dx, dscale, rows, heads, dim_head=32):
     call("ctclip_l2norm_bwd", dxh.data_ptr(), ld_dxh, xraw.data_ptr(), ld_x, scale.data_ptr(), dx.data_ptr(), ld_dx,
-         dscale.data_ptr(), rows, heads, dim_head, _stream())
+         dscale.data_ptr(), rows, heads, dim_head, _stream(), work=("B", float(rows) * heads * dim_head * 6))
 
 
 def sgemm(A, B, Cm, *, M, N, K, trans_a=False, trans_b=False, lda=None, ldb=None, ldc=None, bias=None, act=0,
@@ -201,7 +221,8 @@ def cpb_reduce(dbias, heads, h, w, dtable):
 
 def geglu_bwd(dg, h, *, M, n_pairs, colsum_out=None, ld_dg=None, ld_h=None):
     call("ctclip_geglu_bwd", dg.data_ptr(), ld_dg if ld_dg is not None else dg.stride(0), h.data_ptr(),
-         ld_h if ld_h is not None else h.stride(0), M, n_pairs, _ptr(colsum_out), _stream())
+         ld_h if ld_h is not None else h.stride(0), M, n_pairs, _ptr(colsum_out), _stream(),
+         work=("B", float(M) * n_pairs * 10))
 
 
 def l2norm_rows_bf16(x, y, rows, D):
@@ -265,12 +286,12 @@ def clip_sims(t_hat, Bt, i_hat, Bi, L, temperature, out):
 
 
 def grad_sumsq(g, n, out):
-    call("ctclip_grad_sumsq", g.data_ptr(), n, out.data_ptr(), _stream())
+    call("ctclip_grad_sumsq", g.data_ptr(), n, out.data_ptr(), _stream(), work=("B", 4.0 * n))
 
 
 def adam_step(p, g, m, v, n, *, lr, beta1=0.9, beta2=0.99, eps=1e-8, step, max_norm=0.0, sumsq=None, grad_scale=1.0):
     call("ctclip_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
-         max_norm, _ptr(sumsq), grad_scale, _stream())
+         max_norm, _ptr(sumsq), grad_scale, _stream(), work=("B", 28.0 * n))
 
 
 def bert_embed(ids, word, pos, type0, out, rows, n, H):
