@@ -188,6 +188,17 @@ def run_b200(args):
     for w_ in range(args.warmup):
         trainer.step_on_batch(*dev[w_ % 2])
     barrier()
+    # CPU cost of enqueueing the forward pass (about a third of a step's launches) from an EMPTY launch queue: tells whether
+    # the Python/ctypes launch path could become the bottleneck (the whole-step figure below includes queue back-pressure)
+    clip.train()
+    torch.cuda.synchronize()
+    t_f0 = time.perf_counter()
+    l0 = _lib.launch_count
+    with torch.no_grad():
+        clip(dev[0][1], dev[0][0], return_loss=True, device=device)
+    host_fwd_ms = (time.perf_counter() - t_f0) * 1e3
+    host_fwd_launches = _lib.launch_count - l0
+    barrier()
     gemm_events = []
     ops.GEMM_TIMER = gemm_events
     sampler = ClockSampler(local)
@@ -307,6 +318,8 @@ def run_b200(args):
                                      "launches_per_step": n_g // max(1, args.steps),
                                      "share_of_step": gsum_ms / ms if ms > 0 else None}},
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "host_enqueue_fwd": {"ms": host_fwd_ms, "launches": host_fwd_launches,
+                             "note": "CPU time to enqueue one forward pass from an empty queue (no back-pressure)"},
         "model_tflops": step_flops * vols / (ms * 1e-3) / 1e12,
     }
     if stage_rows is not None:

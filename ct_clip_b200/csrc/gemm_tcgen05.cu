@@ -301,6 +301,21 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
     if (has_bias && colbase < p.N) bnext = __ldg(p.bias + colbase + lane);
     float4 rnext[8], rcur[8];
     if (kResid && colbase < p.N) resid_prefetch(rnext, p.resid + row0 * p.ldr + colbase, p.ldr, lane, rows_valid);
+    if (kResid) {
+      // Pull the residual tile of the NEXT unit of this CTA into L2 now (one 128-byte line per thread and chunk): the
+      // register prefetch above keeps only 4 KB per warp in flight, which capped these HBM-bound epilogues at ~3.8 TB/s.
+      const int nunit = unit + gridDim.x;
+      if (nunit < p.num_units) {
+        const int nn = nunit % p.n_groups;
+        const long long nrow = (long long)((nunit / p.n_groups) % p.m_blks) * BM + q * 32 + lane;
+        if (nrow < p.M) {
+          const float* pr = p.resid + nrow * p.ldr + nn * BN + half * 32;
+#pragma unroll
+          for (int i = 0; i < NCH; i++)
+            if (nn * BN + half * 32 + i * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i * 64));
+        }
+      }
+    }
     mbar_wait(&tfull_bar[acc], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 32;
@@ -828,18 +843,47 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
                       a->ldc % 8 == 0 && a->ldc2 % 8 == 0,
                   "gemm: L2NORM needs C2, norm_scale, N/norm_cols multiples of 32 and 16B-aligned rows");
   if (a->epilogue == EPI_BIAS_GELU) CTB_CHECK_ARG(a->ldc % 8 == 0 && (a->C2 == nullptr || a->ldc2 % 8 == 0), "gemm: BIAS_GELU needs 16B-aligned rows");
-  CTB_CHECK_ARG(a->splits >= 1, "gemm: splits must be >= 1");
+  CTB_CHECK_ARG(a->splits >= 0, "gemm: splits must be >= 0 (0 = choose automatically, ATOMIC_F32 only)");
   CTB_CHECK_ARG(a->splits == 1 || a->epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the ATOMIC_F32 epilogue");
   if (a->epilogue == EPI_ARGMAX) CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
   else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU || a->epilogue == EPI_L2NORM, "gemm: null C");
   if (a->epilogue == EPI_GEGLU) CTB_CHECK_ARG(a->C2 != nullptr && (a->N % 2) == 0, "gemm: GEGLU needs C2 and even N");
   if (a->epilogue == EPI_RESID_F32) CTB_CHECK_ARG(a->resid != nullptr, "gemm: RESID_F32 needs resid");
 
+  // Tile-N selection: 256 whenever N > 128 (a partial last tile costs less than the doubled shared-memory traffic per
+  // flop of 128-wide tiles: gemm_probe, profiles/), 128 for 64 < N <= 128, 64 for tiny N.
+  int bn;
+  if (a->epilogue == EPI_ARGMAX) bn = (a->N % 256 == 0) ? 256 : (a->N > 64 ? 128 : 64);
+  else if (a->N > 128) bn = 256;
+  else if (a->N > 64) bn = 128;
+  else bn = 64;
+  // keep at least ~1 wave of work for mid-sized problems without split-K
+  if (bn == 256 && a->epilogue != EPI_ARGMAX && a->epilogue != EPI_ATOMIC_F32 &&
+      (long long)ceil_div(a->M, BM) * ceil_div(a->N, 256) < num_sms() && a->N % 128 == 0) bn = 128;
+  static const int force_bn = getenv("CTCLIP_GEMM_BN") ? atoi(getenv("CTCLIP_GEMM_BN")) : 0;
+  if ((force_bn == 64 || force_bn == 128 || force_bn == 256) && a->epilogue != EPI_ARGMAX) bn = force_bn;
+
   GemmKParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_blks = ceil_div(a->M, BM);
   p.k_blks = ceil_div(a->K, BK);
-  p.splits = a->splits > p.k_blks ? p.k_blks : a->splits;
+  int want_splits = a->splits;
+  if (want_splits == 0) {
+    // automatic split-K: minimise  waves x (k-blocks per unit + epilogue cost of one unit in k-block equivalents)
+    const long long tiles = (long long)p.m_blks * ceil_div(a->N, bn);
+    const int sms = num_sms();
+    long long best_cost = -1;
+    want_splits = 1;
+    for (int sp = 1; sp <= p.k_blks && sp <= 1024; sp++) {
+      const int kbps = ceil_div(p.k_blks, sp);
+      const int real = ceil_div(p.k_blks, kbps);
+      if (real != sp) continue;
+      const long long waves = (tiles * real + sms - 1) / sms;
+      const long long cost = waves * (kbps + 6);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; want_splits = sp; }
+    }
+  }
+  p.splits = want_splits > p.k_blks ? p.k_blks : want_splits;
   p.k_blks_per_split = ceil_div(p.k_blks, p.splits);
   p.splits = ceil_div(p.k_blks, p.k_blks_per_split);  // no empty splits
   p.epi = a->epilogue;
@@ -865,17 +909,6 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
     p.fast_epi = (ok && (a->N % 32 == 0) && !old_epi) ? 1 : 0;
     if (epi_none && p.fast_epi) p.epi = EPI_NONE_DEBUG;
   }
-
-  // Tile-N selection: 256 where it divides N (fewest B re-reads per MMA), else 128, 64 for tiny N.
-  int bn;
-  if (a->N % 256 == 0) bn = 256;
-  else if (a->N > 64) bn = 128;
-  else bn = 64;
-  // keep at least ~1 wave of work for mid-sized problems
-  if (bn == 256 && a->epilogue != EPI_ARGMAX &&
-      (long long)ceil_div(a->M, BM) * (a->N / 256) * p.splits < num_sms() && a->N % 128 == 0) bn = 128;
-  static const int force_bn = getenv("CTCLIP_GEMM_BN") ? atoi(getenv("CTCLIP_GEMM_BN")) : 0;
-  if ((force_bn == 64 || force_bn == 128 || force_bn == 256) && a->epilogue != EPI_ARGMAX) bn = force_bn;
 
 #define CTB_DISPATCH(BN_)                                                                    \
   do {                                                                                       \

@@ -133,8 +133,9 @@ __global__ void cpb_expand_frag_kernel(const float* __restrict__ table, int head
       v = table[(long long)r1 * heads + hd];
       vt = table[(long long)r2 * heads + hd];
     }
-    frag[idx] = __float2bfloat16(v);
-    frag_t[idx] = __float2bfloat16(vt);
+    // the attention kernels work in the log2 domain: store bias * log2(e) (one multiply less per score element)
+    frag[idx] = __float2bfloat16(v * 1.4426950408889634f);
+    frag_t[idx] = __float2bfloat16(vt * 1.4426950408889634f);
   }
 }
 // dtable[r][hd] = sum over (i,j) with rel(i,j) == r of dbias[hd][i][j]

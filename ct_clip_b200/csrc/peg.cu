@@ -46,11 +46,12 @@ __device__ __forceinline__ long long peg_canon(const PegGeom& g, int a0, int a1,
 // block); a column is walked along the causal axis a0 with a ROLLING ring of planes in shared memory
 // ([slot][a1 halo][a2 halo][32 ch] fp32): every step loads ONE new plane with cp.async (halo factor
 // (A1T+2)(W+2)/(A1T*W) ~ 1.35x of compulsory traffic, 128 B coalesced segments) while the previous one is computed.
-// Each thread (= one line x one channel) slides a register window along a2: 9 LDS + 27 FFMA per output, the window
-// rotates through FOUR register columns so that the loads of output i+1 are issued before the FMAs of output i, and
-// all shared-memory addresses are [running 32-bit offset + immediate] (v2/v3 spent 2/3 of their issue slots on 64-bit
-// address arithmetic and on the integer divisions of the plane loader; the loader's (line, column) decomposition is now
-// done once per column and kept in registers).
+// Each thread (= one line x one PAIR of channels x one half of the a2 range) slides a register window along a2 with
+// packed fp32x2 arithmetic: 18 LDS.64 + 54 FFMA2 per two outputs x two channels (the scalar v2-v4 kernels were
+// issue-bound at 80-95 instructions per output and 48 % issue utilisation with 8 warps per SM; ncu: profiles/). The
+// window holds FOUR register columns, two outputs are computed per load group (four independent FFMA2 chains), and
+// all shared-memory addresses are [running 32-bit offset + immediate]; the plane loader's (line, column) decomposition
+// is done once per column and kept in registers.
 // The grid is PERSISTENT: all (column, plane) steps are linearised and cut into gridDim.x equal contiguous ranges, so
 // every SM gets the same number of plane-steps (the former one-CTA-per-column grid ran 2.6 waves = 3 wave times).
 // ------------------------------------------------------------------------------------------------
@@ -139,39 +140,76 @@ __device__ __forceinline__ void peg_load_dy4(float* buf, const float* __restrict
   }
 }
 
-// shared-memory window loads: [32-bit running byte offset + immediate column offset]
-#define PEG_LD(smb, po, r, col) (*reinterpret_cast<const float*>((smb) + (po)[r] + (col) * (CB * 4)))
-
-// One output of the sliding window. The window holds FOUR columns per row; output ROT uses columns
-// (ROT, ROT+1, ROT+2) mod 4 as (left, centre, right) while column (ROT+3) mod 4 receives the right-hand element of
-// the NEXT output, so those loads are in flight during this output's FMAs. Two accumulation chains.
-template <int ROT>
-__device__ __forceinline__ float peg_out(float (&win)[9][4], const char* smb, const uint32_t (&po)[9],
-                                         const float (&wt)[27], float init) {
-  constexpr int L = ROT % 4, C = (ROT + 1) % 4, R = (ROT + 2) % 4, N = (ROT + 3) % 4;
-#pragma unroll
-  for (int r = 0; r < 9; r++) win[r][N] = PEG_LD(smb, po, r, ROT + 3);
-  float acc0 = init, acc1 = 0.f;
-#pragma unroll
-  for (int r = 0; r < 9; r++) {
-    float& acc = (r & 1) ? acc1 : acc0;
-    acc = fmaf(wt[r * 3 + 0], win[r][L], acc);
-    acc = fmaf(wt[r * 3 + 1], win[r][C], acc);
-    acc = fmaf(wt[r * 3 + 2], win[r][R], acc);
-  }
-  return acc0 + acc1;
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2: two FMAs per issued instruction) -----------------------------------
+typedef unsigned long long f2_t;   // (lo, hi) = (channel c, channel c+1)
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-template <int ROT>
-__device__ __forceinline__ void peg_wout(float (&win)[9][4], const char* smb, const uint32_t (&po)[9], float (&acc)[27],
-                                         float d) {
-  constexpr int L = ROT % 4, C = (ROT + 1) % 4, R = (ROT + 2) % 4, N = (ROT + 3) % 4;
-#pragma unroll
-  for (int r = 0; r < 9; r++) win[r][N] = PEG_LD(smb, po, r, ROT + 3);
+__device__ __forceinline__ float2 f2_unpack(f2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// shared-memory window loads: [32-bit running byte offset + immediate column offset], 8 bytes = one channel pair
+#define PEG_LD2(smb, po, r, col) (*reinterpret_cast<const f2_t*>((smb) + (po)[r] + (col) * (CB * 4)))
+
+// Thread layout of the compute phase (256 threads): pair = tid & 15 (channels 2*pair, 2*pair+1), line = (tid >> 4) & 7,
+// seg = tid >> 7: the a2 range [0, W) is cut into PEG_NSEG segments so that every (line, channel pair) is worked on by
+// PEG_NSEG threads. A half-warp reads / writes the 128 contiguous bytes of one token's 32 channels.
+constexpr int PEG_NSEG = PEG_THREADS / (16 * A1T);   // 2
+
+// Two outputs (a2, a2+1) of the sliding window per call: the window holds FOUR columns per row; the call loads the two
+// columns (halo index a2+2, a2+3) into window slots (R0+2, R0+3) mod 4, output a2 uses slots (R0, R0+1, R0+2) and output
+// a2+1 uses (R0+1, R0+2, R0+3): four independent FFMA2 chains (2 outputs x 2 partial sums).
+template <int R0>
+__device__ __forceinline__ void peg_out2(f2_t (&win)[9][4], const char* smb, const uint32_t (&po)[9], const f2_t (&wt)[27],
+                                         f2_t init, f2_t& o0, f2_t& o1) {
+  constexpr int A = R0 % 4, B = (R0 + 1) % 4, C = (R0 + 2) % 4, D = (R0 + 3) % 4;
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    acc[r * 3 + 0] = fmaf(d, win[r][L], acc[r * 3 + 0]);
-    acc[r * 3 + 1] = fmaf(d, win[r][C], acc[r * 3 + 1]);
-    acc[r * 3 + 2] = fmaf(d, win[r][R], acc[r * 3 + 2]);
+    win[r][C] = PEG_LD2(smb, po, r, R0 + 2);
+    win[r][D] = PEG_LD2(smb, po, r, R0 + 3);
+  }
+  f2_t a0 = init, a1 = 0ull, b0 = init, b1 = 0ull;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    f2_t& x = (r & 1) ? a1 : a0;
+    f2_t& y = (r & 1) ? b1 : b0;
+    x = f2_fma(wt[r * 3 + 0], win[r][A], x);
+    y = f2_fma(wt[r * 3 + 0], win[r][B], y);
+    x = f2_fma(wt[r * 3 + 1], win[r][B], x);
+    y = f2_fma(wt[r * 3 + 1], win[r][C], y);
+    x = f2_fma(wt[r * 3 + 2], win[r][C], x);
+    y = f2_fma(wt[r * 3 + 2], win[r][D], y);
+  }
+  const float2 fa0 = f2_unpack(a0), fa1 = f2_unpack(a1), fb0 = f2_unpack(b0), fb1 = f2_unpack(b1);
+  o0 = f2_pack(fa0.x + fa1.x, fa0.y + fa1.y);
+  o1 = f2_pack(fb0.x + fb1.x, fb0.y + fb1.y);
+}
+template <int R0>
+__device__ __forceinline__ void peg_wout2(f2_t (&win)[9][4], const char* smb, const uint32_t (&po)[9], f2_t (&acc)[27],
+                                          f2_t d0, f2_t d1) {
+  constexpr int A = R0 % 4, B = (R0 + 1) % 4, C = (R0 + 2) % 4, D = (R0 + 3) % 4;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    win[r][C] = PEG_LD2(smb, po, r, R0 + 2);
+    win[r][D] = PEG_LD2(smb, po, r, R0 + 3);
+  }
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    acc[r * 3 + 0] = f2_fma(d0, win[r][A], acc[r * 3 + 0]);
+    acc[r * 3 + 1] = f2_fma(d0, win[r][B], acc[r * 3 + 1]);
+    acc[r * 3 + 2] = f2_fma(d0, win[r][C], acc[r * 3 + 2]);
+    acc[r * 3 + 0] = f2_fma(d1, win[r][B], acc[r * 3 + 0]);
+    acc[r * 3 + 1] = f2_fma(d1, win[r][C], acc[r * 3 + 1]);
+    acc[r * 3 + 2] = f2_fma(d1, win[r][D], acc[r * 3 + 2]);
   }
 }
 
@@ -189,7 +227,9 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
   const int s_begin = blockIdx.x * steps_per_cta;
   const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
-  const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;  // channel, a1 line within the tile
+  const int pair = threadIdx.x & 15, line = (threadIdx.x >> 4) & (A1T - 1), seg = threadIdx.x >> 7;
+  const int seg_len = (((a.W + PEG_NSEG - 1) / PEG_NSEG) + 1) & ~1;   // even
+  const int b0 = min(a.W, seg * seg_len), b1 = min(a.W, b0 + seg_len);
   int* s_tok = reinterpret_cast<int*>(peg_sm + (size_t)NSLOT * slot_elems);   // [2][A1T][W] canonical token of every output
   const char* smb = reinterpret_cast<const char*>(peg_sm);
   int inpl[PEG_MAXIT];
@@ -200,13 +240,17 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
     const int p_end = min(a.T, p_begin + (s_end - s));
     const PegCol cc = peg_column(col, n_cb, n_a1t);
     const float* xin = a.x + (long long)cc.b * vol + cc.c0;
-    float* yout = a.y + (long long)cc.b * vol + cc.c0;
-    __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)cc.b * vol + cc.c0 : nullptr;
-    const int ch = cc.c0 + lane;
-    float wt[27];
+    float* yout = a.y + (long long)cc.b * vol + cc.c0 + 2 * pair;
+    __nv_bfloat16* ybf =
+        a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)cc.b * vol + cc.c0 + 2 * pair : nullptr;
+    const int ch = cc.c0 + 2 * pair;
+    f2_t wt[27];
 #pragma unroll
-    for (int k = 0; k < 27; k++) wt[k] = __ldg(a.weight + (long long)ch * 27 + ((MODE == 0) ? k : 26 - k));
-    const float bias = (MODE == 0 && a.bias != nullptr) ? __ldg(a.bias + ch) : 0.f;
+    for (int k = 0; k < 27; k++) {
+      const int kk = (MODE == 0) ? k : 26 - k;
+      wt[k] = f2_pack(__ldg(a.weight + (long long)ch * 27 + kk), __ldg(a.weight + (long long)(ch + 1) * 27 + kk));
+    }
+    const f2_t bias2 = (MODE == 0 && a.bias != nullptr) ? f2_pack(__ldg(a.bias + ch), __ldg(a.bias + ch + 1)) : 0ull;
     const int a1 = cc.a1_0 + line;
     __syncthreads();   // the previous column's last plane (ring + token table) is fully consumed
     peg_loader_setup(inpl, nit, n_items, a2h, cc.a1_0, a.H, a.W);
@@ -233,33 +277,39 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
         peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
         peg_commit();
       }
-      if (a1 < a.H) {
+      if (a1 < a.H && b0 < b1) {
         uint32_t po[9];
 #pragma unroll
         for (int r = 0; r < 9; r++) {
           const int k0 = r / 3, k1 = r % 3;
           const int pl = (MODE == 0) ? (a0 + k0 - 2) : (a0 + k0);
-          po[r] = (uint32_t)(peg_slot(pl) * slot_elems + (line + k1) * a2h * CB + lane) * 4u;
+          po[r] = (uint32_t)(peg_slot(pl) * slot_elems + ((line + k1) * a2h + b0) * CB + 2 * pair) * 4u;
         }
-        float win[9][4];
+        f2_t win[9][4];
 #pragma unroll
         for (int r = 0; r < 9; r++) {
-          win[r][0] = PEG_LD(smb, po, r, 0);   // a2 = -1 (zero padding)
-          win[r][1] = PEG_LD(smb, po, r, 1);   // a2 = 0
-          win[r][2] = PEG_LD(smb, po, r, 2);   // a2 = 1
+          win[r][0] = PEG_LD2(smb, po, r, 0);   // a2 = b0 - 1 (zero padding when b0 == 0)
+          win[r][1] = PEG_LD2(smb, po, r, 1);   // a2 = b0
         }
         constexpr int CR = (MODE == 0) ? 7 : 1;   // row of the centre tap (k0 = 2 | 0, k1 = 1): its centre element = residual
         const int* tokl = s_tok + par * A1T * a.W + line * a.W;
-        auto emit = [&](int a2, float val) {
-          const long long off = (long long)tokl[a2] * a.D + lane;
-          yout[off] = val;
-          if (ybf != nullptr) ybf[off] = __float2bfloat16(val);
+        auto emit = [&](int a2, f2_t conv, f2_t centre) {
+          const float2 cv = f2_unpack(conv), ce = f2_unpack(centre);
+          const float2 val = make_float2(cv.x + ce.x, cv.y + ce.y);
+          const long long off = (long long)tokl[a2] * a.D;
+          *reinterpret_cast<float2*>(yout + off) = val;
+          if (ybf != nullptr) *reinterpret_cast<uint32_t*>(ybf + off) = pack_bf16x2(val.x, val.y);
         };
-        for (int a2 = 0; a2 < a.W; a2 += 4) {
-          emit(a2, peg_out<0>(win, smb, po, wt, bias) + win[CR][1]);
-          if (a2 + 1 < a.W) emit(a2 + 1, peg_out<1>(win, smb, po, wt, bias) + win[CR][2]);
-          if (a2 + 2 < a.W) emit(a2 + 2, peg_out<2>(win, smb, po, wt, bias) + win[CR][3]);
-          if (a2 + 3 < a.W) emit(a2 + 3, peg_out<3>(win, smb, po, wt, bias) + win[CR][0]);
+        for (int a2 = b0; a2 < b1; a2 += 4) {
+          f2_t o0, o1;
+          peg_out2<0>(win, smb, po, wt, bias2, o0, o1);
+          emit(a2, o0, win[CR][1]);
+          if (a2 + 1 < b1) emit(a2 + 1, o1, win[CR][2]);
+          if (a2 + 2 < b1) {
+            peg_out2<2>(win, smb, po, wt, bias2, o0, o1);
+            emit(a2 + 2, o0, win[CR][3]);
+            if (a2 + 3 < b1) emit(a2 + 3, o1, win[CR][0]);
+          }
 #pragma unroll
           for (int r = 0; r < 9; r++) po[r] += 4 * CB * 4;
         }
@@ -271,8 +321,9 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
 
 // dw[c][k] += sum_p dy[p] * x[p + off(k)], db[c] += sum_p dy[p]
 // x planes in the 4-slot ring, the upstream-gradient tile of the same plane in a 2-slot ring, both prefetched with cp.async.
-// Same persistent (column, plane) ranges as the conv kernel; the 27+1 partial sums of a thread are reduced across the 8
-// lines of the CTA through shared memory at the end of every column segment -> one atomic per (channel, tap).
+// Same persistent (column, plane) ranges and thread layout as the conv kernel; the 27+1 partial sums of a thread are
+// reduced across the 8 lines x 2 segments of the CTA through shared memory at the end of every column segment -> one
+// atomic per (channel, tap).
 __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_args a, int steps_per_cta, int dy_double) {
   extern __shared__ __align__(16) float peg_sm[];
   const PegGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table};
@@ -287,7 +338,9 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
   const int s_begin = blockIdx.x * steps_per_cta;
   const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
-  const int lane = threadIdx.x & 31, line = threadIdx.x >> 5;
+  const int pair = threadIdx.x & 15, line = (threadIdx.x >> 4) & (A1T - 1), seg = threadIdx.x >> 7;
+  const int seg_len = (((a.W + PEG_NSEG - 1) / PEG_NSEG) + 1) & ~1;
+  const int b0 = min(a.W, seg * seg_len), b1 = min(a.W, b0 + seg_len);
   const char* smb = reinterpret_cast<const char*>(peg_sm);
   int inpl[PEG_MAXIT];
   for (int s = s_begin; s < s_end;) {
@@ -298,10 +351,10 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
     const float* xin = a.x + (long long)cc.b * vol + cc.c0;
     const float* dy = a.dy + (long long)cc.b * vol + cc.c0;
     const int a1 = cc.a1_0 + line;
-    float acc[27];
+    f2_t acc[27];
 #pragma unroll
-    for (int k = 0; k < 27; k++) acc[k] = 0.f;
-    float accb = 0.f;
+    for (int k = 0; k < 27; k++) acc[k] = 0ull;
+    float accb0 = 0.f, accb1 = 0.f;
     __syncthreads();   // previous column: reduction scratch / ring fully consumed
     peg_loader_setup(inpl, nit, n_items, a2h, cc.a1_0, a.H, a.W);
     for (int d = 2; d >= 0; d--) {
@@ -324,48 +377,51 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
         if (dy_double) peg_load_dy4(sdy + (size_t)(par ^ 1) * dy_elems, dy, g, a0 + 1, cc.a1_0);
         peg_commit();
       }
-      if (a1 < a.H) {
+      if (a1 < a.H && b0 < b1) {
         uint32_t po[9];
 #pragma unroll
         for (int r = 0; r < 9; r++) {
           const int k0 = r / 3, k1 = r % 3;
-          po[r] = (uint32_t)(peg_slot(a0 + k0 - 2) * slot_elems + (line + k1) * a2h * CB + lane) * 4u;
+          po[r] = (uint32_t)(peg_slot(a0 + k0 - 2) * slot_elems + ((line + k1) * a2h + b0) * CB + 2 * pair) * 4u;
         }
-        const float* dyl = sdy + (size_t)par * dy_elems + (size_t)(line * a.W) * CB + lane;
-        float win[9][4];
+        const f2_t* dyl = reinterpret_cast<const f2_t*>(sdy + (size_t)par * dy_elems + (size_t)(line * a.W) * CB + 2 * pair);
+        f2_t win[9][4];
 #pragma unroll
         for (int r = 0; r < 9; r++) {
-          win[r][0] = PEG_LD(smb, po, r, 0);
-          win[r][1] = PEG_LD(smb, po, r, 1);
-          win[r][2] = PEG_LD(smb, po, r, 2);
+          win[r][0] = PEG_LD2(smb, po, r, 0);
+          win[r][1] = PEG_LD2(smb, po, r, 1);
         }
-        for (int a2 = 0; a2 < a.W; a2 += 4) {
-          const float d0 = dyl[a2 * CB];
-          const float d1 = (a2 + 1 < a.W) ? dyl[(a2 + 1) * CB] : 0.f;
-          const float d2 = (a2 + 2 < a.W) ? dyl[(a2 + 2) * CB] : 0.f;
-          const float d3 = (a2 + 3 < a.W) ? dyl[(a2 + 3) * CB] : 0.f;
-          accb += (d0 + d1) + (d2 + d3);
-          peg_wout<0>(win, smb, po, acc, d0);
-          if (a2 + 1 < a.W) peg_wout<1>(win, smb, po, acc, d1);
-          if (a2 + 2 < a.W) peg_wout<2>(win, smb, po, acc, d2);
-          if (a2 + 3 < a.W) peg_wout<3>(win, smb, po, acc, d3);
+        for (int a2 = b0; a2 < b1; a2 += 4) {
+          const f2_t d0 = dyl[a2 * (CB / 2)];
+          const f2_t d1 = (a2 + 1 < b1) ? dyl[(a2 + 1) * (CB / 2)] : 0ull;
+          const f2_t d2 = (a2 + 2 < b1) ? dyl[(a2 + 2) * (CB / 2)] : 0ull;
+          const f2_t d3 = (a2 + 3 < b1) ? dyl[(a2 + 3) * (CB / 2)] : 0ull;
+          const float2 e0 = f2_unpack(d0), e1 = f2_unpack(d1), e2 = f2_unpack(d2), e3 = f2_unpack(d3);
+          accb0 += (e0.x + e1.x) + (e2.x + e3.x);
+          accb1 += (e0.y + e1.y) + (e2.y + e3.y);
+          peg_wout2<0>(win, smb, po, acc, d0, d1);
+          if (a2 + 2 < b1) peg_wout2<2>(win, smb, po, acc, d2, d3);
 #pragma unroll
           for (int r = 0; r < 9; r++) po[r] += 4 * CB * 4;
         }
       }
     }
-    // reduce the A1T lines of this CTA (same channel = same lane) through shared memory, one atomic per (channel, tap)
+    // reduce the (line, segment) partial sums of this CTA through shared memory, one atomic per (channel, tap)
     __syncthreads();
-    float* red = peg_sm;  // [A1T][28][CB]
+    float* red = peg_sm;  // [A1T * PEG_NSEG][28][CB]
+    const int slot = line * PEG_NSEG + seg;
 #pragma unroll
-    for (int k = 0; k < 27; k++) red[(line * 28 + k) * CB + lane] = acc[k];
-    red[(line * 28 + 27) * CB + lane] = accb;
+    for (int k = 0; k < 27; k++) {
+      const float2 v = f2_unpack(acc[k]);
+      *reinterpret_cast<float2*>(red + (slot * 28 + k) * CB + 2 * pair) = v;
+    }
+    *reinterpret_cast<float2*>(red + (slot * 28 + 27) * CB + 2 * pair) = make_float2(accb0, accb1);
     __syncthreads();
     for (int i = threadIdx.x; i < 28 * CB; i += PEG_THREADS) {
       const int k = i / CB, c = i % CB;
       float t = 0.f;
 #pragma unroll
-      for (int l = 0; l < A1T; l++) t += red[(l * 28 + k) * CB + c];
+      for (int l = 0; l < A1T * PEG_NSEG; l++) t += red[(l * 28 + k) * CB + c];
       if (k < 27) atomicAdd(a.dweight + (long long)(cc.c0 + c) * 27 + k, t);
       else if (a.dbias != nullptr) atomicAdd(a.dbias + cc.c0 + c, t);
     }
@@ -399,7 +455,7 @@ static void peg_launch_shape(const ctclip_peg_args* a, int dy_bufs, int* grid, i
   if (dy_bufs == 0) *smem += sizeof(int) * 2 * (size_t)A1T * a->W;   // token-index table of the conv kernels
   *smem += sizeof(float) * dy_bufs * (size_t)A1T * a->W * CB;
   *smem += 1024;   // the rotating window reads up to 6 columns past the end of the last row
-  const size_t red_bytes = sizeof(float) * A1T * 28 * CB;  // weight-gradient reduction scratch
+  const size_t red_bytes = sizeof(float) * A1T * PEG_NSEG * 28 * CB;  // weight-gradient reduction scratch
   if (*smem < red_bytes) *smem = red_bytes;
 }
 

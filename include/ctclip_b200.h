@@ -56,7 +56,7 @@ const char* ctclip_last_error(void);
  *                C2(bf16)[m,n] = acc / max(||acc_group||, 1e-12) * norm_scale[n % 32]   for n < norm_cols
  *                (attention.py:152-154 l2norm(q)*q_scale fused into the projection)
  *   7 BIAS_GELU  C(bf16) = gelu_erf(acc + bias), C2(bf16, optional) = acc + bias  (BERT intermediate)
- * splits: split-K factor (only with ATOMIC_F32), >= 1.
+ * splits: split-K factor (only with ATOMIC_F32), >= 1; 0 = chosen by the library (minimises waves x k-blocks per unit).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t M, N, K;
@@ -201,8 +201,9 @@ typedef struct {
   int64_t total_rows;
   const int32_t* key_mask; /* optional [num_seqs, n]: non-zero = key may be attended (BERT padding mask) */
   /* optional: the same bias (and its transpose) re-ordered per MMA fragment by ctclip_cpb_expand_frag:
-   * bf16 [heads, ceil16(n)/16, ceil64(n)/64, 32 lanes, 8 n-tiles, 4]; when given they replace bias / bias_t in the
-   * forward, dQ and dK/dV kernels (fully coalesced 16-byte loads). */
+   * bf16 [heads, ceil16(n)/16, ceil64(n)/64, 32 lanes, 8 n-tiles, 4], values PRE-MULTIPLIED by log2(e) (the kernels
+   * work in the log2 domain); when given they replace bias / bias_t in the forward, dQ and dK/dV kernels (fully
+   * coalesced 16-byte loads). */
   const uint16_t* bias_frag;
   const uint16_t* bias_t_frag;
 } ctclip_attn_args;
@@ -242,7 +243,7 @@ int ctclip_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int ctclip_cpb_inputs(float* X, int32_t h, int32_t w, void* stream);
 int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, int32_t w, void* bias, void* bias_t, void* stream);
 int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream);
-/* fragment-ordered copies of the bias and of its transpose (see ctclip_attn_args.bias_frag) */
+/* fragment-ordered copies of bias * log2(e) and of its transpose (see ctclip_attn_args.bias_frag) */
 int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t w, void* bias_frag, void* bias_t_frag,
                            void* stream);
 

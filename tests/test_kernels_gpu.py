@@ -164,8 +164,9 @@ def test_attention_fwd_bwd(mode, b, T, S):
     o = torch.empty(M, I, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(M, heads, device=DEV)
     if use_frag:    # fragment-ordered bias tables (what the encoder uses); the dense table still feeds the dbias kernel
-        geom["bias_frag"] = _to_frag(bias)
-        geom["bias_t_frag"] = _to_frag(bias_t)
+        log2e = 1.4426950408889634   # the fragment tables hold bias * log2(e) (ctclip_cpb_expand_frag)
+        geom["bias_frag"] = _to_frag((bias.float() * log2e).to(bias.dtype))
+        geom["bias_t_frag"] = _to_frag((bias_t.float() * log2e).to(bias_t.dtype))
         bias_t = None
     ops.attn_fwd(q, k, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, **geom)
     qs, ks, vs = (to_seq(t).requires_grad_(True) for t in (q, k, v))

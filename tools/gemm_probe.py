@@ -22,9 +22,11 @@ SHAPES = [
     (M, 512, 256, 0, 0, 2, 1, "out-proj fwd RESID"),
     (M, 512, 512, 0, 0, 6, 1, "kv-proj fwd L2NORM"),
     (M, 256, 512, 0, 0, 6, 1, "q-proj fwd L2NORM"),
-    (2816, 512, M, 1, 1, 4, 7, "FF1 wgrad"),
-    (512, 1365, M, 1, 1, 4, 14, "FF2 wgrad"),
+    (2816, 512, M, 1, 1, 4, 0, "FF1 wgrad"),
+    (512, 1365, M, 1, 1, 4, 0, "FF2 wgrad"),
     (M, 512, 4000, 0, 0, 1, 1, "patch fwd F32"),
+    (512, 512, M, 1, 1, 4, 0, "kv wgrad"),
+    (512, 4000, M, 1, 1, 4, 0, "patch wgrad"),
 ]
 
 
@@ -80,10 +82,10 @@ VARIANTS = [
     ("default (v2 epilogue)", {}),
     ("v1 epilogue", {"CTCLIP_GEMM_OLD_EPI": "1"}),
     ("no epilogue stores (mainloop ceiling)", {"CTCLIP_GEMM_EPI_NONE": "1"}),
-    ("BN=256 forced", {"CTCLIP_GEMM_BN": "256"}),
     ("BN=128 forced", {"CTCLIP_GEMM_BN": "128"}),
-    ("BN=128, no epilogue stores", {"CTCLIP_GEMM_BN": "128", "CTCLIP_GEMM_EPI_NONE": "1"}),
 ]
+if "--quick" in sys.argv:
+    VARIANTS = [VARIANTS[0], VARIANTS[2]]
 
 if __name__ == "__main__":
     if "--one" in sys.argv:
