@@ -243,6 +243,24 @@ __device__ __forceinline__ void logits_tile_full(float (&s)[NT][4], float sc2, c
   }
 }
 
+// Same with the bias fragments already in registers (loaded one key block ahead: the L2 latency of the table used to be
+// the top stall of the forward / dQ / dKV kernels).
+template <int NT>
+__device__ __forceinline__ void logits_tile_full_regs(float (&s)[NT][4], float sc2, const uint4 (&b)[NT / 2]) {
+#pragma unroll
+  for (int i = 0; i < NT / 2; i++) {
+    const float2 a0 = unpack_bf16x2(b[i].x), b0 = unpack_bf16x2(b[i].y), a1 = unpack_bf16x2(b[i].z), b1 = unpack_bf16x2(b[i].w);
+    s[2 * i][0] = fmaf(s[2 * i][0], sc2, a0.x);
+    s[2 * i][1] = fmaf(s[2 * i][1], sc2, a0.y);
+    s[2 * i][2] = fmaf(s[2 * i][2], sc2, b0.x);
+    s[2 * i][3] = fmaf(s[2 * i][3], sc2, b0.y);
+    s[2 * i + 1][0] = fmaf(s[2 * i + 1][0], sc2, a1.x);
+    s[2 * i + 1][1] = fmaf(s[2 * i + 1][1], sc2, a1.y);
+    s[2 * i + 1][2] = fmaf(s[2 * i + 1][2], sc2, b1.x);
+    s[2 * i + 1][3] = fmaf(s[2 * i + 1][3], sc2, b1.y);
+  }
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -302,6 +320,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
     float oacc[DH / 8][4];
 #pragma unroll
     for (int dt = 0; dt < DH / 8; dt++) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+    const bool use_frag = !MASK && bias_frag != nullptr;
+    const uint2* bfr_row = use_frag ? bias_frag + (((long long)head * row_tiles + rt) * kblocks * 32 + lane) * 8 : nullptr;
+    uint4 bcur[4];
+    if (use_frag && 64 <= a.n) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) bcur[i] = __ldg(reinterpret_cast<const uint4*>(bfr_row) + i);
+    }
     for (int key0 = 0; key0 < n_pad; key0 += 64) {
       float s[8][4];
       const int rem = n_pad - key0;  // multiple of 16
@@ -309,9 +334,20 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8
                                    : nullptr;
       const bool full = !MASK && (key0 + 64 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
+      const bool nfull = use_frag && (key0 + 128 <= a.n);   // the next key block is complete too: fetch its bias now
+      uint4 bnxt[4];
+      if (nfull) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) bnxt[i] = __ldg(reinterpret_cast<const uint4*>(bfr + 256) + i);
+      }
       if (full) {
         qk_block<8, DH, true>(s, qa, sK, key0, lane);
-        logits_tile_full<8>(s, sc2, bfr);
+        if (use_frag) logits_tile_full_regs<8>(s, sc2, bcur);
+        else logits_tile_full<8>(s, sc2, nullptr);
+        if (nfull) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) bcur[i] = bnxt[i];
+        }
       } else {
         qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
         logits_tile<8, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 64 <= a.n, pair_ok, sMask, ntv, bfr);
@@ -427,6 +463,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
     float dqa[DH / 8][4];
 #pragma unroll
     for (int dt = 0; dt < DH / 8; dt++) dqa[dt][0] = dqa[dt][1] = dqa[dt][2] = dqa[dt][3] = 0.f;
+    const bool use_frag = !MASK && bias_frag != nullptr;
+    uint4 bcur[2];
+    if (use_frag && 32 <= a.n) {
+      const uint4* p0 = reinterpret_cast<const uint4*>(bias_frag + (((long long)head * row_tiles + rt) * kblocks * 32 + lane) * 8);
+      bcur[0] = __ldg(p0);
+      bcur[1] = __ldg(p0 + 1);
+    }
     for (int key0 = 0; key0 < n_pad; key0 += 32) {
       float s[4][4], dp[4][4];
       const int rem = n_pad - key0;
@@ -435,10 +478,19 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
                                          ((key0 >> 5) & 1) * 4
                                    : nullptr;
       const bool full = !MASK && (key0 + 32 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
+      const bool nfull = use_frag && (key0 + 64 <= a.n);
+      uint4 bnxt[2];
+      if (nfull) {   // fragments of the next 32-key block: second half of this 64-key table block, or the next table block
+        const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((key0 >> 5) & 1) ? 256 - 4 : 4));
+        bnxt[0] = __ldg(pn);
+        bnxt[1] = __ldg(pn + 1);
+      }
       if (full) {
         qk_block<4, DH, true>(s, qa, sK, key0, lane);
         qk_block<4, DH, true>(dp, da, sV, key0, lane);
-        logits_tile_full<4>(s, sc2, bfr);
+        if (use_frag) logits_tile_full_regs<4>(s, sc2, bcur);
+        else logits_tile_full<4>(s, sc2, nullptr);
+        if (nfull) { bcur[0] = bnxt[0]; bcur[1] = bnxt[1]; }
       } else {
         qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
         qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
@@ -534,11 +586,19 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       dka[dt][0] = dka[dt][1] = dka[dt][2] = dka[dt][3] = 0.f;
       dva[dt][0] = dva[dt][1] = dva[dt][2] = dva[dt][3] = 0.f;
     }
+    const bool use_frag = bias_t_frag != nullptr;
+    uint4 bcur[2];
+    if (use_frag && 32 <= a.n) {
+      const uint4* p0 = reinterpret_cast<const uint4*>(bias_t_frag + (((long long)head * key_tiles + kt_) * qblocks * 32 + lane) * 8);
+      bcur[0] = __ldg(p0);
+      bcur[1] = __ldg(p0 + 1);
+    }
     for (int q0 = 0; q0 < n_pad; q0 += 32) {
       float s[4][4], dp[4][4];
       const int rem = n_pad - q0;
       const int ntv = rem >= 32 ? 4 : 2;
       const bool full = (q0 + 32 <= a.n) && (biasT == nullptr || bias_t_frag != nullptr);   // warp-uniform
+      const bool nfull = use_frag && (q0 + 64 <= a.n);
       if (full) {
         qk_block<4, DH, true>(s, ka, sQ, q0, lane);
         qk_block<4, DH, true>(dp, va, sDO, q0, lane);
@@ -550,8 +610,19 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       const uint2* bfr = bias_t_frag ? bias_t_frag + ((((long long)head * key_tiles + kt_) * qblocks + (q0 >> 6)) * 32 + lane) * 8 +
                                            ((q0 >> 5) & 1) * 4
                                      : nullptr;
-      if (full) logits_tile_full<4>(s, sc2, bfr);
-      else logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
+      uint4 bnxt[2];
+      if (nfull) {
+        const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((q0 >> 5) & 1) ? 256 - 4 : 4));
+        bnxt[0] = __ldg(pn);
+        bnxt[1] = __ldg(pn + 1);
+      }
+      if (full) {
+        if (use_frag) logits_tile_full_regs<4>(s, sc2, bcur);
+        else logits_tile_full<4>(s, sc2, nullptr);
+        if (nfull) { bcur[0] = bnxt[0]; bcur[1] = bnxt[1]; }
+      } else {
+        logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
+      }
       float ds[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {

@@ -19,8 +19,9 @@ namespace ctb {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;    // generic kernel; the EPW = 16 instantiation serves the register-light fused epilogues
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
+constexpr int EPW_LIGHT = 12;   // epilogue warps of the register-light variant: 14 warps -> 128 registers / thread
 
 enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5, EPI_L2NORM = 6, EPI_BIAS_GELU = 7 };
 
@@ -47,14 +48,14 @@ struct GemmKParams {
   int fast_epi;    // use the specialised epilogue loops (fast_store && N % 32 == 0 && not ARGMAX / ATOMIC)
 };
 
-template <int BN>
+template <int BN, int EPW = EPI_WARPS>
 struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/ + 1024 /*argmax merge*/ +
-                                    EPI_WARPS * 2048 /*epilogue store staging*/ + 1024 /*align*/;
+                                    EPW * 2048 /*epilogue store staging*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
@@ -279,14 +280,16 @@ __device__ __forceinline__ void fstore_f32(uint32_t st, int lane, const float (&
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int EPW>
 __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t st, uint32_t sb, int warp, int lane) {
-  constexpr int NCH = (BN / 32 + 1) / 2;        // 32-column chunks per warp and tile (chunks half, half+2, ...)
+  constexpr int CSTR = EPW / 4;                           // warps per TMEM lane quarter = chunk stride of one warp
+  constexpr int NCH = (BN / 32 + CSTR - 1) / CSTR;        // 32-column chunks per warp and tile (chunks half, half+CSTR, ...)
   constexpr bool kResid = (EPI == EPI_RESID_F32);
-  constexpr bool kTmemPrefetch = !kResid;       // RESID keeps its registers for the residual prefetch instead
+  // RESID keeps its registers for the residual prefetch; the 16-warp variant (112 registers / thread) has none to spare
+  constexpr bool kTmemPrefetch = !kResid && EPW == 8;
   const int q = warp & 3;
-  const int half = (warp - 2) >> 2;
+  const int half = (warp - 2) >> 2;                       // 0 .. CSTR-1
   const bool has_bias = p.bias != nullptr;
   uint32_t it = 0;
   for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, it++) {
@@ -312,7 +315,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
           const float* pr = p.resid + nrow * p.ldr + nn * BN + half * 32;
 #pragma unroll
           for (int i = 0; i < NCH; i++)
-            if (nn * BN + half * 32 + i * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i * 64));
+            if ((half + i * CSTR) * 32 < BN && nn * BN + half * 32 + i * (CSTR * 32) < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i * (CSTR * 32)));
         }
       }
     }
@@ -323,19 +326,19 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
     if (colbase < p.N) tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
-      const int col0 = colbase + i * 64;
-      if (col0 >= p.N) break;   // warp-uniform
+      const int col0 = colbase + i * (CSTR * 32);
+      if ((half + i * CSTR) * 32 >= BN || col0 >= p.N) break;   // warp-uniform
       constexpr int kCurMask = kTmemPrefetch ? 1 : 0;
       uint32_t(&cur)[32] = raw[i & kCurMask];
       tmem_ld_wait();
       reg_fence32(cur);
-      const bool has_next = (i + 1 < NCH) && (col0 + 64 < p.N);
-      if (kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * 64, raw[(i + 1) & 1]);
+      const bool has_next = (i + 1 < NCH) && ((half + (i + 1) * CSTR) * 32 < BN) && (col0 + CSTR * 32 < p.N);
+      if (kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * (CSTR * 32), raw[(i + 1) & 1]);
       float v[32];
       if (has_bias) {
         sts32(sb + lane * 4, bnext);
         __syncwarp();
-        if (has_next) bnext = __ldg(p.bias + col0 + 64 + lane);
+        if (has_next) bnext = __ldg(p.bias + col0 + CSTR * 32 + lane);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           const uint4 b = lds128(sb + k * 16);
@@ -352,9 +355,9 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
       if (kResid) {
 #pragma unroll
         for (int k = 0; k < 8; k++) rcur[k] = rnext[k];
-        if (has_next) resid_prefetch(rnext, p.resid + row0 * p.ldr + col0 + 64, p.ldr, lane, rows_valid);
+        if (has_next) resid_prefetch(rnext, p.resid + row0 * p.ldr + col0 + CSTR * 32, p.ldr, lane, rows_valid);
       }
-      if (!kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * 64, raw[0]);   // v[] holds this chunk already
+      if (!kTmemPrefetch && has_next) tmem_ld_32x32(taddr + (i + 1) * (CSTR * 32), raw[0]);   // v[] holds this chunk already
       if (EPI == EPI_BF16) {
         fstore_bf16(st, lane, v, reinterpret_cast<__nv_bfloat16*>(p.C) + row0 * p.ldc + col0, p.ldc, rows_valid);
       } else if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
@@ -400,11 +403,11 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
   }
 }
 
-template <int BN, int AMAJ, int BMAJ>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int AMAJ, int BMAJ, int EPW>
+__global__ void __launch_bounds__((2 + EPW) * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPW>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -434,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], EPW);
     }
     fence_barrier_init();
   }
@@ -529,17 +532,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================== epilogue warps (2..9) =====================
     if (p.fast_epi) {   // kernel-uniform: specialised loops (fast_store shapes, one N tile per unit)
       const uint32_t st32 = smem_u32(stage_all + (warp - 2) * 2048);
-      const uint32_t sb32 = smem_u32(arg_merge) + (warp - 2) * 128;   // per-warp bias broadcast buffer (argmax scratch is free here)
-      switch (p.epi) {
-        case EPI_BF16: epilogue_fast<BN, EPI_BF16>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        case EPI_F32: epilogue_fast<BN, EPI_F32>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        case EPI_RESID_F32: epilogue_fast<BN, EPI_RESID_F32>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        case EPI_GEGLU: epilogue_fast<BN, EPI_GEGLU>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        case EPI_L2NORM: epilogue_fast<BN, EPI_L2NORM>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        case EPI_BIAS_GELU: epilogue_fast<BN, EPI_BIAS_GELU>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
-        default: epilogue_fast<BN, EPI_NONE_DEBUG>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+      const uint32_t sb32 = st32;   // bias broadcast buffer = first 128 B of the staging buffer (disjoint in time)
+      if (EPW == EPW_LIGHT) {              // register-light epilogues only (128 registers / thread)
+        switch (p.epi) {
+          case EPI_BF16: epilogue_fast<BN, EPI_BF16, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_F32: epilogue_fast<BN, EPI_F32, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_GEGLU: epilogue_fast<BN, EPI_GEGLU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_L2NORM: epilogue_fast<BN, EPI_L2NORM, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_BIAS_GELU: epilogue_fast<BN, EPI_BIAS_GELU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          default: epilogue_fast<BN, EPI_NONE_DEBUG, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        }
+      } else {
+        switch (p.epi) {
+          case EPI_BF16: epilogue_fast<BN, EPI_BF16, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_F32: epilogue_fast<BN, EPI_F32, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_RESID_F32: epilogue_fast<BN, EPI_RESID_F32, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_GEGLU: epilogue_fast<BN, EPI_GEGLU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_L2NORM: epilogue_fast<BN, EPI_L2NORM, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_BIAS_GELU: epilogue_fast<BN, EPI_BIAS_GELU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          default: epilogue_fast<BN, EPI_NONE_DEBUG, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+        }
       }
-    } else {
+    } else if (EPW == EPI_WARPS) {   // v1 generic epilogue (odd shapes, ARGMAX, ATOMIC): 8 epilogue warps only
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which alternate 32-column chunks this warp handles
     uint32_t it = 0;
@@ -787,9 +801,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 }
 
-template <int BN, int AMAJ, int BMAJ>
-static int launch_gemm(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int AMAJ, int BMAJ, int EPW>
+static int launch_gemm_epw(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPW>;
   CUtensorMap ta, tb;
   int rc;
   if (AMAJ == 0)
@@ -812,16 +826,28 @@ static int launch_gemm(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t s
   p.n_groups = p.n_blks / p.n_per_unit;
   p.num_units = p.m_blks * p.n_groups * p.splits;
 
-  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, EPW>;
   static bool attr_set = false;
   if (!attr_set) {
     CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, (2 + EPW) * 32, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
+}
+
+// 12 epilogue warps (3 per TMEM lane quarter, 128 registers each) for the fused epilogues that are latency-bound with
+// two warps per scheduler (GEGLU: 390 instructions per 32-column chunk incl. 16 erf-GELUs); the residual / atomic /
+// argmax / odd-shape epilogues keep the 8-warp kernel with its larger register budget.
+template <int BN, int AMAJ, int BMAJ>
+static int launch_gemm(const ctclip_gemm_args* a, GemmKParams& p, cudaStream_t stream) {
+  static const int no16 = getenv("CTCLIP_GEMM_EPW8") ? atoi(getenv("CTCLIP_GEMM_EPW8")) : 0;   // debug knob
+  const bool light = p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_GEGLU || p.epi == EPI_L2NORM ||
+                     p.epi == EPI_BIAS_GELU || p.epi == EPI_NONE_DEBUG;
+  if (BN >= 128 && p.fast_epi && light && !no16) return launch_gemm_epw<(BN >= 128 ? BN : 128), AMAJ, BMAJ, EPW_LIGHT>(a, p, stream);
+  return launch_gemm_epw<BN, AMAJ, BMAJ, EPI_WARPS>(a, p, stream);
 }
 
 }  // namespace ctb

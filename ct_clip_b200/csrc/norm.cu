@@ -81,8 +81,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(ctclip_ln_bwd_args a) {
   const bool want_param = (a.dgamma != nullptr) || (a.dbeta != nullptr);
   for (long long row = (long long)blockIdx.x * warps_per_cta + warp; row < a.M;
        row += (long long)gridDim.x * warps_per_cta) {
-    float4 g[NCH], h[NCH];
+    float4 g[NCH], h[NCH], rin[NCH];
+    uint2 radd[NCH];
     float s1 = 0.f, s2 = 0.f;
+    // every load of the row is issued before the first reduction: the residual-gradient reads used to start only after
+    // the two warp reductions, i.e. a second exposed DRAM round trip per row (52-56 % of the copy bandwidth)
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      const int c = i * 128 + lane * 4;
+      if (a.dres_in != nullptr) rin[i] = *reinterpret_cast<const float4*>(a.dres_in + row * D + c);
+      if (a.add_bf16 != nullptr) radd[i] = *reinterpret_cast<const uint2*>(a.add_bf16 + row * D + c);
+    }
+    const float rstd = a.rstd[row];
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
       const int c = i * 128 + lane * 4;
@@ -110,18 +120,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(ctclip_ln_bwd_args a) {
     }
     const float c1 = warp_sum(s1) / D;
     const float c2 = warp_sum(s2) / D;
-    const float rstd = a.rstd[row];
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
       const int c = i * 128 + lane * 4;
       float4 dx = make_float4(rstd * (g[i].x - c1 - h[i].x * c2), rstd * (g[i].y - c1 - h[i].y * c2),
                               rstd * (g[i].z - c1 - h[i].z * c2), rstd * (g[i].w - c1 - h[i].w * c2));
       if (a.dres_in != nullptr) {
-        const float4 r = *reinterpret_cast<const float4*>(a.dres_in + row * D + c);
+        const float4 r = rin[i];
         dx.x += r.x; dx.y += r.y; dx.z += r.z; dx.w += r.w;
       }
       if (a.add_bf16 != nullptr) {
-        const uint2 u = *reinterpret_cast<const uint2*>(a.add_bf16 + row * D + c);
+        const uint2 u = radd[i];
         const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y);
         dx.x += p0.x; dx.y += p0.y; dx.z += p1.x; dx.w += p1.y;
       }

@@ -100,25 +100,40 @@ __device__ __forceinline__ void peg_loader_setup(int (&inpl)[PEG_MAXIT], int nit
     inpl[it] = v;
   }
 }
-// async load of plane `a0` (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one ring slot
-__device__ __forceinline__ void peg_load_plane4(float* slot, const float* __restrict__ src, const PegGeom& g, int a0,
-                                                const int (&inpl)[PEG_MAXIT], int nit) {
+// canonical tokens of plane a0 for this thread's loader items (temporal stack: one table lookup per item). Called ONE
+// plane ahead of the copy that uses them, so the dependent LDG -> cp.async address chain is off the critical path.
+__device__ __forceinline__ void peg_plane_tokens(int (&tok)[PEG_MAXIT], const PegGeom& g, int a0, const int (&inpl)[PEG_MAXIT],
+                                                 int nit) {
   const bool pl_ok = a0 >= 0 && a0 < g.T;
   const int fbase = a0 * g.H * g.W;
-  const int q4 = (threadIdx.x & 7) * 4;
 #pragma unroll
   for (int it = 0; it < PEG_MAXIT; it++) {
     if (it < nit) {
       const int v = inpl[it];
-      if (v != -2) {
-        const bool ok = pl_ok && v >= 0;
-        long long tok = 0;
-        if (ok) {
-          const int f = fbase + v;
-          tok = !g.temporal ? f : (g.table != nullptr ? __ldg(g.table + f) : (int)peg_canon_f(g, f));
-        }
-        peg_cp16(slot + (size_t)(threadIdx.x + it * PEG_THREADS) * 4, src + tok * g.D + q4, ok);
+      int tk = -1;
+      if (pl_ok && v >= 0) {
+        const int f = fbase + v;
+        tk = !g.temporal ? f : (g.table != nullptr ? __ldg(g.table + f) : (int)peg_canon_f(g, f));
       }
+      tok[it] = tk;
+    }
+  }
+}
+// async load of one plane (rows a1_0-1 .. a1_0+A1T, cols -1 .. W) of a [tokens, D] fp32 tensor into one ring slot;
+// tok[] from peg_plane_tokens (-1: zero fill), src already offset to the column's first channel.
+__device__ __forceinline__ void peg_load_plane5(float* slot, const float* __restrict__ src, int D, const int (&tok)[PEG_MAXIT],
+                                                const int (&inpl)[PEG_MAXIT], int nit) {
+  const uint32_t sbase = smem_u32(slot) + threadIdx.x * 16;
+  const float* s4 = src + (threadIdx.x & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < PEG_MAXIT; it++) {
+    if (it < nit && inpl[it] != -2) {
+      const int tk = tok[it];
+      const bool ok = tk >= 0;
+      const float* p = ok ? s4 + (long long)tk * D : s4;
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + it * (PEG_THREADS * 16)), "l"(p), "r"(bytes)
+                   : "memory");
     }
   }
 }
@@ -177,21 +192,28 @@ __device__ __forceinline__ void peg_out2(f2_t (&win)[9][4], const char* smb, con
     win[r][C] = PEG_LD2(smb, po, r, R0 + 2);
     win[r][D] = PEG_LD2(smb, po, r, R0 + 3);
   }
-  f2_t a0 = init, a1 = 0ull, b0 = init, b1 = 0ull;
+  // six accumulation chains of 8-10 FFMA2; the three that only touch the two columns already in registers come first,
+  // so the 18 loads above have ~27 issue slots to land before their first use
+  f2_t xa = init, xb = 0ull, yb = init;
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    f2_t& x = (r & 1) ? a1 : a0;
-    f2_t& y = (r & 1) ? b1 : b0;
+    f2_t& x = (r & 1) ? xb : xa;
     x = f2_fma(wt[r * 3 + 0], win[r][A], x);
-    y = f2_fma(wt[r * 3 + 0], win[r][B], y);
+    yb = f2_fma(wt[r * 3 + 0], win[r][B], yb);
     x = f2_fma(wt[r * 3 + 1], win[r][B], x);
+  }
+  f2_t xc = 0ull, yc = 0ull, yd = 0ull;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    f2_t& y = (r & 1) ? yd : yc;
+    xc = f2_fma(wt[r * 3 + 2], win[r][C], xc);
     y = f2_fma(wt[r * 3 + 1], win[r][C], y);
-    x = f2_fma(wt[r * 3 + 2], win[r][C], x);
     y = f2_fma(wt[r * 3 + 2], win[r][D], y);
   }
-  const float2 fa0 = f2_unpack(a0), fa1 = f2_unpack(a1), fb0 = f2_unpack(b0), fb1 = f2_unpack(b1);
-  o0 = f2_pack(fa0.x + fa1.x, fa0.y + fa1.y);
-  o1 = f2_pack(fb0.x + fb1.x, fb0.y + fb1.y);
+  const float2 f0 = f2_unpack(xa), f1 = f2_unpack(xb), f2 = f2_unpack(xc);
+  const float2 h0 = f2_unpack(yb), h1 = f2_unpack(yc), h2 = f2_unpack(yd);
+  o0 = f2_pack((f0.x + f1.x) + f2.x, (f0.y + f1.y) + f2.y);
+  o1 = f2_pack((h0.x + h1.x) + h2.x, (h0.y + h1.y) + h2.y);
 }
 template <int R0>
 __device__ __forceinline__ void peg_wout2(f2_t (&win)[9][4], const char* smb, const uint32_t (&po)[9], f2_t (&acc)[27],
@@ -203,11 +225,14 @@ __device__ __forceinline__ void peg_wout2(f2_t (&win)[9][4], const char* smb, co
     win[r][D] = PEG_LD2(smb, po, r, R0 + 3);
   }
 #pragma unroll
-  for (int r = 0; r < 9; r++) {
+  for (int r = 0; r < 9; r++) {   // taps on the two columns already in registers first
     acc[r * 3 + 0] = f2_fma(d0, win[r][A], acc[r * 3 + 0]);
     acc[r * 3 + 1] = f2_fma(d0, win[r][B], acc[r * 3 + 1]);
-    acc[r * 3 + 2] = f2_fma(d0, win[r][C], acc[r * 3 + 2]);
+  }
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
     acc[r * 3 + 0] = f2_fma(d1, win[r][B], acc[r * 3 + 0]);
+    acc[r * 3 + 2] = f2_fma(d0, win[r][C], acc[r * 3 + 2]);
     acc[r * 3 + 1] = f2_fma(d1, win[r][C], acc[r * 3 + 1]);
     acc[r * 3 + 2] = f2_fma(d1, win[r][D], acc[r * 3 + 2]);
   }
@@ -258,11 +283,14 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
     // so that only ONE new plane enters per step.
     const int first = (MODE == 0) ? p_begin : p_end - 1;
     const int dirn = (MODE == 0) ? 1 : -1;
+    int ptok[PEG_MAXIT];
     for (int d = 2; d >= 0; d--) {
       const int pl = first - dirn * d;
-      peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
+      peg_plane_tokens(ptok, g, pl, inpl, nit);
+      peg_load_plane5(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, a.D, ptok, inpl, nit);
     }
     peg_commit();
+    peg_plane_tokens(ptok, g, first + dirn, inpl, nit);   // tokens of the first prefetched plane
     const int n_steps = p_end - p_begin;
     for (int step = 0; step < n_steps; step++, par ^= 1) {
       const int a0 = first + dirn * step;
@@ -274,8 +302,9 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_conv4_kernel(ctclip_peg_ar
       __syncthreads();   // plane a0 landed for everyone; everyone finished computing the previous plane
       if (step + 1 < n_steps) {   // prefetch the next plane into the slot released by plane a0 - 3*dirn
         const int pl = a0 + dirn;
-        peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
+        peg_load_plane5(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, a.D, ptok, inpl, nit);
         peg_commit();
+        if (step + 2 < n_steps) peg_plane_tokens(ptok, g, pl + dirn, inpl, nit);   // used one step from now
       }
       if (a1 < a.H && b0 < b1) {
         uint32_t po[9];
@@ -357,12 +386,15 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
     float accb0 = 0.f, accb1 = 0.f;
     __syncthreads();   // previous column: reduction scratch / ring fully consumed
     peg_loader_setup(inpl, nit, n_items, a2h, cc.a1_0, a.H, a.W);
+    int ptok[PEG_MAXIT];
     for (int d = 2; d >= 0; d--) {
       const int pl = p_begin - d;
-      peg_load_plane4(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, g, pl, inpl, nit);
+      peg_plane_tokens(ptok, g, pl, inpl, nit);
+      peg_load_plane5(peg_sm + (size_t)peg_slot(pl) * slot_elems, xin, a.D, ptok, inpl, nit);
     }
     peg_load_dy4(sdy, dy, g, p_begin, cc.a1_0);
     peg_commit();
+    peg_plane_tokens(ptok, g, p_begin + 1, inpl, nit);
     for (int a0 = p_begin; a0 < p_end; a0++) {
       const int par = dy_double ? ((a0 - p_begin) & 1) : 0;
       if (!dy_double && a0 > p_begin) {   // wide grids: a single gradient tile fits; fetch it without overlap
@@ -373,9 +405,10 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
       peg_wait_all();
       __syncthreads();
       if (a0 + 1 < p_end) {
-        peg_load_plane4(peg_sm + (size_t)peg_slot(a0 + 1) * slot_elems, xin, g, a0 + 1, inpl, nit);
+        peg_load_plane5(peg_sm + (size_t)peg_slot(a0 + 1) * slot_elems, xin, a.D, ptok, inpl, nit);
         if (dy_double) peg_load_dy4(sdy + (size_t)(par ^ 1) * dy_elems, dy, g, a0 + 1, cc.a1_0);
         peg_commit();
+        if (a0 + 2 < p_end) peg_plane_tokens(ptok, g, a0 + 2, inpl, nit);
       }
       if (a1 < a.H && b0 < b1) {
         uint32_t po[9];

@@ -204,20 +204,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // rcp.approx / ex2.approx -- ~14 instructions instead of ~30 for erff(). Used inside GEMM epilogues, where the exact
 // version made the epilogue (not the MMA) the bottleneck of the K=512 GEGLU GEMM.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
+  // gelu(x) = x/2 + |x|/2 * erf(|x|/sqrt 2) = (x/2 + |x|/2) - |x|/2 * poly(t) * exp(-x^2/2),  t = 1/(1 + p |x|/sqrt 2)
+  const float ax = fabsf(x);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-az * az * 1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf = copysignf(erf_abs, z);
-  return 0.5f * x * (1.0f + erf);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));
+  const float h = 0.5f * ax;
+  return fmaf(-h, poly * e, fmaf(0.5f, x, h));
 }
 // d/dx gelu(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
