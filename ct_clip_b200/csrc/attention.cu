@@ -334,19 +334,14 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
       const uint2* bfr = bias_frag ? bias_frag + ((((long long)head * row_tiles + rt) * kblocks + (key0 >> 6)) * 32 + lane) * 8
                                    : nullptr;
       const bool full = !MASK && (key0 + 64 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
-      const bool nfull = use_frag && (key0 + 128 <= a.n);   // the next key block is complete too: fetch its bias now
-      uint4 bnxt[4];
-      if (nfull) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) bnxt[i] = __ldg(reinterpret_cast<const uint4*>(bfr + 256) + i);
-      }
+      const bool nfull = use_frag && (key0 + 128 <= a.n);   // the next key block is complete too
       if (full) {
         qk_block<8, DH, true>(s, qa, sK, key0, lane);
         if (use_frag) logits_tile_full_regs<8>(s, sc2, bcur);
         else logits_tile_full<8>(s, sc2, nullptr);
-        if (nfull) {
+        if (nfull) {   // refill the (now dead) fragment registers for the next block: the exps and PV MMAs below hide the L2 latency
 #pragma unroll
-          for (int i = 0; i < 4; i++) bcur[i] = bnxt[i];
+          for (int i = 0; i < 4; i++) bcur[i] = __ldg(reinterpret_cast<const uint4*>(bfr + 256) + i);
         }
       } else {
         qk_block<8, DH>(s, qa, sK, key0, lane, ntv);
@@ -479,18 +474,16 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
                                    : nullptr;
       const bool full = !MASK && (key0 + 32 <= a.n) && (bias == nullptr || bias_frag != nullptr);   // warp-uniform
       const bool nfull = use_frag && (key0 + 64 <= a.n);
-      uint4 bnxt[2];
-      if (nfull) {   // fragments of the next 32-key block: second half of this 64-key table block, or the next table block
-        const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((key0 >> 5) & 1) ? 256 - 4 : 4));
-        bnxt[0] = __ldg(pn);
-        bnxt[1] = __ldg(pn + 1);
-      }
       if (full) {
         qk_block<4, DH, true>(s, qa, sK, key0, lane);
         qk_block<4, DH, true>(dp, da, sV, key0, lane);
         if (use_frag) logits_tile_full_regs<4>(s, sc2, bcur);
         else logits_tile_full<4>(s, sc2, nullptr);
-        if (nfull) { bcur[0] = bnxt[0]; bcur[1] = bnxt[1]; }
+        if (nfull) {   // fragments of the next 32-key block: second half of this 64-key table block, or the next table block
+          const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((key0 >> 5) & 1) ? 256 - 4 : 4));
+          bcur[0] = __ldg(pn);
+          bcur[1] = __ldg(pn + 1);
+        }
       } else {
         qk_block<4, DH>(s, qa, sK, key0, lane, ntv);
         qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
@@ -610,16 +603,14 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
       const uint2* bfr = bias_t_frag ? bias_t_frag + ((((long long)head * key_tiles + kt_) * qblocks + (q0 >> 6)) * 32 + lane) * 8 +
                                            ((q0 >> 5) & 1) * 4
                                      : nullptr;
-      uint4 bnxt[2];
-      if (nfull) {
-        const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((q0 >> 5) & 1) ? 256 - 4 : 4));
-        bnxt[0] = __ldg(pn);
-        bnxt[1] = __ldg(pn + 1);
-      }
       if (full) {
         if (use_frag) logits_tile_full_regs<4>(s, sc2, bcur);
         else logits_tile_full<4>(s, sc2, nullptr);
-        if (nfull) { bcur[0] = bnxt[0]; bcur[1] = bnxt[1]; }
+        if (nfull) {
+          const uint4* pn = reinterpret_cast<const uint4*>(bfr + (((q0 >> 5) & 1) ? 256 - 4 : 4));
+          bcur[0] = __ldg(pn);
+          bcur[1] = __ldg(pn + 1);
+        }
       } else {
         logits_tile<4, false>(s, sc2, brow_a, brow_b, q0, t, a.n, q0 + 32 <= a.n, pair_ok, nullptr, ntv, bfr);
       }

@@ -192,28 +192,28 @@ __device__ __forceinline__ void peg_out2(f2_t (&win)[9][4], const char* smb, con
     win[r][C] = PEG_LD2(smb, po, r, R0 + 2);
     win[r][D] = PEG_LD2(smb, po, r, R0 + 3);
   }
-  // six accumulation chains of 8-10 FFMA2; the three that only touch the two columns already in registers come first,
-  // so the 18 loads above have ~27 issue slots to land before their first use
-  f2_t xa = init, xb = 0ull, yb = init;
+  // Six independent FFMA2 chains are kept in flight in both passes (ptxas keeps the source order: with two chains the
+  // kernel sat in fixed-latency "wait" stalls). Pass 1 only touches the two columns already in registers, so the 18
+  // loads above have ~27 issue slots to land; pass 2 continues on the same accumulators.
+  f2_t x0[2] = {init, 0ull}, x1[2] = {0ull, 0ull}, y0[2] = {init, 0ull}, y2[2] = {0ull, 0ull};
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    f2_t& x = (r & 1) ? xb : xa;
-    x = f2_fma(wt[r * 3 + 0], win[r][A], x);
-    yb = f2_fma(wt[r * 3 + 0], win[r][B], yb);
-    x = f2_fma(wt[r * 3 + 1], win[r][B], x);
+    const int p = r & 1;
+    x0[p] = f2_fma(wt[r * 3 + 0], win[r][A], x0[p]);
+    y0[p] = f2_fma(wt[r * 3 + 0], win[r][B], y0[p]);
+    x1[p] = f2_fma(wt[r * 3 + 1], win[r][B], x1[p]);
   }
-  f2_t xc = 0ull, yc = 0ull, yd = 0ull;
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    f2_t& y = (r & 1) ? yd : yc;
-    xc = f2_fma(wt[r * 3 + 2], win[r][C], xc);
-    y = f2_fma(wt[r * 3 + 1], win[r][C], y);
-    y = f2_fma(wt[r * 3 + 2], win[r][D], y);
+    const int p = r & 1;
+    x0[p] = f2_fma(wt[r * 3 + 2], win[r][C], x0[p]);
+    y0[p] = f2_fma(wt[r * 3 + 1], win[r][C], y0[p]);
+    y2[p] = f2_fma(wt[r * 3 + 2], win[r][D], y2[p]);
   }
-  const float2 f0 = f2_unpack(xa), f1 = f2_unpack(xb), f2 = f2_unpack(xc);
-  const float2 h0 = f2_unpack(yb), h1 = f2_unpack(yc), h2 = f2_unpack(yd);
-  o0 = f2_pack((f0.x + f1.x) + f2.x, (f0.y + f1.y) + f2.y);
-  o1 = f2_pack((h0.x + h1.x) + h2.x, (h0.y + h1.y) + h2.y);
+  const float2 a0 = f2_unpack(x0[0]), a1 = f2_unpack(x0[1]), a2 = f2_unpack(x1[0]), a3 = f2_unpack(x1[1]);
+  const float2 b0 = f2_unpack(y0[0]), b1 = f2_unpack(y0[1]), b2 = f2_unpack(y2[0]), b3 = f2_unpack(y2[1]);
+  o0 = f2_pack((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+  o1 = f2_pack((b0.x + b1.x) + (b2.x + b3.x), (b0.y + b1.y) + (b2.y + b3.y));
 }
 template <int R0>
 __device__ __forceinline__ void peg_wout2(f2_t (&win)[9][4], const char* smb, const uint32_t (&po)[9], f2_t (&acc)[27],
