@@ -107,7 +107,10 @@ def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
 
 
 def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
-              dbias=None, lines=4, canon_table=None):
+              dbias=None, lines=4, canon_table=None, exact=False):
+    """exact=True selects the fp32 stencil kernels (ctclip_peg_args.lines = -1); default = bf16 tensor-core kernels."""
+    if exact:
+        lines = -1
     a = PegArgs()
     a.x, a.dy, a.y, a.y_bf16 = x.data_ptr(), _ptr(dy), _ptr(y), _ptr(y_bf16)
     a.weight, a.bias, a.dweight, a.dbias = _ptr(weight), _ptr(bias), _ptr(dweight), _ptr(dbias)
@@ -117,7 +120,7 @@ def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_b
 
 
 def _peg_tag(kw):
-    return "temporal" if kw.get("temporal") else "spatial"
+    return ("temporal" if kw.get("temporal") else "spatial") + (" fp32" if kw.get("exact") else "")
 
 
 def peg_fwd(x, y, weight, bias, **kw):

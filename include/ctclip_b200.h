@@ -148,6 +148,8 @@ int ctclip_patchify(const ctclip_patchify_args* args, void* stream);
  * PEG: causal depthwise 3x3x3 conv + residual on the canonical fp32 token stream [B,T,H,W,D].
  * attention.py:63-84 + the residual at :324. temporal = 1 reproduces the reference's reshape of
  * the (b,h,w,t)-ordered tokens as (b,T,H,W) (SURVEY trap T1).
+ * Default arithmetic: m16n8k16 bf16 MMAs with block-diagonal weights (csrc/peg_mma.cu); lines = -1 selects the exact
+ * fp32 (packed FFMA2) stencil kernels (csrc/peg.cu), also used when the tile does not fit shared memory (W > 24..42).
  *   ctclip_peg_fwd        : y = x + conv(x) + bias          (y_bf16 optional bf16 copy)
  *   ctclip_peg_bwd_data   : y = x + conv^T(x)  with x = upstream gradient
  *   ctclip_peg_bwd_weight : dweight[D,27] += ..., dbias[D] += ...  (x = forward input, dy = upstream)
@@ -163,7 +165,8 @@ typedef struct {
   float* dbias;
   int32_t B, T, H, W, D;
   int32_t temporal;
-  int32_t lines;       /* unused (kept for ABI stability) */
+  int32_t lines;       /* -1: exact fp32 stencil kernels; any other value: bf16 tensor-core kernels (conv operands rounded
+                          to bf16 like the reference's autocast, fp32 accumulation / bias / residual) where supported */
   const int32_t* canon_table; /* optional, temporal only: canon_table[f] = canonical token of conv-grid index
                                  f = (a0*H + a1)*W + a2, i.e. ((f % T)*H + f / (T*W))*W + (f / T) % W */
 } ctclip_peg_args;
