@@ -61,7 +61,7 @@ class AttnArgs(C.Structure):
                 ("seq_outer_stride", I64), ("tok_stride", I64), ("scale", F32),
                 ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
                 ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P),
-                ("bias_frag", P), ("bias_t_frag", P)]
+                ("bias_frag", P), ("bias_t_frag", P), ("ds_scratch", P)]
 
 
 class SgemmArgs(C.Structure):

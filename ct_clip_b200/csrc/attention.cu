@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
   const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(a.d_o);
   const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   __nv_bfloat16* dq = reinterpret_cast<__nv_bfloat16*>(a.dq);
+  __nv_bfloat16* ds_out = (a.dbias != nullptr) ? reinterpret_cast<__nv_bfloat16*>(a.ds_scratch) : nullptr;
   if (active) {
     const int tid = wig * 32 + lane;
     load_rows<DH>(sK, k, a.ldk, head, g, seq, n_pad, tid, WPG * 32);
@@ -495,6 +496,18 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
         for (int e = 0; e < 4; e++) {
           const float p = fast_exp2(s[nt][e] - ((e < 2) ? lse_a : lse_b));           // -inf logits -> 0
           s[nt][e] = p * (dp[nt][e] - ((e < 2) ? del_a : del_b));                    // d logits (the softmax scale is applied to dq below)
+        }
+      }
+      if (ds_out != nullptr) {   // d logits == d bias: spill them (bf16) for the sequence reduction that replaces the third pass
+        __nv_bfloat16* da_ = ds_out + ((long long)item * a.n + ra) * a.n + key0 + 2 * t;
+        __nv_bfloat16* db_ = ds_out + ((long long)item * a.n + rb) * a.n + key0 + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const int c = key0 + nt * 8 + 2 * t;
+          if (c + 1 < a.n) {   // n is even on this path (checked by the launcher): pairs never straddle the row end
+            if (ra < a.n) *reinterpret_cast<uint32_t*>(da_ + nt * 8) = pack_bf16x2(s[nt][0], s[nt][1]);
+            if (rb < a.n) *reinterpret_cast<uint32_t*>(db_ + nt * 8) = pack_bf16x2(s[nt][2], s[nt][3]);
+          }
         }
       }
       if (full) pv_block<4, DH, true>(dqa, s, sK, key0, lane);
@@ -1065,6 +1078,29 @@ __global__ void __launch_bounds__(SH_BWD_WARPS * 32, 1) attn_short_bwd_kernel(ct
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// dbias[h, i, j] += sum over sequences of the d logits the dQ kernel spilled (bf16 [num_seqs*heads][n*n]); 4 elements/thread
+__global__ void __launch_bounds__(256) attn_dbias_reduce_kernel(const __nv_bfloat16* __restrict__ ds, float* __restrict__ dbias,
+                                                                int num_seqs, int heads, long long nn) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long quads = nn / 4;
+  if (q >= (long long)heads * quads) return;
+  const int h = (int)(q / quads);
+  const long long e = (q - (long long)h * quads) * 4;
+  const __nv_bfloat16* p = ds + (long long)h * nn + e;
+  const long long stride = (long long)heads * nn;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+  for (int sq = 0; sq < num_seqs; sq++) {
+    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(p + (long long)sq * stride));
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y);
+    acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+  }
+  float4* d = reinterpret_cast<float4*>(dbias + (long long)h * nn + e);
+  float4 o = *d;
+  o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+  *d = o;
+}
+
 // delta[row, head] = sum_d dO[row, head, d] * O[row, head, d]
 template <int DH>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
@@ -1258,7 +1294,14 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
   }
   if (int rc = attn_route(1, a, stream)) return rc;
   if (int rc = attn_route(2, a, stream)) return rc;
-  if (a->dbias != nullptr) {
+  if (a->dbias != nullptr && a->ds_scratch != nullptr && a->n % 2 == 0) {
+    // the dQ kernel spilled its d logits: reduce them over the sequences (replaces the recomputing third pass)
+    const long long nn = (long long)a->n * a->n;
+    const long long threads = (long long)a->heads * (nn / 4);
+    attn_dbias_reduce_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->ds_scratch), a->dbias, a->num_seqs, a->heads, nn);
+    CTB_LAUNCH_CHECK();
+  } else if (a->dbias != nullptr) {
     // sequence chunks: enough CTAs for ~2 waves at 3 CTAs/SM
     const int tiles = ((a->n + 63) / 64) * ((a->n + 63) / 64) * a->heads;
     int chunks = (6 * num_sms() + tiles - 1) / tiles;

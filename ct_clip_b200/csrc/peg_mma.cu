@@ -35,7 +35,9 @@ constexpr int PM_THREADS = 512;  // 16 warps: warp = (channel group = warp & 3, 
 constexpr int PM_WARPS = PM_THREADS / 32;
 constexpr int PM_TOKB = 80;      // bytes per token in the bf16 ring (32 ch x 2 B + 16 B pad)
 constexpr int PM_NSLOT = 3;      // bf16 ring: planes a0-2, a0-1, a0
-constexpr int PM_NSTG = 3;       // fp32 staging buffers (all three are used to prime a column in one round trip)
+constexpr int PM_NSTG = 3;       // fp32 staging buffers of the conv kernels: three planes in flight (the step is far shorter
+                                 // than the DRAM latency: with one plane in flight Little's law capped the kernel at ~2 TB/s)
+constexpr int PM_NSTG_W = 2;     // weight-gradient kernel: two x planes + two dy tiles in flight
 constexpr int PM_MAXIT = 7;      // loader items per thread and plane: (A1T+2)(W+2)*8/512 <= 7  <=>  W <= 42
 constexpr int PM_PADTOK = 18;    // tokens past the last halo row that shifted ldmatrix rows may touch
 
@@ -75,6 +77,8 @@ __device__ __forceinline__ void pm_cp16(uint32_t dst, const void* src, bool vali
 }
 __device__ __forceinline__ void pm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void pm_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pm_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct PmCol {
   int b, a1_0, c0;
@@ -149,12 +153,12 @@ struct PmSmem {
   int* s_tok;        // [2][n_mt * 16]
   uint32_t slot_bytes;
 };
-__device__ __forceinline__ PmSmem pm_carve(uint8_t* base, const PmGeom& g) {
+__device__ __forceinline__ PmSmem pm_carve(uint8_t* base, const PmGeom& g, int nstg) {
   PmSmem s;
   s.slot_bytes = (uint32_t)(g.n_tok + PM_PADTOK) * PM_TOKB;
   s.ring = base;
   s.stg = reinterpret_cast<float*>(base + (size_t)PM_NSLOT * s.slot_bytes);
-  s.s_tok = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s.stg) + (size_t)PM_NSTG * g.n_tok * 128);
+  s.s_tok = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s.stg) + (size_t)nstg * g.n_tok * 128);
   return s;
 }
 __device__ __forceinline__ int pm_slot(int pl) { return ((pl % PM_NSLOT) + PM_NSLOT) % PM_NSLOT; }
@@ -164,7 +168,7 @@ template <int MODE>
 __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_args a, int steps_per_cta) {
   extern __shared__ __align__(128) uint8_t pm_sm[];
   PmGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table, a.W + 2, (PM_A1T + 2) * (a.W + 2), (PM_A1T * (a.W + 2) + 15) / 16};
-  const PmSmem sm = pm_carve(pm_sm, g);
+  const PmSmem sm = pm_carve(pm_sm, g, PM_NSTG);
   const int n_a1t = (a.H + PM_A1T - 1) / PM_A1T, n_cb = a.D / PM_CB;
   const int total = n_cb * n_a1t * a.B * a.T;
   const int s_begin = blockIdx.x * steps_per_cta;
@@ -235,12 +239,19 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
       pm_convert_plane(sm.stg + (size_t)d * g.n_tok * 32, sm.ring + (size_t)pm_slot(first - dirn * d) * sm.slot_bytes, inpl);
     __syncthreads();
     const int n_steps = p_end - p_begin;
+    // three planes ahead: plane first + d*dirn -> staging buffer (d-1) % 3, one cp.async group per plane (empty groups
+    // keep the group arithmetic uniform near the end of the column)
+#pragma unroll
+    for (int d = 1; d <= 3; d++) {
+      if (d < n_steps) pm_issue_plane(stg_u32 + ((d - 1) % PM_NSTG) * g.n_tok * 128, xin, g, first + dirn * d, inpl);
+      pm_commit();
+    }
     for (int step = 0; step < n_steps; step++, par ^= 1) {
       const int a0 = first + dirn * step;
       const bool more = step + 1 < n_steps;
-      const uint32_t stg_n = stg_u32 + (step % PM_NSTG) * g.n_tok * 128;
-      if (more) {   // fp32 plane of the next step -> staging (lands while this plane is computed)
-        pm_issue_plane(stg_n, xin, g, a0 + dirn, inpl);
+      if (step >= 1) {   // the buffer converted at the end of the previous step is free again: refill it, 3 planes ahead
+        if (step + 3 < n_steps)
+          pm_issue_plane(stg_u32 + ((step - 1) % PM_NSTG) * g.n_tok * 128, xin, g, a0 + 3 * dirn, inpl);
         pm_commit();
       }
       // ---- compute plane a0
@@ -280,8 +291,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
         }
       }
       if (more) {
-        pm_wait_all();
-        __syncthreads();   // everyone finished reading plane a0 - 2*dirn (its slot is refilled now); staging landed
+        pm_wait_pending<2>();   // the plane of the next step has landed (the two younger groups may still be in flight)
+        __syncthreads();        // everyone finished reading plane a0 - 2*dirn (its slot is refilled now)
         pm_convert_plane(sm.stg + (size_t)(step % PM_NSTG) * g.n_tok * 32,
                          sm.ring + (size_t)pm_slot(a0 + dirn) * sm.slot_bytes, inpl);
         pm_write_tokens(sm.s_tok + (par ^ 1) * g.n_mt * 16, g, a0 + dirn, cc.a1_0);
@@ -296,11 +307,13 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
 __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_wgrad_kernel(ctclip_peg_args a, int steps_per_cta) {
   extern __shared__ __align__(128) uint8_t pm_sm[];
   PmGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table, a.W + 2, (PM_A1T + 2) * (a.W + 2), (PM_A1T * (a.W + 2) + 15) / 16};
-  const PmSmem sm = pm_carve(pm_sm, g);
-  // after the conv kernel's regions: dy tile bf16 [n_mt*16 tokens][80 B], dy staging fp32 [A1T*W][32], 128 B of bf16 ones
+  const PmSmem sm = pm_carve(pm_sm, g, PM_NSTG_W);
+  // after the conv kernel's regions: dy tile bf16 [n_mt*16 tokens][80 B], two dy staging tiles fp32 [A1T*W][32] (contiguous:
+  // together they also receive the third plane when a column is primed), 128 B of bf16 ones
   uint8_t* sdy = reinterpret_cast<uint8_t*>(sm.s_tok + 2 * g.n_mt * 16);
   float* dy_stg = reinterpret_cast<float*>(sdy + (size_t)g.n_mt * 16 * PM_TOKB);
-  uint8_t* ones = reinterpret_cast<uint8_t*>(dy_stg + (size_t)PM_A1T * g.W * 32);
+  const int dy_elems = PM_A1T * g.W * 32;
+  uint8_t* ones = reinterpret_cast<uint8_t*>(dy_stg + (size_t)2 * dy_elems);
   const int n_a1t = (a.H + PM_A1T - 1) / PM_A1T, n_cb = a.D / PM_CB;
   const int total = n_cb * n_a1t * a.B * a.T;
   const int s_begin = blockIdx.x * steps_per_cta;
@@ -342,45 +355,65 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_wgrad_kernel(ctclip_peg
     for (int i = 0; i < 15; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     __syncthreads();
     pm_loader_setup(inpl, g, cc.a1_0);
-    // upstream-gradient tile loader: A1T lines x W tokens x 8 quads, fp32 -> staging
-    auto issue_dy = [&](int a0) {
+    // upstream-gradient tile loader: A1T lines x W tokens x 8 quads, fp32 -> staging tile `buf`
+    auto issue_dy = [&](int a0, int buf) {
       const int n_valid = min(PM_A1T, g.H - cc.a1_0) * g.W;
       for (int idx = threadIdx.x; idx < PM_A1T * g.W * 8; idx += PM_THREADS) {
         const int tok = idx >> 3;
         const bool ok = tok < n_valid;
         const float* p = dyin + (idx & 7) * 4;
         if (ok) p += (long long)pm_canon(g, (a0 * g.H + cc.a1_0) * g.W + tok) * g.D;
-        pm_cp16(dystg_u32 + idx * 16, p, ok);
+        pm_cp16(dystg_u32 + buf * dy_elems * 4 + idx * 16, p, ok);
       }
     };
-    auto convert_dy = [&]() {
+    auto convert_dy = [&](int buf) {
+      const float* src = dy_stg + (size_t)buf * dy_elems;
       for (int idx = threadIdx.x; idx < PM_A1T * g.W * 8; idx += PM_THREADS) {
         const int tok = idx >> 3;
         const int l = tok / g.W, c = tok - l * g.W;
-        const float4 v = *reinterpret_cast<const float4*>(dy_stg + (size_t)idx * 4);
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)idx * 4);
         uint2 u;
         u.x = pack_bf16x2(v.x, v.y);
         u.y = pack_bf16x2(v.z, v.w);
         *reinterpret_cast<uint2*>(sdy + (size_t)(l * g.a2h + c) * PM_TOKB + (idx & 7) * 8) = u;
       }
     };
-#pragma unroll
-    for (int d = 0; d < 3; d++) pm_issue_plane(stg_u32 + d * g.n_tok * 128, xin, g, p_begin - d, inpl);
-    issue_dy(p_begin);
+    const int n_steps = p_end - p_begin;
+    // prime the ring in one round trip: planes p_begin-2, p_begin-1 -> the two x staging buffers, plane p_begin -> the
+    // (contiguous, still unused) dy staging tiles
+    pm_issue_plane(stg_u32, xin, g, p_begin - 2, inpl);
+    pm_issue_plane(stg_u32 + g.n_tok * 128, xin, g, p_begin - 1, inpl);
+    pm_issue_plane(dystg_u32, xin, g, p_begin, inpl);
     pm_commit();
     pm_wait_all();
     __syncthreads();
-#pragma unroll
-    for (int d = 0; d < 3; d++)
-      pm_convert_plane(sm.stg + (size_t)d * g.n_tok * 32, sm.ring + (size_t)pm_slot(p_begin - d) * sm.slot_bytes, inpl);
-    convert_dy();
+    pm_convert_plane(sm.stg, sm.ring + (size_t)pm_slot(p_begin - 2) * sm.slot_bytes, inpl);
+    pm_convert_plane(sm.stg + (size_t)g.n_tok * 32, sm.ring + (size_t)pm_slot(p_begin - 1) * sm.slot_bytes, inpl);
+    pm_convert_plane(dy_stg, sm.ring + (size_t)pm_slot(p_begin) * sm.slot_bytes, inpl);
     __syncthreads();
-    for (int a0 = p_begin; a0 < p_end; a0++) {
-      const bool more = a0 + 1 < p_end;
-      const int sb = (a0 - p_begin) % PM_NSTG;
-      if (more) {
-        pm_issue_plane(stg_u32 + sb * g.n_tok * 128, xin, g, a0 + 1, inpl);
-        issue_dy(a0 + 1);
+    issue_dy(p_begin, 0);
+    pm_commit();
+    pm_wait_all();
+    __syncthreads();
+    convert_dy(0);
+    __syncthreads();
+    // two planes ahead: plane q = p_begin + i uses x staging buffer i % 2 and dy staging tile i % 2, one group per plane
+#pragma unroll
+    for (int d = 1; d <= 2; d++) {
+      if (d < n_steps) {
+        pm_issue_plane(stg_u32 + (d % PM_NSTG_W) * g.n_tok * 128, xin, g, p_begin + d, inpl);
+        issue_dy(p_begin + d, d % 2);
+      }
+      pm_commit();
+    }
+    for (int i = 0; i < n_steps; i++) {
+      const int a0 = p_begin + i;
+      const bool more = i + 1 < n_steps;
+      if (i >= 1) {   // buffers i % 2 were converted at the end of the previous step: refill them with plane a0 + 2
+        if (i + 2 < n_steps) {
+          pm_issue_plane(stg_u32 + (i % PM_NSTG_W) * g.n_tok * 128, xin, g, a0 + 2, inpl);
+          issue_dy(a0 + 2, i % 2);
+        }
         pm_commit();
       }
       uint32_t pb[3];
@@ -403,10 +436,11 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_wgrad_kernel(ctclip_peg
         }
       }
       if (more) {
-        pm_wait_all();
+        pm_wait_pending<1>();   // plane a0 + 1 (x and dy) landed; plane a0 + 2 may still be in flight
         __syncthreads();
-        pm_convert_plane(sm.stg + (size_t)sb * g.n_tok * 32, sm.ring + (size_t)pm_slot(a0 + 1) * sm.slot_bytes, inpl);
-        convert_dy();
+        pm_convert_plane(sm.stg + (size_t)((i + 1) % PM_NSTG_W) * g.n_tok * 32,
+                         sm.ring + (size_t)pm_slot(a0 + 1) * sm.slot_bytes, inpl);
+        convert_dy((i + 1) % 2);
         __syncthreads();
       }
     }
@@ -435,8 +469,9 @@ static size_t pm_smem_bytes(const ctclip_peg_args* a, bool wgrad) {
   const int a2h = a->W + 2;
   const size_t n_tok = (size_t)(PM_A1T + 2) * a2h;
   const size_t n_mt = (PM_A1T * (size_t)a2h + 15) / 16;
-  size_t b = (size_t)PM_NSLOT * (n_tok + PM_PADTOK) * PM_TOKB + (size_t)PM_NSTG * n_tok * 128 + 2 * n_mt * 16 * sizeof(int);
-  if (wgrad) b += n_mt * 16 * PM_TOKB + (size_t)PM_A1T * a->W * 128 + 128;
+  size_t b = (size_t)PM_NSLOT * (n_tok + PM_PADTOK) * PM_TOKB + (size_t)(wgrad ? PM_NSTG_W : PM_NSTG) * n_tok * 128 +
+             2 * n_mt * 16 * sizeof(int);
+  if (wgrad) b += n_mt * 16 * PM_TOKB + (size_t)2 * PM_A1T * a->W * 128 + 128;
   return b + 128;
 }
 
@@ -444,6 +479,7 @@ static size_t pm_smem_bytes(const ctclip_peg_args* a, bool wgrad) {
 bool peg_mma_supported(const ctclip_peg_args* a, bool wgrad) {
   static const int off = getenv("CTCLIP_PEG_FP32") ? atoi(getenv("CTCLIP_PEG_FP32")) : 0;   // debug knob: force the fp32 stencil
   if (off || a->lines == -1) return false;
+  if (wgrad && 2 * PM_A1T * a->W < (PM_A1T + 2) * (a->W + 2)) return false;   // the dy staging tiles must hold one x plane (W >= 4)
   return a->D % PM_CB == 0 && a->W <= 42 && pm_smem_bytes(a, wgrad) <= 227 * 1024 &&
          (long long)a->B * a->T * a->H * a->W < (1ll << 31) / 64;
 }

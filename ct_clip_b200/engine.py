@@ -144,6 +144,14 @@ class CTViTEngine:
         ops.l2norm_rows_bf16(P["vq._codebook.embed"], self.ehat, g.codebook_size, g.dim)
 
     # ------------------------------------------------------------------------------------------
+    def _ds_scratch(self, b, T):
+        """bf16 [b*T*heads, S, S] scratch for the d-logits spill of the spatial backward (1 GB at configs[1]); kept across steps."""
+        g = self.g
+        n = b * T * g.heads * g.S * g.S
+        if getattr(self, "_ds_buf", None) is None or self._ds_buf.numel() < n:
+            self._ds_buf = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+        return self._ds_buf
+
     def _attn_geom(self, b, T, temporal):
         g = self.g
         if not temporal:
@@ -341,7 +349,8 @@ class CTViTEngine:
         ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
                      ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias,
                      bias_frag=bias_t[0] if bias_t else None, bias_t_frag=bias_t[1] if bias_t else None,
-                     dbias=dbias, **self._attn_geom(b, T, temporal))
+                     dbias=dbias, ds_scratch=self._ds_scratch(b, T) if dbias is not None else None,
+                     **self._attn_geom(b, T, temporal))
         # ---- l2norm * scale backward (attention.py:152-154); dq/dk overwritten with raw-projection gradients
         ops.l2norm_bwd(dqh, I, sv.q_raw, I, P[a + "q_scale"], dqh, I, G[a + "q_scale"], M, g.heads)
         ops.l2norm_bwd(dkv, 2 * I, sv.kv_raw, 2 * I, P[a + "k_scale"], dkv, 2 * I, G[a + "k_scale"], M, g.heads)

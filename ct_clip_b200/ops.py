@@ -161,8 +161,9 @@ def attn_fwd(q, k, v, o, lse, **kw):
          work=("F", _attn_flops(kw)))
 
 
-def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, **kw):
+def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, ds_scratch=None, **kw):
     a = _attn_args(q, k, v, o, lse, **kw)
+    a.ds_scratch = _ptr(ds_scratch)
     a.d_o, a.delta = d_o.data_ptr(), delta.data_ptr()
     a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = dq.data_ptr(), ld_dq, dk.data_ptr(), ld_dk, dv.data_ptr(), ld_dv
     a.dbias = _ptr(dbias)

@@ -209,6 +209,9 @@ typedef struct {
    * coalesced 16-byte loads). */
   const uint16_t* bias_frag;
   const uint16_t* bias_t_frag;
+  /* optional scratch, bf16 [num_seqs*heads, n, n] (n even): with dbias, the dQ kernel spills its d logits there and a
+   * streaming reduction over the sequences replaces the third (recomputing) backward pass */
+  uint16_t* ds_scratch;
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);

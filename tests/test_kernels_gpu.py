@@ -203,6 +203,16 @@ def test_attention_fwd_bwd(mode, b, T, S):
     assert rel_err(dkv[:, I:], from_seq(vs.grad)) < 2e-2
     if bias is not None:
         assert rel_err(dbias, bref.grad) < 2e-2
+        if n % 2 == 0:   # second route to dbias: d logits spilled by the dQ kernel + streaming reduction over the sequences
+            num_items = geom["num_seqs"] * heads
+            scratch = torch.full((num_items * n * n,), float("nan"), dtype=torch.bfloat16, device=DEV)
+            dbias2 = torch.zeros(heads, n, n, device=DEV)
+            dq2 = torch.empty_like(dq)
+            ops.attn_bwd(q, k, v, o, lse, d_o, delta, dq2, dkv, dkv[:, I:], ldq=I, ldk=I, ldv=2 * I, ldo=I, ld_dq=I,
+                         ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias, bias_t=bias_t, dbias=dbias2, ds_scratch=scratch,
+                         **geom)
+            assert torch.equal(dq2, dq)
+            assert rel_err(dbias2, bref.grad) < 2e-2
 
 
 def test_l2norm_bwd_and_epilogue():
