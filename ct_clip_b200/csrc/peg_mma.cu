@@ -35,8 +35,8 @@ constexpr int PM_THREADS = 512;  // 16 warps: warp = (channel group = warp & 3, 
 constexpr int PM_WARPS = PM_THREADS / 32;
 constexpr int PM_TOKB = 80;      // bytes per token in the bf16 ring (32 ch x 2 B + 16 B pad)
 constexpr int PM_NSLOT = 3;      // bf16 ring: planes a0-2, a0-1, a0
-constexpr int PM_NSTG = 3;       // fp32 staging buffers of the conv kernels: three planes in flight (the step is far shorter
-                                 // than the DRAM latency: with one plane in flight Little's law capped the kernel at ~2 TB/s)
+constexpr int PM_NSTG = 4;       // fp32 staging buffers of the conv kernels: the plane being computed (its centre tap is the
+                                 // fp32 residual) + three planes in flight (the step is far shorter than the DRAM latency)
 constexpr int PM_NSTG_W = 2;     // weight-gradient kernel: two x planes + two dy tiles in flight
 constexpr int PM_MAXIT = 7;      // loader items per thread and plane: (A1T+2)(W+2)*8/512 <= 7  <=>  W <= 42
 constexpr int PM_PADTOK = 18;    // tokens past the last halo row that shifted ldmatrix rows may touch
@@ -169,9 +169,15 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
   extern __shared__ __align__(128) uint8_t pm_sm[];
   PmGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table, a.W + 2, (PM_A1T + 2) * (a.W + 2), (PM_A1T * (a.W + 2) + 15) / 16};
   const PmSmem sm = pm_carve(pm_sm, g, PM_NSTG);
+  // TEAM scheduling: the n_cb channel blocks of one (volume, line tile, plane) are processed by n_cb CTAs (a team) at
+  // about the same time, so that the 128-byte channel slices of a 2 KB token row are requested while its DRAM page is
+  // open (one CTA per column at its own pace left every 128-byte read on a closed page: all kernel variants plateaued
+  // at 1.4-1.8 TB/s). Team = blockIdx.x / n_cb, channel block = blockIdx.x % n_cb; a team owns a contiguous range of
+  // (volume, line tile, plane) steps.
   const int n_a1t = (a.H + PM_A1T - 1) / PM_A1T, n_cb = a.D / PM_CB;
-  const int total = n_cb * n_a1t * a.B * a.T;
-  const int s_begin = blockIdx.x * steps_per_cta;
+  const int total = n_a1t * a.B * a.T;
+  const int team = blockIdx.x / n_cb, my_cb = blockIdx.x % n_cb;
+  const int s_begin = team * steps_per_cta;
   const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,10 +205,9 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
     const int col = s / a.T;
     const int p_begin = s - col * a.T;
     const int p_end = min(a.T, p_begin + (s_end - s));
-    const PmCol cc = pm_column(col, n_cb, n_a1t);
+    const PmCol cc = pm_column(col * n_cb + my_cb, n_cb, n_a1t);
     const float* xin = a.x + (long long)cc.b * vol + cc.c0;
     const int chp = cc.c0 + cg * 8 + 2 * t;   // this lane's output channel pair
-    const float* xres = a.x + (long long)cc.b * vol + chp;
     float* yout = a.y + (long long)cc.b * vol + chp;
     __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)cc.b * vol + chp : nullptr;
     // block-diagonal weight fragments: B[k = (tap sel, ch_in)][n = ch_out = gq]; this lane holds k = 2t, 2t+1 (+8)
@@ -227,33 +232,38 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
     pm_loader_setup(inpl, g, cc.a1_0);
     const int first = (MODE == 0) ? p_begin : p_end - 1;
     const int dirn = (MODE == 0) ? 1 : -1;
+    // staging buffer of the plane that enters at step i (i = -2, -1: the two extra planes of the first output): i mod 4
     // prime: the three planes of the first output plane in one round trip
 #pragma unroll
-    for (int d = 0; d < 3; d++) pm_issue_plane(stg_u32 + d * g.n_tok * 128, xin, g, first - dirn * d, inpl);
+    for (int d = 0; d < 3; d++)
+      pm_issue_plane(stg_u32 + ((PM_NSTG - d) % PM_NSTG) * g.n_tok * 128, xin, g, first - dirn * d, inpl);
     pm_commit();
     pm_write_tokens(sm.s_tok + par * g.n_mt * 16, g, first, cc.a1_0);
     pm_wait_all();
     __syncthreads();
 #pragma unroll
     for (int d = 0; d < 3; d++)
-      pm_convert_plane(sm.stg + (size_t)d * g.n_tok * 32, sm.ring + (size_t)pm_slot(first - dirn * d) * sm.slot_bytes, inpl);
+      pm_convert_plane(sm.stg + (size_t)((PM_NSTG - d) % PM_NSTG) * g.n_tok * 32,
+                       sm.ring + (size_t)pm_slot(first - dirn * d) * sm.slot_bytes, inpl);
     __syncthreads();
     const int n_steps = p_end - p_begin;
-    // three planes ahead: plane first + d*dirn -> staging buffer (d-1) % 3, one cp.async group per plane (empty groups
-    // keep the group arithmetic uniform near the end of the column)
+    // three planes ahead, one cp.async group per plane (empty groups keep the group arithmetic uniform near the end)
 #pragma unroll
     for (int d = 1; d <= 3; d++) {
-      if (d < n_steps) pm_issue_plane(stg_u32 + ((d - 1) % PM_NSTG) * g.n_tok * 128, xin, g, first + dirn * d, inpl);
+      if (d < n_steps) pm_issue_plane(stg_u32 + (d % PM_NSTG) * g.n_tok * 128, xin, g, first + dirn * d, inpl);
       pm_commit();
     }
     for (int step = 0; step < n_steps; step++, par ^= 1) {
       const int a0 = first + dirn * step;
       const bool more = step + 1 < n_steps;
-      if (step >= 1) {   // the buffer converted at the end of the previous step is free again: refill it, 3 planes ahead
+      if (step >= 1) {   // the fp32 copy of the previous plane is dead (its residual is written): refill it, 3 planes ahead
         if (step + 3 < n_steps)
-          pm_issue_plane(stg_u32 + ((step - 1) % PM_NSTG) * g.n_tok * 128, xin, g, a0 + 3 * dirn, inpl);
+          pm_issue_plane(stg_u32 + ((step + 3) % PM_NSTG) * g.n_tok * 128, xin, g, a0 + 3 * dirn, inpl);
         pm_commit();
       }
+      // fp32 residual = centre tap of the plane that entered at this step: read from its staging buffer (halo token
+      // index of output o is o + a2h + 1), not from global memory (a dependent L2 round trip per row tile otherwise)
+      const float* res_s = sm.stg + (size_t)(step % PM_NSTG) * g.n_tok * 32 + (size_t)(g.a2h + 1) * 32 + cg * 8 + 2 * t;
       // ---- compute plane a0
       uint32_t pb[3];
 #pragma unroll
@@ -265,9 +275,8 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
       for (int mt = mq; mt < g.n_mt; mt += PM_WARPS / 4) {
         const int o0 = mt * 16;
         const int tka = tokp[o0 + gq], tkb = tokp[o0 + gq + 8];
-        float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
-        if (tka >= 0) ra = *reinterpret_cast<const float2*>(xres + (long long)tka * a.D);
-        if (tkb >= 0) rb = *reinterpret_cast<const float2*>(xres + (long long)tkb * a.D);
+        const float2 ra = *reinterpret_cast<const float2*>(res_s + (size_t)(o0 + gq) * 32);
+        const float2 rb = *reinterpret_cast<const float2*>(res_s + (size_t)(o0 + gq + 8) * 32);
         float acc[4] = {bias2.x, bias2.y, bias2.x, bias2.y};
 #pragma unroll
         for (int k0 = 0; k0 < 3; k0++) {
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
       if (more) {
         pm_wait_pending<2>();   // the plane of the next step has landed (the two younger groups may still be in flight)
         __syncthreads();        // everyone finished reading plane a0 - 2*dirn (its slot is refilled now)
-        pm_convert_plane(sm.stg + (size_t)(step % PM_NSTG) * g.n_tok * 32,
+        pm_convert_plane(sm.stg + (size_t)((step + 1) % PM_NSTG) * g.n_tok * 32,
                          sm.ring + (size_t)pm_slot(a0 + dirn) * sm.slot_bytes, inpl);
         pm_write_tokens(sm.s_tok + (par ^ 1) * g.n_mt * 16, g, a0 + dirn, cc.a1_0);
         __syncthreads();
@@ -314,9 +323,15 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_wgrad_kernel(ctclip_peg
   float* dy_stg = reinterpret_cast<float*>(sdy + (size_t)g.n_mt * 16 * PM_TOKB);
   const int dy_elems = PM_A1T * g.W * 32;
   uint8_t* ones = reinterpret_cast<uint8_t*>(dy_stg + (size_t)2 * dy_elems);
+  // TEAM scheduling: the n_cb channel blocks of one (volume, line tile, plane) are processed by n_cb CTAs (a team) at
+  // about the same time, so that the 128-byte channel slices of a 2 KB token row are requested while its DRAM page is
+  // open (one CTA per column at its own pace left every 128-byte read on a closed page: all kernel variants plateaued
+  // at 1.4-1.8 TB/s). Team = blockIdx.x / n_cb, channel block = blockIdx.x % n_cb; a team owns a contiguous range of
+  // (volume, line tile, plane) steps.
   const int n_a1t = (a.H + PM_A1T - 1) / PM_A1T, n_cb = a.D / PM_CB;
-  const int total = n_cb * n_a1t * a.B * a.T;
-  const int s_begin = blockIdx.x * steps_per_cta;
+  const int total = n_a1t * a.B * a.T;
+  const int team = blockIdx.x / n_cb, my_cb = blockIdx.x % n_cb;
+  const int s_begin = team * steps_per_cta;
   const int s_end = min(total, s_begin + steps_per_cta);
   const long long vol = (long long)a.T * a.H * a.W * a.D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,7 +362,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_wgrad_kernel(ctclip_peg
     const int col = s / a.T;
     const int p_begin = s - col * a.T;
     const int p_end = min(a.T, p_begin + (s_end - s));
-    const PmCol cc = pm_column(col, n_cb, n_a1t);
+    const PmCol cc = pm_column(col * n_cb + my_cb, n_cb, n_a1t);
     const float* xin = a.x + (long long)cc.b * vol + cc.c0;
     const float* dyin = a.dy + (long long)cc.b * vol + cc.c0;
     float acc[15][4];
@@ -484,13 +499,16 @@ bool peg_mma_supported(const ctclip_peg_args* a, bool wgrad) {
          (long long)a->B * a->T * a->H * a->W < (1ll << 31) / 64;
 }
 
-static void pm_launch_shape(const ctclip_peg_args* a, int* grid, int* steps_per_cta) {
+static void pm_launch_shape(const ctclip_peg_args* a, int* grid, int* steps_per_team) {
   const int n_a1t = (a->H + PM_A1T - 1) / PM_A1T;
-  const long long total = (long long)(a->D / PM_CB) * n_a1t * a->B * a->T;
-  long long ctas = num_sms();
-  if (ctas > total) ctas = total;
-  *steps_per_cta = (int)((total + ctas - 1) / ctas);
-  *grid = (int)((total + *steps_per_cta - 1) / *steps_per_cta);
+  const int n_cb = a->D / PM_CB;
+  const long long total = (long long)n_a1t * a->B * a->T;      // (volume, line tile, plane) steps, each done by n_cb CTAs
+  long long teams = num_sms() / n_cb;
+  if (teams < 1) teams = 1;
+  if (teams > total) teams = total;
+  *steps_per_team = (int)((total + teams - 1) / teams);
+  teams = (total + *steps_per_team - 1) / *steps_per_team;
+  *grid = (int)(teams * n_cb);
 }
 
 int peg_mma_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream) {
