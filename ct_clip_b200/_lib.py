@@ -70,6 +70,11 @@ class SgemmArgs(C.Structure):
                 ("mask_ref", P), ("ld_mask", I64), ("accumulate", I32)]
 
 
+class PrepDesc(C.Structure):
+    _fields_ = [("W", P), ("ldw", I64), ("gamma", P), ("beta", P), ("bias_in", P), ("rowmap", P), ("out", P),
+                ("K", I32), ("Np", I32), ("Kp", I32), ("kind", I32)]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("t_raw", P), ("i_raw", P), ("B", I32), ("L", I32), ("temperature", P), ("t_hat", P), ("i_hat", P),
                 ("inv_norm", P), ("sim", P), ("loss", P), ("dtemperature", P), ("d_t_raw", P), ("d_i_raw", P),
@@ -106,6 +111,7 @@ SIGNATURES = {
     "ctclip_vq_ema_update": [P, P, P, P, I32, I32, F32, P],
     "ctclip_prep_weight": [P, I64, I32, P, P, I32, I32, P, P],
     "ctclip_prep_bias": [P, I64, I32, P, P, P, I32, P, P],
+    "ctclip_prep_batched": [P, I32, I32, P],
     "ctclip_unprep_wgrad": [P, I64, P, I64, I32, P, P, I32, P, P, P, P, P, P],
     "ctclip_clip_loss": [C.POINTER(LossArgs), P],
     "ctclip_clip_sims": [P, I32, P, I32, I32, P, P, P],

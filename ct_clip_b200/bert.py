@@ -59,14 +59,18 @@ class BertEngine:
         if ver == self._version:
             return
         H, I = self.H, self.inter
+        if getattr(self, "_prep", None) is None:
+            self._prep = ops.PrepBatch()
+        pb = self._prep
         for i, w in enumerate(self.w):
             lp = f"encoder.layer.{i}."
             for j, nm in enumerate(("query", "key", "value")):
-                ops.prep_weight(P[lp + f"attention.self.{nm}.weight"], w["qkv"][j * H:(j + 1) * H], K=H, Np=H, Kp=H)
+                pb.weight(P[lp + f"attention.self.{nm}.weight"], w["qkv"][j * H:(j + 1) * H], K=H, Np=H, Kp=H)
                 w["bqkv"][j * H:(j + 1) * H].copy_(P[lp + f"attention.self.{nm}.bias"])      # 768-float memcpy
-            ops.prep_weight(P[lp + "attention.output.dense.weight"], w["wo"], K=H, Np=H, Kp=H)
-            ops.prep_weight(P[lp + "intermediate.dense.weight"], w["wi"], K=H, Np=I, Kp=H)
-            ops.prep_weight(P[lp + "output.dense.weight"], w["wo2"], K=I, Np=H, Kp=I)
+            pb.weight(P[lp + "attention.output.dense.weight"], w["wo"], K=H, Np=H, Kp=H)
+            pb.weight(P[lp + "intermediate.dense.weight"], w["wi"], K=H, Np=I, Kp=H)
+            pb.weight(P[lp + "output.dense.weight"], w["wo2"], K=I, Np=H, Kp=I)
+        pb.run()      # all operands of the tower in one launch
         self._version = ver
 
     def mark_dirty(self):

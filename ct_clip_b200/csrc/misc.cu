@@ -341,6 +341,35 @@ __global__ void prep_bias_kernel(const float* __restrict__ W, long long ldw, int
   s = warp_sum(s);
   if (lane == 0) out[warp] = (src >= 0) ? s + (bias_in ? bias_in[src] : 0.f) : 0.f;
 }
+// Batched weight preparation: one launch walks a DEVICE table of descriptors (blockIdx.y = descriptor). kind 0 = operand
+// (prep_weight_kernel), kind 1 = bias (prep_bias_kernel). 193 separate launches of 5-12 us each cost 2.3 ms per optimiser
+// step at configs[1]; the data is 150 MB (25 us).
+__global__ void __launch_bounds__(256) prep_batched_kernel(const ctclip_prep_desc* __restrict__ descs) {
+  const ctclip_prep_desc d = descs[blockIdx.y];
+  if (d.kind == 0) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    const long long total = (long long)d.Np * d.Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int k = (int)(i % d.Kp);
+      const int r = (int)(i / d.Kp);
+      const int src = d.rowmap ? d.rowmap[r] : r;
+      float v = 0.f;
+      if (src >= 0 && k < d.K) v = d.W[(long long)src * d.ldw + k] * (d.gamma ? d.gamma[k] : 1.f);
+      out[i] = __float2bfloat16(v);
+    }
+  } else {
+    float* out = reinterpret_cast<float*>(d.out);
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < d.Np; row += gridDim.x * (blockDim.x >> 5)) {
+      const int src = d.rowmap ? d.rowmap[row] : row;
+      float s = 0.f;
+      if (src >= 0 && d.beta != nullptr)
+        for (int k = lane; k < d.K; k += 32) s += d.W[(long long)src * d.ldw + k] * d.beta[k];
+      s = warp_sum(s);
+      if (lane == 0) out[row] = (src >= 0) ? s + (d.bias_in ? d.bias_in[src] : 0.f) : 0.f;
+    }
+  }
+}
 // Given G = dL/dW' (W' = prepared weight, fp32 [Np, ldg]) and s[r] = dL/db'[r]:
 //   dW[src, k] += G[r, k] * gamma[k];  dgamma[k] += sum_r W[src,k] * G[r,k];  dbeta[k] += sum_r W[src,k] * s[r]
 //   dbias[src] += s[r]
@@ -614,6 +643,13 @@ extern "C" int ctclip_prep_weight(const float* W, int64_t ldw, int32_t K, const 
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }
+extern "C" int ctclip_prep_batched(const ctclip_prep_desc* descs_device, int32_t n, int32_t blocks_per_desc, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(descs_device && n > 0 && blocks_per_desc > 0, "prep_batched: bad args");
+  prep_batched_kernel<<<dim3((unsigned)blocks_per_desc, (unsigned)n), 256, 0, stream>>>(descs_device);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
 extern "C" int ctclip_prep_bias(const float* W, int64_t ldw, int32_t K, const float* beta, const float* bias_in,
                                 const int32_t* rowmap, int32_t Np, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -627,7 +663,7 @@ extern "C" int ctclip_unprep_wgrad(const float* G, int64_t ldg, const float* W, 
                                    float* dbeta, float* dbias, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(G && W && dW && K > 0 && Np > 0, "unprep_wgrad: bad args");
-  const int rows_per_cta = 64;
+  const int rows_per_cta = 16;   // 64 serial rows per thread left this kernel latency-bound (43 us for 17 MB)
   dim3 grid(ceil_div(K, 128), ceil_div(Np, rows_per_cta));
   unprep_wgrad_kernel<<<grid, 128, 0, stream>>>(G, ldg, W, ldw, K, gamma, rowmap, Np, s, dW, dgamma, dbeta, dbias, rows_per_cta);
   CTB_LAUNCH_CHECK();

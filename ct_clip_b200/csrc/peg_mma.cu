@@ -11,9 +11,12 @@
 // The weight gradient is the same contraction with positions as K:  dW[(tap, c), c'] = sum_pos x[pos + off, c] dy[pos, c'],
 // of which the diagonal c == c' is kept; an extra all-ones "tap" row yields the bias gradient for free.
 //
+// STATUS: correct (tests/test_kernels_gpu.py::test_peg_fwd_bwd[mma]) but SLOWER than the packed-fp32 stencil of peg.cu on
+// B200 (see peg_mma_supported below), so it is opt-in and the stencil stays the default path.
+//
 // Numerics: the convolution operands (x or dy, and w) are rounded to bf16, exactly what the reference's bf16 autocast does to
 // nn.Conv3d (CTCLIPTrainer.py runs the model under accelerate's bf16 autocast); accumulation, bias and the residual
-// `peg(x) + x` (attention.py:324) stay fp32. The exact-fp32 stencil kernels remain available (ctclip_peg_args.lines = -1).
+// `peg(x) + x` (attention.py:324) stay fp32.
 //
 // Tiling (shared with peg.cu): work unit = one plane-step of a COLUMN (volume, 8 conv-grid lines along a1, 32 channels);
 // planes of the causal axis a0 roll through a 3-slot bf16 ring [token][40 bf16] (80-byte token pitch: conflict-free
@@ -164,8 +167,10 @@ __device__ __forceinline__ PmSmem pm_carve(uint8_t* base, const PmGeom& g, int n
 __device__ __forceinline__ int pm_slot(int pl) { return ((pl % PM_NSLOT) + PM_NSLOT) % PM_NSLOT; }
 
 // MODE 0: y = x + conv(x) + bias (taps a0-2..a0)      MODE 1: dx = dy + conv^T(dy) (taps a0..a0+2, mirrored weights)
+// dbg (probing only, CTCLIP_PEG_DEBUG): bit 0 = no plane loads, bit 1 = no MMAs / output stores, bit 2 = no output stores,
+// bit 3 = no fp32 -> bf16 conversion
 template <int MODE>
-__global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_args a, int steps_per_cta) {
+__global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_args a, int steps_per_cta, int dbg) {
   extern __shared__ __align__(128) uint8_t pm_sm[];
   PmGeom g{a.T, a.H, a.W, a.D, a.temporal, a.canon_table, a.W + 2, (PM_A1T + 2) * (a.W + 2), (PM_A1T * (a.W + 2) + 15) / 16};
   const PmSmem sm = pm_carve(pm_sm, g, PM_NSTG);
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
       const int a0 = first + dirn * step;
       const bool more = step + 1 < n_steps;
       if (step >= 1) {   // the fp32 copy of the previous plane is dead (its residual is written): refill it, 3 planes ahead
-        if (step + 3 < n_steps)
+        if (step + 3 < n_steps && !(dbg & 1))
           pm_issue_plane(stg_u32 + ((step + 3) % PM_NSTG) * g.n_tok * 128, xin, g, a0 + 3 * dirn, inpl);
         pm_commit();
       }
@@ -272,9 +277,10 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
         pb[k0] = ring_u32 + pm_slot(pl) * sm.slot_bytes + lane_off;
       }
       const int* tokp = sm.s_tok + par * g.n_mt * 16;
-      for (int mt = mq; mt < g.n_mt; mt += PM_WARPS / 4) {
+      for (int mt = mq; mt < g.n_mt && !(dbg & 2); mt += PM_WARPS / 4) {
         const int o0 = mt * 16;
-        const int tka = tokp[o0 + gq], tkb = tokp[o0 + gq + 8];
+        int tka = tokp[o0 + gq], tkb = tokp[o0 + gq + 8];
+        if (dbg & 4) tka = tkb = -1;
         const float2 ra = *reinterpret_cast<const float2*>(res_s + (size_t)(o0 + gq) * 32);
         const float2 rb = *reinterpret_cast<const float2*>(res_s + (size_t)(o0 + gq + 8) * 32);
         float acc[4] = {bias2.x, bias2.y, bias2.x, bias2.y};
@@ -302,8 +308,9 @@ __global__ void __launch_bounds__(PM_THREADS, 1) peg_mma_conv_kernel(ctclip_peg_
       if (more) {
         pm_wait_pending<2>();   // the plane of the next step has landed (the two younger groups may still be in flight)
         __syncthreads();        // everyone finished reading plane a0 - 2*dirn (its slot is refilled now)
-        pm_convert_plane(sm.stg + (size_t)((step + 1) % PM_NSTG) * g.n_tok * 32,
-                         sm.ring + (size_t)pm_slot(a0 + dirn) * sm.slot_bytes, inpl);
+        if (!(dbg & 8))
+          pm_convert_plane(sm.stg + (size_t)((step + 1) % PM_NSTG) * g.n_tok * 32,
+                           sm.ring + (size_t)pm_slot(a0 + dirn) * sm.slot_bytes, inpl);
         pm_write_tokens(sm.s_tok + (par ^ 1) * g.n_mt * 16, g, a0 + dirn, cc.a1_0);
         __syncthreads();
       }
@@ -492,8 +499,12 @@ static size_t pm_smem_bytes(const ctclip_peg_args* a, bool wgrad) {
 
 // the tensor-core path needs D % 32 == 0, W <= 42 and the tiles above in <= 227 KB of shared memory
 bool peg_mma_supported(const ctclip_peg_args* a, bool wgrad) {
-  static const int off = getenv("CTCLIP_PEG_FP32") ? atoi(getenv("CTCLIP_PEG_FP32")) : 0;   // debug knob: force the fp32 stencil
-  if (off || a->lines == -1) return false;
+  // Opt-in (ctclip_peg_args.lines == -2 or CTCLIP_PEG_MMA=1). Measured on B200 at configs[1] (tools/peg_probe.py, profiles/):
+  // 305 us per forward launch against 238 us for the packed-fp32 stencil. The formulation re-reads every input element 27
+  // times through ldmatrix (once per tap): 3.7 GB of shared-memory traffic per launch = 100 us at 128 B/clk/SM, plus a
+  // 15-deep dependent HMMA chain per row tile; removing loads, conversion or stores changes little (probe knobs below).
+  static const int on = getenv("CTCLIP_PEG_MMA") ? atoi(getenv("CTCLIP_PEG_MMA")) : 0;
+  if (!(on || a->lines == -2)) return false;
   if (wgrad && 2 * PM_A1T * a->W < (PM_A1T + 2) * (a->W + 2)) return false;   // the dy staging tiles must hold one x plane (W >= 4)
   return a->D % PM_CB == 0 && a->W <= 42 && pm_smem_bytes(a, wgrad) <= 227 * 1024 &&
          (long long)a->B * a->T * a->H * a->W < (1ll << 31) / 64;
@@ -515,12 +526,13 @@ int peg_mma_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream)
   int grid, spc;
   pm_launch_shape(a, &grid, &spc);
   const size_t smem = pm_smem_bytes(a, false);
+  const int dbg = getenv("CTCLIP_PEG_DEBUG") ? atoi(getenv("CTCLIP_PEG_DEBUG")) : 0;
   if (mode == 0) {
     CTB_CUDA(cudaFuncSetAttribute(peg_mma_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    peg_mma_conv_kernel<0><<<grid, PM_THREADS, smem, stream>>>(*a, spc);
+    peg_mma_conv_kernel<0><<<grid, PM_THREADS, smem, stream>>>(*a, spc, dbg);
   } else {
     CTB_CUDA(cudaFuncSetAttribute(peg_mma_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    peg_mma_conv_kernel<1><<<grid, PM_THREADS, smem, stream>>>(*a, spc);
+    peg_mma_conv_kernel<1><<<grid, PM_THREADS, smem, stream>>>(*a, spc, dbg);
   }
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;

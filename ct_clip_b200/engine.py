@@ -93,6 +93,7 @@ class CTViTEngine:
         self.cpb_x = torch.empty(R, 2, device=device)
         ops.cpb_inputs(self.cpb_x, g.H, g.W)
         self._canon = {}
+        self._prep = ops.PrepBatch()
 
     def _canon_table(self, T):
         """canon(f) of the temporal stack's PEG (SURVEY trap T1) as an int32 lookup table (index prep, built once per T)."""
@@ -120,23 +121,25 @@ class CTViTEngine:
         self.ehat = torch.empty(g.codebook_size, g.dim, **bf)
 
     def prepare_weights(self, P: dict):
-        """fp32 master parameters (reference state-dict names, prefix stripped) -> bf16 GEMM operands."""
+        """fp32 master parameters (reference state-dict names, prefix stripped) -> bf16 GEMM operands; ONE launch."""
         g = self.g
         D, I, F, Fp = g.dim, g.inner, g.ff_inner, g.ff_pad
+        pb = self._prep
         for stack, lws in (("enc_spatial_transformer", self.spatial_w), ("enc_temporal_transformer", self.temporal_w)):
             for i, lw in enumerate(lws):
                 a, f = f"{stack}.layers.{i}.1.", f"{stack}.layers.{i}.3."
-                ops.prep_weight(P[a + "to_q.weight"], lw.wq, K=D, Np=I, Kp=D, gamma=P[a + "norm.gamma"])
-                ops.prep_bias(P[a + "to_q.weight"], lw.bq, K=D, Np=I, beta=P[a + "norm.beta"])
-                ops.prep_weight(P[a + "to_kv.weight"], lw.wkv, K=D, Np=2 * I, Kp=D)
-                ops.prep_weight(P[a + "to_out.weight"], lw.wo, K=I, Np=D, Kp=I)
-                ops.prep_weight(P[f + "1.weight"], lw.w1, K=D, Np=2 * Fp, Kp=D, gamma=P[f + "0.weight"], rowmap=self.geglu_map)
-                ops.prep_bias(P[f + "1.weight"], lw.b1, K=D, Np=2 * Fp, beta=P[f + "0.bias"], rowmap=self.geglu_map)
-                ops.prep_weight(P[f + "4.weight"], lw.w2, K=F, Np=D, Kp=Fp)
-        ops.prep_weight(P["to_patch_emb.2.weight"], self.wp, K=g.patch_voxels, Np=D, Kp=g.patch_voxels,
-                        gamma=P["to_patch_emb.1.weight"])
-        ops.prep_bias(P["to_patch_emb.2.weight"], self.bp, K=g.patch_voxels, Np=D, beta=P["to_patch_emb.1.bias"],
-                      bias_in=P["to_patch_emb.2.bias"])
+                pb.weight(P[a + "to_q.weight"], lw.wq, K=D, Np=I, Kp=D, gamma=P[a + "norm.gamma"])
+                pb.bias(P[a + "to_q.weight"], lw.bq, K=D, Np=I, beta=P[a + "norm.beta"])
+                pb.weight(P[a + "to_kv.weight"], lw.wkv, K=D, Np=2 * I, Kp=D)
+                pb.weight(P[a + "to_out.weight"], lw.wo, K=I, Np=D, Kp=I)
+                pb.weight(P[f + "1.weight"], lw.w1, K=D, Np=2 * Fp, Kp=D, gamma=P[f + "0.weight"], rowmap=self.geglu_map)
+                pb.bias(P[f + "1.weight"], lw.b1, K=D, Np=2 * Fp, beta=P[f + "0.bias"], rowmap=self.geglu_map)
+                pb.weight(P[f + "4.weight"], lw.w2, K=F, Np=D, Kp=Fp)
+        pb.weight(P["to_patch_emb.2.weight"], self.wp, K=g.patch_voxels, Np=D, Kp=g.patch_voxels,
+                  gamma=P["to_patch_emb.1.weight"])
+        pb.bias(P["to_patch_emb.2.weight"], self.bp, K=g.patch_voxels, Np=D, beta=P["to_patch_emb.1.bias"],
+                bias_in=P["to_patch_emb.2.bias"])
+        pb.run()
         self.prepare_codebook(P)
 
     def prepare_codebook(self, P):

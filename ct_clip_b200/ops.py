@@ -107,10 +107,10 @@ def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
 
 
 def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
-              dbias=None, lines=4, canon_table=None, exact=False):
-    """exact=True selects the fp32 stencil kernels (ctclip_peg_args.lines = -1); default = bf16 tensor-core kernels."""
-    if exact:
-        lines = -1
+              dbias=None, lines=4, canon_table=None, mma=False):
+    """mma=True opts in to the bf16 tensor-core formulation (ctclip_peg_args.lines = -2); default = exact fp32 stencil."""
+    if mma:
+        lines = -2
     a = PegArgs()
     a.x, a.dy, a.y, a.y_bf16 = x.data_ptr(), _ptr(dy), _ptr(y), _ptr(y_bf16)
     a.weight, a.bias, a.dweight, a.dbias = _ptr(weight), _ptr(bias), _ptr(dweight), _ptr(dbias)
@@ -120,7 +120,7 @@ def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_b
 
 
 def _peg_tag(kw):
-    return ("temporal" if kw.get("temporal") else "spatial") + (" fp32" if kw.get("exact") else "")
+    return ("temporal" if kw.get("temporal") else "spatial") + (" mma" if kw.get("mma") else "")
 
 
 def peg_fwd(x, y, weight, bias, **kw):
@@ -257,6 +257,39 @@ def vq_ema_update(embed, cluster_size, bins, embed_sum, Cn, D, decay=0.8):
 def prep_weight(W, out, *, K, Np, Kp, gamma=None, rowmap=None, ldw=None):
     call("ctclip_prep_weight", W.data_ptr(), ldw if ldw is not None else W.stride(0), K, _ptr(gamma), _ptr(rowmap), Np,
          Kp, out.data_ptr(), _stream())
+
+
+class PrepBatch:
+    """Collects prep_weight / prep_bias work items and runs them in ONE launch (ctclip_prep_batched). The descriptor table
+    lives on the device and is rebuilt only when a tensor address changes (parameters in the trainer's arena never move)."""
+
+    def __init__(self):
+        self.items, self._key, self._table, self._keep = [], None, None, None
+
+    def weight(self, W, out, *, K, Np, Kp, gamma=None, rowmap=None, ldw=None):
+        self.items.append((0, W, ldw if ldw is not None else W.stride(0), gamma, None, None, rowmap, out, K, Np, Kp))
+
+    def bias(self, W, out, *, K, Np, beta=None, bias_in=None, rowmap=None, ldw=None):
+        self.items.append((1, W, ldw if ldw is not None else W.stride(0), None, beta, bias_in, rowmap, out, K, Np, 0))
+
+    def run(self):
+        import numpy as np
+        items, self.items = self.items, []
+        if not items:
+            return
+        key = tuple((it[0], it[1].data_ptr(), it[2], _ptr(it[3]) or 0, _ptr(it[4]) or 0, _ptr(it[5]) or 0, _ptr(it[6]) or 0,
+                     it[7].data_ptr(), it[8], it[9], it[10]) for it in items)
+        if key != self._key:
+            arr = (_lib.PrepDesc * len(items))()
+            for d, it in zip(arr, items):
+                kind, W, ldw, gamma, beta, bias_in, rowmap, out, K, Np, Kp = it
+                d.W, d.ldw, d.gamma, d.beta, d.bias_in = W.data_ptr(), ldw, _ptr(gamma), _ptr(beta), _ptr(bias_in)
+                d.rowmap, d.out, d.K, d.Np, d.Kp, d.kind = _ptr(rowmap), out.data_ptr(), K, Np, Kp, kind
+            host = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+            self._table = host.to(items[0][7].device)
+            self._key = key
+        self._keep = items      # keep the tensors alive until the next run
+        call("ctclip_prep_batched", self._table.data_ptr(), len(items), 64, _stream(), tag=f"{len(items)} operands")
 
 
 def prep_bias(W, out, *, K, Np, beta=None, bias_in=None, rowmap=None, ldw=None):

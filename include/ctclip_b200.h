@@ -148,8 +148,8 @@ int ctclip_patchify(const ctclip_patchify_args* args, void* stream);
  * PEG: causal depthwise 3x3x3 conv + residual on the canonical fp32 token stream [B,T,H,W,D].
  * attention.py:63-84 + the residual at :324. temporal = 1 reproduces the reference's reshape of
  * the (b,h,w,t)-ordered tokens as (b,T,H,W) (SURVEY trap T1).
- * Default arithmetic: m16n8k16 bf16 MMAs with block-diagonal weights (csrc/peg_mma.cu); lines = -1 selects the exact
- * fp32 (packed FFMA2) stencil kernels (csrc/peg.cu), also used when the tile does not fit shared memory (W > 24..42).
+ * Default arithmetic: exact fp32 (packed FFMA2 stencil, csrc/peg.cu); lines = -2 selects the bf16 m16n8k16 formulation
+ * with block-diagonal weights (csrc/peg_mma.cu), kept as a measured alternative.
  *   ctclip_peg_fwd        : y = x + conv(x) + bias          (y_bf16 optional bf16 copy)
  *   ctclip_peg_bwd_data   : y = x + conv^T(x)  with x = upstream gradient
  *   ctclip_peg_bwd_weight : dweight[D,27] += ..., dbias[D] += ...  (x = forward input, dy = upstream)
@@ -165,8 +165,9 @@ typedef struct {
   float* dbias;
   int32_t B, T, H, W, D;
   int32_t temporal;
-  int32_t lines;       /* -1: exact fp32 stencil kernels; any other value: bf16 tensor-core kernels (conv operands rounded
-                          to bf16 like the reference's autocast, fp32 accumulation / bias / residual) where supported */
+  int32_t lines;       /* -2: opt in to the bf16 tensor-core formulation (csrc/peg_mma.cu: conv operands rounded to bf16 like
+                          the reference's autocast; measured slower than the default on B200); anything else: exact fp32
+                          packed-FFMA2 stencil kernels (csrc/peg.cu) */
   const int32_t* canon_table; /* optional, temporal only: canon_table[f] = canonical token of conv-grid index
                                  f = (a0*H + a1)*W + a2, i.e. ((f % T)*H + f / (T*W))*W + (f / T) % W */
 } ctclip_peg_args;
@@ -274,6 +275,19 @@ int ctclip_vq_ema_update(float* embed, float* cluster_size, const float* bins, c
  * bias' [Np] = W[rowmap[r], :] . beta + bias_in[rowmap[r]]; and the reverse mapping of gradients. */
 int ctclip_prep_weight(const float* W, int64_t ldw, int32_t K, const float* gamma, const int32_t* rowmap, int32_t Np,
                        int32_t Kp, void* out, void* stream);
+/* The same two operations for a whole model in ONE launch: `descs` is a DEVICE array of n descriptors (kind 0: operand as
+ * ctclip_prep_weight, kind 1: bias as ctclip_prep_bias), blocks_per_desc CTAs of 256 threads work on each descriptor. */
+typedef struct {
+  const float* W;
+  int64_t ldw;
+  const float* gamma;       /* kind 0 */
+  const float* beta;        /* kind 1 */
+  const float* bias_in;     /* kind 1 */
+  const int32_t* rowmap;
+  void* out;                /* kind 0: bf16 [Np, Kp]; kind 1: f32 [Np] */
+  int32_t K, Np, Kp, kind;
+} ctclip_prep_desc;
+int ctclip_prep_batched(const ctclip_prep_desc* descs, int32_t n, int32_t blocks_per_desc, void* stream);
 int ctclip_prep_bias(const float* W, int64_t ldw, int32_t K, const float* beta, const float* bias_in, const int32_t* rowmap,
                      int32_t Np, float* out, void* stream);
 int ctclip_unprep_wgrad(const float* G, int64_t ldg, const float* W, int64_t ldw, int32_t K, const float* gamma,

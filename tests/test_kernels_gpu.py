@@ -60,7 +60,8 @@ def test_layernorm_fwd_bwd(D):
 @pytest.mark.parametrize("temporal,T,H,W", [(False, 4, 4, 4), (True, 4, 4, 4), (False, 5, 3, 6), (True, 5, 3, 6), (True, 6, 4, 4),
                                             (False, 3, 10, 24), (True, 6, 10, 24)])
 def test_peg_fwd_bwd(temporal, T, H, W, exact):
-    """exact=True: fp32 stencil kernels against the fp32 oracle (1e-5). exact=False: bf16 tensor-core kernels, checked
+    """exact=True: fp32 stencil kernels (the default path) against the fp32 oracle (1e-5). exact=False: the opt-in bf16
+    tensor-core kernels (csrc/peg_mma.cu), checked
     (a) tightly against the oracle evaluated on bf16-ROUNDED conv operands (same arithmetic, different summation order) and
     (b) against the fp32 oracle within the bf16 tolerance of north_star (1e-2)."""
     from ct_clip_b200 import ops
@@ -70,7 +71,7 @@ def test_peg_fwd_bwd(temporal, T, H, W, exact):
     w = 0.2 * _randn(D, 1, 3, 3, 3, seed=8)
     bias = 0.1 * _randn(D, seed=9)
     y = torch.empty_like(x)
-    kw = dict(B=b, T=T, H=H, W=W, D=D, temporal=temporal, exact=exact)
+    kw = dict(B=b, T=T, H=H, W=W, D=D, temporal=temporal, mma=not exact)
     if temporal and T == 6:     # also exercise the precomputed canon(f) table
         f = torch.arange(T * H * W)
         kw["canon_table"] = (((f % T) * H + f // (T * W)) * W + (f // T) % W).to(torch.int32).to(DEV)
