@@ -23,6 +23,7 @@ import threading
 import time
 from pathlib import Path
 
+_OUT_FD = 1
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 os.environ.setdefault("HF_HUB_OFFLINE", "1")
@@ -327,7 +328,7 @@ def run_b200(args):
                               frac=round(r[6], 3)) for r in stage_rows[:16]]
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_volumes=max(2, args.cpu_sample_volumes), timed_steps=1)
-    print(json.dumps(out), flush=True)
+    _emit(_OUT_FD, out)
 
 
 def cpu_baseline(args, sample_volumes=1, timed_steps=1, sample_frames=None):
@@ -426,11 +427,25 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    _emit(_OUT_FD, out)
+
+
+def _quiet_stdout():
+    """Native libraries (NCCL prints its version banner) write to file descriptor 1: route fd 1 to stderr for the whole run
+    and keep a private duplicate for the ONE JSON line the contract asks for."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(fd, obj):
+    os.write(fd, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
     a = parse()
+    _OUT_FD = _quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

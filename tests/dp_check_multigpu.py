@@ -56,6 +56,8 @@ def main():
         torch.cuda.synchronize()
         worst = 0.0
         for k, v in tr1.CTClip.named_parameters():
+            if v.numel() == 0:      # null_kv (heads, 0, dim_head)
+                continue
             d = (v.detach() - after_dp[k]).abs().max().item()
             worst = max(worst, d)
         emb_d = (tr1.CTClip.visual_transformer.vq._codebook.embed - emb_dp).abs().max().item()
