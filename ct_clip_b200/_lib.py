@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("epilogue", I32), ("splits", I32),
         ("C", P), ("ldc", I64), ("bias", P), ("resid", P), ("ldr", I64),
         ("C2", P), ("ldc2", I64), ("arg_out", P), ("argval_out", P),
-        ("norm_cols", I32), ("norm_scale", P),
+        ("norm_cols", I32), ("norm_scale", P), ("colsum", P),
     ]
 
 
@@ -81,7 +81,7 @@ class LossArgs(C.Structure):
                 ("row0", I32), ("nrows", I32), ("loss_scale", F32)]
 
 
-EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_L2NORM, EPI_BIAS_GELU = range(8)
+EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_GEGLU, EPI_ATOMIC_F32, EPI_ARGMAX, EPI_L2NORM, EPI_BIAS_GELU, EPI_GEGLU_BWD = range(9)
 
 # name -> argtypes (every entry point returns int and takes the stream last)
 SIGNATURES = {

@@ -23,7 +23,8 @@ constexpr int EPI_WARPS = 8;    // generic kernel; the EPW = 16 instantiation se
 constexpr int GEMM_THREADS = (2 + EPI_WARPS) * 32;
 constexpr int EPW_LIGHT = 12;   // epilogue warps of the register-light variant: 14 warps -> 128 registers / thread
 
-enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5, EPI_L2NORM = 6, EPI_BIAS_GELU = 7 };
+enum { EPI_BF16 = 0, EPI_F32 = 1, EPI_RESID_F32 = 2, EPI_GEGLU = 3, EPI_ATOMIC_F32 = 4, EPI_ARGMAX = 5, EPI_L2NORM = 6, EPI_BIAS_GELU = 7,
+       EPI_GEGLU_BWD = 8 };
 
 struct GemmKParams {
   int M, N, K;
@@ -45,6 +46,7 @@ struct GemmKParams {
   int norm_cols;
   const float* norm_scale;
   int fast_store;  // all output / residual rows are 16-byte aligned: staged, fully coalesced epilogue stores
+  float* colsum;   // GEGLU_BWD: global column sums of the result (2N floats), accumulated through shared memory
   int fast_epi;    // use the specialised epilogue loops (fast_store && N % 32 == 0 && not ARGMAX / ATOMIC)
 };
 
@@ -177,7 +179,7 @@ __device__ __forceinline__ void resid_prefetch(float4 (&buf)[8], const float* rb
 // single coalesced load per warp and broadcast through 128 B of shared memory (v1 issued eight dependent
 // ld.global.nc.v4 per thread right before their first use; that long-scoreboard stall was the top stall of the K=512
 // GEMMs).
-constexpr int EPI_NONE_DEBUG = 8;   // probe: drain the accumulator without storing (mainloop ceiling)
+constexpr int EPI_NONE_DEBUG = 9;   // probe: drain the accumulator without storing (mainloop ceiling)
 
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& u) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
@@ -403,6 +405,129 @@ __device__ __forceinline__ void epilogue_fast(const GemmKParams& p, uint32_t tme
   }
 }
 
+// ---- GEGLU backward fused into the d(g) GEMM -------------------------------------------------------------------------
+// acc = dg[m, j] = dL/d(gelu(gate_j) value_j); C = h (bf16, interleaved pre-activation (value_j, gate_j) at columns 2j, 2j+1),
+// updated IN PLACE to (dvalue_j, dgate_j) = (dg gelu(gate), dg value gelu'(gate)); column sums of the result (the bias
+// gradient of the folded LayerNorm) are accumulated in shared memory per CTA and flushed once at the end.
+// Replaces a 311 MB bf16 round trip of dg plus a separate elementwise kernel (attention.py:39-42 backward).
+// gelu / gelu' share one exp and one erf (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7).
+__device__ __forceinline__ void geglu_bwd_pair(float dg, float value, float gate, float& dval, float& dgate) {
+  const float ax = fabsf(gate);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((gate * gate) * (-0.5f * 1.4426950408889634f)));
+  const float half_erfc = 0.5f * poly * e;                         // 0.5 erfc(|gate| / sqrt 2)
+  const float cdf = (gate >= 0.f) ? 1.0f - half_erfc : half_erfc;  // Phi(gate)
+  const float pdf = 0.39894228040143267794f * e;                   // phi(gate)
+  dval = dg * (gate * cdf);
+  dgate = dg * value * fmaf(gate, pdf, cdf);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_geglu_bwd(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                   uint64_t* tempty_bar, uint32_t st, float* s_cs, int warp, int lane) {
+  constexpr int NCH = (BN / 32 + 1) / 2;
+  const int q = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int tid_e = threadIdx.x - 64;    // 0 .. 255 among the epilogue warps
+  for (int i = tid_e; i < 2 * p.N; i += EPI_WARPS * 32) s_cs[i] = 0.f;
+  asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+  __nv_bfloat16* hbase = reinterpret_cast<__nv_bfloat16*>(p.C);
+  uint32_t it_ = 0;
+  for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, it_++) {
+    const int n_blk = unit % p.n_groups;
+    const int m_blk = (unit / p.n_groups) % p.m_blks;
+    const long long row0 = (long long)m_blk * BM + q * 32;
+    const int rows_valid = (int)max(0LL, min(32LL, (long long)p.M - row0));
+    const uint32_t acc = it_ & 1;
+    const uint32_t acc_phase = (it_ >> 1) & 1;
+    const int colbase = n_blk * BN + half * 32;
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * 32;
+#pragma unroll 1
+    for (int i = 0; i < NCH; i++) {
+      const int col0 = colbase + i * 64;
+      if (col0 >= p.N) break;   // warp-uniform
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + i * 64, raw);
+      // this lane's h elements in the transposed ownership: rows it*8 + lane/4, dg columns hh*16 + (lane%4)*4 .. +3
+      uint4 hv[2][4];
+      __nv_bfloat16* hp = hbase + (row0 + (lane >> 2)) * p.ldc + 2 * (col0 + (lane & 3) * 4);
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          const int r = it * 8 + (lane >> 2);
+          hv[hh][it] = (r < rows_valid) ? *reinterpret_cast<const uint4*>(hp + (long long)it * 8 * p.ldc + hh * 32)
+                                        : make_uint4(0, 0, 0, 0);
+        }
+      tmem_ld_wait();
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint4 u;
+          u.x = raw[16 * hh + 4 * k + 0];
+          u.y = raw[16 * hh + 4 * k + 1];
+          u.z = raw[16 * hh + 4 * k + 2];
+          u.w = raw[16 * hh + 4 * k + 3];
+          sts128(stg_put_addr(st, lane, k), u);
+        }
+        __syncwarp();
+        float cs[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) cs[k] = 0.f;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          const int r = it * 8 + (lane >> 2);
+          const uint4 d4 = lds128(stg_get_addr(st, r, lane & 3));
+          const float dgv[4] = {__uint_as_float(d4.x), __uint_as_float(d4.y), __uint_as_float(d4.z), __uint_as_float(d4.w)};
+          uint4 hw = hv[hh][it];
+          uint32_t* ph = reinterpret_cast<uint32_t*>(&hw);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float2 xv = unpack_bf16x2(ph[k]);   // (value, gate)
+            float dval, dgate;
+            geglu_bwd_pair(dgv[k], xv.x, xv.y, dval, dgate);
+            ph[k] = pack_bf16x2(dval, dgate);
+            if (r < rows_valid) {
+              cs[2 * k] += dval;
+              cs[2 * k + 1] += dgate;
+            }
+          }
+          if (r < rows_valid) *reinterpret_cast<uint4*>(hp + (long long)it * 8 * p.ldc + hh * 32) = hw;
+        }
+        __syncwarp();
+        // column sums: reduce over the 8 lanes that share lane % 4, then one shared-memory add per column
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+          cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+          cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+        }
+        if ((lane >> 2) == 0) {
+          float* dst = s_cs + 2 * (col0 + hh * 16 + (lane & 3) * 4);
+#pragma unroll
+          for (int k = 0; k < 8; k++) atomicAdd(dst + k, cs[k]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+  if (p.colsum != nullptr)
+    for (int i = tid_e; i < 2 * p.N; i += EPI_WARPS * 32) atomicAdd(p.colsum + i, s_cs[i]);
+}
+
 template <int BN, int AMAJ, int BMAJ, int EPW>
 __global__ void __launch_bounds__((2 + EPW) * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -550,6 +675,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           case EPI_GEGLU: epilogue_fast<BN, EPI_GEGLU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
           case EPI_L2NORM: epilogue_fast<BN, EPI_L2NORM, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
           case EPI_BIAS_GELU: epilogue_fast<BN, EPI_BIAS_GELU, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
+          case EPI_GEGLU_BWD:
+            if (EPW == EPI_WARPS)
+              epilogue_geglu_bwd<BN>(p, tmem_base, tfull_bar, tempty_bar, st32, reinterpret_cast<float*>(stage_all + EPW * 2048), warp, lane);
+            break;
           default: epilogue_fast<BN, EPI_NONE_DEBUG, EPW>(p, tmem_base, tfull_bar, tempty_bar, st32, sb32, warp, lane); break;
         }
       }
@@ -827,13 +956,21 @@ static int launch_gemm_epw(const ctclip_gemm_args* a, GemmKParams& p, cudaStream
   p.num_units = p.m_blks * p.n_groups * p.splits;
 
   auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, EPW>;
+  constexpr int kColsumBytes = 12 * 1024;   // GEGLU_BWD: per-CTA column-sum accumulator (2N floats, N <= 1536)
+  constexpr int kMaxSmem = (Cfg::SMEM_BYTES + kColsumBytes <= 227 * 1024) ? Cfg::SMEM_BYTES + kColsumBytes : Cfg::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
+  int smem = Cfg::SMEM_BYTES;
+  if (p.epi == EPI_GEGLU_BWD) {
+    CTB_CHECK_ARG(EPW == EPI_WARPS && kMaxSmem > Cfg::SMEM_BYTES && 2 * p.N * 4 <= kColsumBytes && p.fast_epi,
+                  "gemm: GEGLU_BWD needs N <= 1536, 16-byte aligned rows of C and the 8-warp kernel");
+    smem = kMaxSmem;
+  }
   const int grid = p.num_units < num_sms() ? p.num_units : num_sms();
-  kern<<<grid, (2 + EPW) * 32, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, (2 + EPW) * 32, smem, stream>>>(ta, tb, p);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }
@@ -863,7 +1000,10 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
                 "gemm: operand pitch must be a multiple of 16 bytes (lda=%lld ldb=%lld)",
                 (long long)a->lda, (long long)a->ldb);
   CTB_CHECK_ARG(((uintptr_t)a->A % 16) == 0 && ((uintptr_t)a->B % 16) == 0, "gemm: operands must be 16B aligned");
-  CTB_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 7, "gemm: bad epilogue %d", a->epilogue);
+  CTB_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 8, "gemm: bad epilogue %d", a->epilogue);
+  if (a->epilogue == EPI_GEGLU_BWD)
+    CTB_CHECK_ARG(a->C != nullptr && a->N % 32 == 0 && a->ldc % 8 == 0 && a->bias == nullptr,
+                  "gemm: GEGLU_BWD needs C = h (bf16 [M, 2N], 16-byte aligned rows), N a multiple of 32 and no bias");
   if (a->epilogue == EPI_L2NORM)
     CTB_CHECK_ARG(a->C2 != nullptr && a->norm_scale != nullptr && a->N % 32 == 0 && a->norm_cols % 32 == 0 &&
                       a->ldc % 8 == 0 && a->ldc2 % 8 == 0,
@@ -919,6 +1059,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   p.C2 = a->C2; p.ldc2 = a->ldc2;
   p.arg_out = a->arg_out; p.argval_out = a->argval_out;
   p.norm_cols = a->norm_cols; p.norm_scale = a->norm_scale;
+  p.colsum = a->colsum;
   {
     const bool out_f32 = (a->epilogue == EPI_F32 || a->epilogue == EPI_RESID_F32);
     const int esz = out_f32 ? 4 : 2;

@@ -135,6 +135,7 @@ class CTCLIP(nn.Module):
         # data-parallel hooks (set by CTClipTrainer): gather latents of all ranks before the loss
         self.dp_rank, self.dp_world = 0, 1
         self.dp_all_gather = None
+        self.dp_early_reduce = None      # callable(param name): start the gradient all-reduce of that tensor right away
         self._wv_bf16 = None
         self._wv_version = None
         self._grad_sink = None
@@ -280,6 +281,8 @@ class CTCLIP(nn.Module):
         ops.cast_bf16(d_i, d_i_bf, b * L)
         ops.gemm(d_i_bf, st.pooled_bf16, M=L, N=K, K=b, a_major=1, b_major=1, epilogue=ops.EPI_ATOMIC_F32,
                  C_out=G["to_visual_latent.weight"], ldc=K)
+        if self.dp_early_reduce is not None:   # 604 MB of the 1.14 GB gradient are final here: all-reduce them behind the towers' backward
+            self.dp_early_reduce("to_visual_latent.weight")
         dpooled = torch.empty(b, K, device=dev)
         ops.gemm(d_i_bf, self._visual_weight_bf16(P["to_visual_latent.weight"]), M=b, N=K, K=L, b_major=1,
                  epilogue=ops.EPI_F32, C_out=dpooled)

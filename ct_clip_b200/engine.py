@@ -328,11 +328,14 @@ class CTViTEngine:
         a, f = pre + "1.", pre + "3."
         # ---- feed-forward: x3 = x2 + g W2^T,  (h, g) = GEGLU(xhat2 W1'^T + b1')
         self._wgrad(dxb, sv.g, G[f + "4.weight"], n_out=D, k_out=F, rows=M)
-        dg = torch.empty(M, Fp, **bf)
-        ops.gemm(dxb, lw.w2, M=M, N=Fp, K=D, b_major=1, epilogue=ops.EPI_BF16, C_out=dg)
         s1 = torch.zeros(2 * Fp, device=dev)
-        ops.geglu_bwd(dg, sv.h, M=M, n_pairs=Fp, colsum_out=s1)          # sv.h now holds dh
-        del dg
+        if Fp <= 1536:    # dg = dxb W2 and the GEGLU backward in ONE kernel: sv.h (value, gate) -> dh in place, s1 = column sums
+            ops.gemm(dxb, lw.w2, M=M, N=Fp, K=D, b_major=1, epilogue=ops.EPI_GEGLU_BWD, C_out=sv.h, ldc=2 * Fp, colsum=s1)
+        else:             # wider feed-forward (dim 768): the shared-memory column-sum accumulator does not fit
+            dg = torch.empty(M, Fp, **bf)
+            ops.gemm(dxb, lw.w2, M=M, N=Fp, K=D, b_major=1, epilogue=ops.EPI_BF16, C_out=dg)
+            ops.geglu_bwd(dg, sv.h, M=M, n_pairs=Fp, colsum_out=s1)          # sv.h now holds dh
+            del dg
         G1 = torch.zeros(2 * Fp, D, device=dev)
         self._wgrad(sv.h, sv.xhat2, G1, n_out=2 * Fp, k_out=D, rows=M)
         ops.unprep_wgrad(G1, P[f + "1.weight"], G[f + "1.weight"], K=D, Np=2 * Fp, gamma=P[f + "0.weight"],

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_BIAS_GELU, EPI_F32, EPI_GEGLU, EPI_L2NORM,  # noqa: F401
+from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_BIAS_GELU, EPI_F32, EPI_GEGLU, EPI_GEGLU_BWD, EPI_L2NORM,  # noqa: F401
                    EPI_RESID_F32, AttnArgs, GemmArgs, LnBwdArgs, LnFwdArgs, LossArgs, PatchifyArgs, PegArgs,
                    SgemmArgs, call)
 
@@ -30,7 +30,7 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, bias=None, resid=None, C2=None,
          arg_out=None, argval_out=None, splits=1, lda=None, ldb=None, ldc=None, ldc2=None, norm_cols=0,
-         norm_scale=None):
+         norm_scale=None, colsum=None):
     """C[M,N] = sum_k A(m,k) B(n,k); see include/ctclip_b200.h for the epilogues."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
     a = GemmArgs()
@@ -50,6 +50,7 @@ def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, 
     a.argval_out = _ptr(argval_out)
     a.norm_cols = norm_cols
     a.norm_scale = _ptr(norm_scale)
+    a.colsum = _ptr(colsum)
     if GEMM_TIMER is None:
         call("ctclip_gemm_bf16", C.byref(a), _stream(), tag=f"{M}x{N}x{K} a{a_major}b{b_major} epi{epilogue} s{splits}",
              work=("F", 2.0 * M * N * K))

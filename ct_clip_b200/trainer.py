@@ -147,6 +147,13 @@ class CTClipTrainer(nn.Module):
 
         from .dist_utils import gather_latents as gather
         clip.dp_all_gather = gather
+        self._early = None
+
+        def early(name):
+            # NCCL runs on the process group's own stream: the collective starts once the kernels enqueued so far are done
+            # and overlaps everything enqueued after it (the whole image/text tower backward)
+            self._early = (name, dist.all_reduce(self.arena.grad_views[name], op=dist.ReduceOp.SUM, async_op=True))
+        clip.dp_early_reduce = early
         clip.visual_transformer.ema_all_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     @property
@@ -188,7 +195,19 @@ class CTClipTrainer(nn.Module):
         loss = self.CTClip(text_tokens, video, return_loss=True, device=self.device)
         loss.backward()
         if self.world > 1:
-            dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)
+            if self._early is not None:      # the visual projection's gradient is already on the wire: reduce the rest
+                name, work = self._early
+                self._early = None
+                i = self.arena.names.index(name)
+                lo = self.arena.offsets[i]
+                hi = self.arena.offsets[i + 1] if i + 1 < len(self.arena.offsets) else self.arena.numel
+                if lo > 0:
+                    dist.all_reduce(self.arena.g[:lo], op=dist.ReduceOp.SUM)
+                if hi < self.arena.numel:
+                    dist.all_reduce(self.arena.g[hi:], op=dist.ReduceOp.SUM)
+                work.wait()
+            else:
+                dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)
         self.arena.adam_step(lr=self.lr, max_norm=self.max_grad_norm)
         self.CTClip.mark_weights_dirty()
         return loss

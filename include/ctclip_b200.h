@@ -56,6 +56,9 @@ const char* ctclip_last_error(void);
  *                C2(bf16)[m,n] = acc / max(||acc_group||, 1e-12) * norm_scale[n % 32]   for n < norm_cols
  *                (attention.py:152-154 l2norm(q)*q_scale fused into the projection)
  *   7 BIAS_GELU  C(bf16) = gelu_erf(acc + bias), C2(bf16, optional) = acc + bias  (BERT intermediate)
+ *   8 GEGLU_BWD  acc = dL/d(gelu(gate_j) value_j); C = h(bf16)[m, 2N] interleaved pre-activation, updated IN PLACE:
+ *                h[m,2j] <- acc * gelu(gate_j), h[m,2j+1] <- acc * value_j * gelu'(gate_j); colsum[2N] += column sums
+ *                of the result (optional). N <= 1536. Fuses ctclip_geglu_bwd into the preceding GEMM.
  * splits: split-K factor (only with ATOMIC_F32), >= 1; 0 = chosen by the library (minimises waves x k-blocks per unit).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -78,6 +81,7 @@ typedef struct {
   float* argval_out;
   int32_t norm_cols;
   const float* norm_scale;
+  float* colsum;          /* GEGLU_BWD: [2N] column sums, accumulated */
 } ctclip_gemm_args;
 
 int ctclip_gemm_bf16(const ctclip_gemm_args* args, void* stream);

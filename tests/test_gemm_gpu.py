@@ -71,6 +71,26 @@ def test_gemm_geglu(M, N, K):
     _close(G, refg, 1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 1408, 512), (384, 64, 128), (300, 96, 256)])
+def test_gemm_geglu_bwd_fused(M, N, K):
+    """epilogue 8: dg = A W (W stored [K, N], MN-major as in the engine) fused with the GEGLU backward on the interleaved
+    pre-activation h (in place) and the column sums of the result (attention.py:39-42 backward)."""
+    from ct_clip_b200 import ops
+    A, W = _mk(M, K, 21), _mk(K, N, 22, 0.05)
+    h = _mk(M, 2 * N, 23)
+    h0 = h.clone()
+    cs = torch.zeros(2 * N, device="cuda")
+    ops.gemm(A, W, M=M, N=N, K=K, b_major=1, epilogue=ops.EPI_GEGLU_BWD, C_out=h, ldc=2 * N, colsum=cs)
+    torch.cuda.synchronize()
+    dg = A.float() @ W.float()
+    value, gate = h0.float()[:, 0::2].clone().requires_grad_(True), h0.float()[:, 1::2].clone().requires_grad_(True)
+    (torch.nn.functional.gelu(gate) * value * dg).sum().backward()
+    ref = torch.empty(M, 2 * N, device="cuda")
+    ref[:, 0::2], ref[:, 1::2] = value.grad, gate.grad
+    _close(h, ref, 1e-2)
+    _close(cs, ref.sum(0), 1e-2)
+
+
 @pytest.mark.parametrize("amaj,bmaj", [(1, 1), (0, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K,splits", [(768, 512, 4096, 1), (2816, 512, 8192, 8), (512, 4000, 1024, 3), (256, 128, 200, 2)])
 def test_gemm_mn_major_atomic(amaj, bmaj, M, N, K, splits):
