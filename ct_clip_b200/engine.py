@@ -94,6 +94,7 @@ class CTViTEngine:
         ops.cpb_inputs(self.cpb_x, g.H, g.W)
         self._canon = {}
         self._prep = ops.PrepBatch()
+        self.fused_geglu_bwd = False
 
     def _canon_table(self, T):
         """canon(f) of the temporal stack's PEG (SURVEY trap T1) as an int32 lookup table (index prep, built once per T)."""
@@ -329,7 +330,10 @@ class CTViTEngine:
         # ---- feed-forward: x3 = x2 + g W2^T,  (h, g) = GEGLU(xhat2 W1'^T + b1')
         self._wgrad(dxb, sv.g, G[f + "4.weight"], n_out=D, k_out=F, rows=M)
         s1 = torch.zeros(2 * Fp, device=dev)
-        if Fp <= 1536:    # dg = dxb W2 and the GEGLU backward in ONE kernel: sv.h (value, gate) -> dh in place, s1 = column sums
+        # GEMM epilogue 8 fuses these two kernels (tests/test_gemm_gpu.py::test_gemm_geglu_bwd_fused) but measured 0.66 ms
+        # per layer against 0.15 + 0.33 ms for the pair on B200 (the 8-warp epilogue becomes the bottleneck: ~25
+        # instructions per (value, gate) pair + column-sum shuffles): kept opt-in.
+        if self.fused_geglu_bwd and Fp <= 1536:    # dg = dxb W2 and the GEGLU backward in ONE kernel
             ops.gemm(dxb, lw.w2, M=M, N=Fp, K=D, b_major=1, epilogue=ops.EPI_GEGLU_BWD, C_out=sv.h, ldc=2 * Fp, colsum=s1)
         else:             # wider feed-forward (dim 768): the shared-memory column-sum accumulator does not fit
             dg = torch.empty(M, Fp, **bf)
