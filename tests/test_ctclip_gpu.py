@@ -36,11 +36,17 @@ def build_clip(kw, bert_layers=2, seed=0):
     return clip.cuda(), sd, cfg
 
 
-def test_contrastive_step_matches_oracle():
+# BASELINE.json configs[4] geometry scaled down: dim 768 (24 PEG channel blocks, ff inner 2048, LayerNorm D = 6 x 128),
+# T = 6 != H = W = 4 (temporal PEG axis scramble), 1+1 layers
+CFG5_SMALL = dict(dim=768, codebook_size=1024, image_size=64, patch_size=16, temporal_patch_size=8, spatial_depth=1,
+                  temporal_depth=1, dim_head=32, heads=8)
+
+
+@pytest.mark.parametrize("kw,frames", [(CFG1_VIT, 32), (CFG5_SMALL, 48)], ids=["cfg1", "cfg5_small"])
+def test_contrastive_step_matches_oracle(kw, frames):
     from oracle import ctclip_oracle as O
-    kw = CFG1_VIT
     clip, sd, cfg = build_clip(kw)
-    hu, ids, mask = O.synth_inputs(2, 32, 64, 32)
+    hu, ids, mask = O.synth_inputs(2, frames, 64, 32)
     video = hu.float() / 1000.0
     # ---- oracle (CPU fp32, autograd)
     sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
