@@ -77,7 +77,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def window(self, t0, t1):
+        """keep only the samples taken inside [t0, t1] (the sampler is started early: nvidia-smi needs ~0.3 s to come up)"""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if inside:
+            self.rows = inside
 
     def stop(self):
         if self.proc is None:
@@ -85,6 +91,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
+            r = r[1:]
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -186,6 +193,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident steps (value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()      # early: nvidia-smi takes a few hundred ms to deliver its first sample
     for w_ in range(args.warmup):
         trainer.step_on_batch(*dev[w_ % 2])
     barrier()
@@ -202,10 +212,8 @@ def run_b200(args):
     barrier()
     gemm_events = []
     ops.GEMM_TIMER = gemm_events
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count
+    t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
@@ -216,6 +224,8 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = (_lib.launch_count - launches0) // max(1, args.steps)
+    if rank == 0:
+        sampler.window(t_wall0, time.time())
     clocks = sampler.stop() if rank == 0 else None
     ops.GEMM_TIMER = None
     loss_val = float(loss.item())
