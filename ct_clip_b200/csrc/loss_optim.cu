@@ -167,13 +167,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     coef *= fminf(1.f, max_norm / (norm + 1e-6f));
   }
   const float step = lr / bc1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  auto upd = [&](float gi_, float& mi_, float& vi_, float& pi_) {
+    const float gi = gi_ * coef;
+    mi_ = beta1 * mi_ + (1.f - beta1) * gi;
+    vi_ = beta2 * vi_ + (1.f - beta2) * gi * gi;
+    pi_ -= step * mi_ / (sqrtf(vi_) / bc2_sqrt + eps);
+  };
+  // 16-byte accesses (the arena keeps every tensor 16-byte aligned): 28 B/param of traffic, four streams per thread
+  const long long n4 = (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                          reinterpret_cast<uintptr_t>(v)) & 15) == 0) ? n / 4 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    upd(g4.x, m4.x, v4.x, p4.x);
+    upd(g4.y, m4.y, v4.y, p4.y);
+    upd(g4.z, m4.z, v4.z, p4.z);
+    upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
     m[i] = mi;
     v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi;
   }
 }
 
