@@ -1292,7 +1292,11 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
     CTB_LAUNCH_CHECK();
     return CTCLIP_OK;
   }
-  if (int rc = attn_route(1, a, stream)) return rc;
+  // the d-logits spill stores bf16 PAIRS: only with an even sequence length (else the recomputing dbias kernel is used)
+  ctclip_attn_args a_nospill = *a;
+  a_nospill.ds_scratch = nullptr;
+  const ctclip_attn_args* a_dq = (a->ds_scratch != nullptr && a->n % 2 == 0) ? a : &a_nospill;
+  if (int rc = attn_route(1, a_dq, stream)) return rc;
   if (int rc = attn_route(2, a, stream)) return rc;
   if (a->dbias != nullptr && a->ds_scratch != nullptr && a->n % 2 == 0) {
     // the dQ kernel spilled its d logits: reduce them over the sequences (replaces the recomputing third pass)
