@@ -370,7 +370,14 @@ def cpu_baseline(args, sample_volumes=1, timed_steps=1, sample_frames=None):
         out["loss"].backward()
     dt = time.time() - t0
     frac = sample_frames / args.frames
+    cpu_model = "unknown CPU"
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next(ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name"))
+    except Exception:
+        pass
     return {"value": sample_volumes * frac * timed_steps / dt, "unit": "volumes/s", "cores": cores, "kind": "port",
+            "cpu": f"{cpu_model}, {os.cpu_count()} hardware threads on the host, {cores} used",
             "sample": f"{timed_steps} step(s) of forward+loss+backward on {sample_volumes} slab(s) of {sample_frames}/{args.frames} "
                       f"frames ({args.image}x{args.image}, depth {args.depth}+{args.depth}, BERT {args.bert_layers}L, {args.text_len} tokens), "
                       f"fp32, torch CPU {cores} threads, no optimiser step; scaled by {1 / frac:.0f} slabs per volume",
@@ -419,7 +426,7 @@ def run_reference(args):
     if rank != 0:
         return
     vols_per_step = 2      # two slabs (the InfoNCE loss needs >= 2 samples to be non-trivial)
-    t_all, vals, sample = [], [], ""
+    t_all, vals, sample, cpu = [], [], "", ""
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_baseline(args, sample_volumes=vols_per_step, timed_steps=1)
     for _ in range(max(1, min(args.steps, 3))):
@@ -427,6 +434,7 @@ def run_reference(args):
         t_all.append(r["seconds"])
         vals.append(r["value"])
         sample = r["sample"]
+        cpu = r.get("cpu", "")
     ms = 1e3 * sum(t_all) / len(t_all)
     val = sum(vals) / len(vals)
     cores = min(os.cpu_count() or 1, 32)
@@ -434,7 +442,7 @@ def run_reference(args):
            "unit": "volumes/s", "n_gpus": args.gpus, "steps": len(t_all), "warmup": min(args.warmup, 1), "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "same model/config as the b200 arm; each step = a bounded sample: " + sample, "parallelism": "cpu"},
-           "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "volumes/s", "cores": cores, "kind": "port", "cpu": cpu, "sample": sample},
            "e2e": {"value": val, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     _emit(_OUT_FD, out)
