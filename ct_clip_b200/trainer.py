@@ -35,6 +35,15 @@ def _dist_env():
     return world, rank, local
 
 
+def rest_slices(names, offsets, numel, name):
+    """[lo, hi) ranges of a flat arena (tensor `names[i]` starts at `offsets[i]`) that are NOT covered by tensor `name`:
+    what remains to be all-reduced after `name` went out early."""
+    i = names.index(name)
+    lo = offsets[i]
+    hi = offsets[i + 1] if i + 1 < len(offsets) else numel
+    return [(a, b) for a, b in ((0, lo), (hi, numel)) if b > a]
+
+
 class ParamArena:
     """Flat fp32 storage for parameters, gradients and Adam moments; module parameters become views into it."""
 
@@ -198,13 +207,8 @@ class CTClipTrainer(nn.Module):
             if self._early is not None:      # the visual projection's gradient is already on the wire: reduce the rest
                 name, work = self._early
                 self._early = None
-                i = self.arena.names.index(name)
-                lo = self.arena.offsets[i]
-                hi = self.arena.offsets[i + 1] if i + 1 < len(self.arena.offsets) else self.arena.numel
-                if lo > 0:
-                    dist.all_reduce(self.arena.g[:lo], op=dist.ReduceOp.SUM)
-                if hi < self.arena.numel:
-                    dist.all_reduce(self.arena.g[hi:], op=dist.ReduceOp.SUM)
+                for lo, hi in rest_slices(self.arena.names, self.arena.offsets, self.arena.numel, name):
+                    dist.all_reduce(self.arena.g[lo:hi], op=dist.ReduceOp.SUM)
                 work.wait()
             else:
                 dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)

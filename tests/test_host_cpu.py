@@ -37,7 +37,7 @@ def test_dropin_import_names_and_constructor_surface():
     from zero_shot import CTClipInference  # noqa: F401    (run_zero_shot.py:4)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "scramble"])
+@pytest.mark.parametrize("name", ["cfg1", "scramble", "cfg5_small"])
 def test_state_dict_layout_matches_reference_golden(name):
     """Key set and shapes equal the reference's own state_dict (recorded in the golden file)."""
     from transformers import BertConfig, BertModel
@@ -126,6 +126,45 @@ def _dp_worker(rank, world, port, b, L, ret):
     dist.all_reduce(gw, op=dist.ReduceOp.SUM)          # gradients are SUMMED across ranks (not averaged)
     ret[rank] = (loss.item(), t_loc.grad.clone(), gw)
     dist.destroy_process_group()
+
+
+def _bucket_worker(rank, world, port, ret):
+    """early all-reduce of one tensor of the flat gradient arena + the remaining slices == one all-reduce of the arena"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ct_clip_b200.trainer import ParamArena, rest_slices
+    g = torch.Generator().manual_seed(5)
+    ps = [(n, torch.nn.Parameter(torch.randn(shp, generator=g))) for n, shp in
+          (("head", (3, 5)), ("big", (7, 9)), ("temperature", ()), ("tail", (11,)))]
+    ar = ParamArena(ps, torch.device("cpu"))
+    ar.g.copy_(torch.randn(ar.numel, generator=torch.Generator().manual_seed(100 + rank)))
+    whole = ar.g.clone()
+    dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+    for name in ("big", "head", "tail"):
+        flat = ar.g.clone()
+        o = ar.offsets[ar.names.index(name)]
+        k = dict(ps)[name].numel()
+        work = dist.all_reduce(flat[o:o + k], op=dist.ReduceOp.SUM, async_op=True)      # what CTCLIP.dp_early_reduce starts
+        for lo, hi in rest_slices(ar.names, ar.offsets, ar.numel, name):
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+        work.wait()
+        # padding elements between tensors may be reduced twice or never: they are zero gradients of no parameter
+        for n, p in ps:
+            oo = ar.offsets[ar.names.index(n)]
+            assert torch.allclose(flat[oo:oo + p.numel()], whole[oo:oo + p.numel()]), (name, n)
+    ret[rank] = True
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_all_reduce_two_ranks_gloo():
+    from ct_clip_b200.trainer import rest_slices
+    assert rest_slices(["a", "b", "c"], [0, 16, 20], 28, "a") == [(16, 28)]
+    assert rest_slices(["a", "b", "c"], [0, 16, 20], 28, "b") == [(0, 16), (20, 28)]
+    assert rest_slices(["a", "b", "c"], [0, 16, 20], 28, "c") == [(0, 20)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bucket_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)
 
 
 def test_data_parallel_global_loss_two_ranks_gloo():

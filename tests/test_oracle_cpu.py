@@ -31,7 +31,7 @@ def _cfg(case):
                           bert=O.BertConfigLite(layers=case["bert_layers"]))
 
 
-@pytest.mark.parametrize("name", ["cfg1", "scramble"])
+@pytest.mark.parametrize("name", ["cfg1", "scramble", "cfg5_small"])
 def test_oracle_matches_golden_reference_outputs(name):
     g = torch.load(GOLD / f"{name}.pt", weights_only=False)
     case, cfg = g["case"], _cfg(g["case"])
