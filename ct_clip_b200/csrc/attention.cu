@@ -1129,7 +1129,6 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 
 // Backward of  x_hat = x / max(||x||, eps) * scale  per (row, head):  given d(x_hat) and raw x:
 //   u = scale * dxh;  dx = (u - xn * (xn . u)) / ||x||  with xn = x/||x||;   dscale[d] += dxh[d] * xn[d]
-template <bool TWO>   // TWO: two (row, head) items per thread and iteration, all four 16-byte loads issued up front
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ dxh, long long ld_dxh,
                                                         const __nv_bfloat16* __restrict__ xraw, long long ld_x,
                                                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ dx,
@@ -1143,9 +1142,12 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
   float sc[8], dsc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) { sc[i] = scale[part * 8 + i]; dsc[i] = 0.f; }
-  const long long total = rows * heads;
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 2);
-  auto process = [&](const uint4& ug, const uint4& ux, long long row, int head) {
+  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); idx < rows * heads;
+       idx += (long long)gridDim.x * (blockDim.x >> 2)) {
+    const long long row = idx / heads;
+    const int head = (int)(idx % heads);
+    const uint4 ug = *reinterpret_cast<const uint4*>(dxh + row * ld_dxh + head * DH + part * 8);
+    const uint4 ux = *reinterpret_cast<const uint4*>(xraw + row * ld_x + head * DH + part * 8);
     const uint32_t* pg = reinterpret_cast<const uint32_t*>(&ug);
     const uint32_t* px = reinterpret_cast<const uint32_t*>(&ux);
     float gg[8], xx[8];
@@ -1174,25 +1176,6 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
     for (int i = 0; i < 4; i++)
       po[i] = pack_bf16x2((gg[2 * i] - xx[2 * i] * dot) * inv, (gg[2 * i + 1] - xx[2 * i + 1] * dot) * inv);
     *reinterpret_cast<uint4*>(dx + row * ld_dx + head * DH + part * 8) = out;
-  };
-  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); idx < total;
-       idx += (TWO ? 2 : 1) * stride) {
-    const long long row0 = idx / heads;
-    const int head0 = (int)(idx % heads);
-    const uint4 ug0 = *reinterpret_cast<const uint4*>(dxh + row0 * ld_dxh + head0 * DH + part * 8);
-    const uint4 ux0 = *reinterpret_cast<const uint4*>(xraw + row0 * ld_x + head0 * DH + part * 8);
-    if (TWO) {
-      const long long idx1 = idx + stride;
-      const bool two = idx1 < total;       // quad-uniform (and warp-uniform whenever total % 8 == 0)
-      const long long row1 = two ? idx1 / heads : row0;
-      const int head1 = two ? (int)(idx1 % heads) : head0;
-      const uint4 ug1 = *reinterpret_cast<const uint4*>(dxh + row1 * ld_dxh + head1 * DH + part * 8);
-      const uint4 ux1 = *reinterpret_cast<const uint4*>(xraw + row1 * ld_x + head1 * DH + part * 8);
-      process(ug0, ux0, row0, head0);
-      if (two) process(ug1, ux1, row1, head1);
-    } else {
-      process(ug0, ux0, row0, head0);
-    }
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) atomicAdd(&sds[part * 8 + i], dsc[i]);
@@ -1345,15 +1328,9 @@ extern "C" int ctclip_l2norm_bwd(const void* dxh, int64_t ld_dxh, const void* xr
   long long ctas = (rows * heads + 63) / 64;
   const long long cap = (long long)num_sms() * 8;
   if (ctas > cap) ctas = cap;
-  const int two = getenv("CTCLIP_L2NORM_V2") ? atoi(getenv("CTCLIP_L2NORM_V2")) : 0;   // opt-in until measured on a GPU
-  if (two && (rows * heads) % 8 == 0)
-    l2norm_bwd_kernel<true><<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,
-                                                          reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,
-                                                          reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, rows, heads);
-  else
-    l2norm_bwd_kernel<false><<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,
-                                                           reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,
-                                                           reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, rows, heads);
+  l2norm_bwd_kernel<<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,
+                                                  reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,
+                                                  reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, rows, heads);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A/B of two opt-in kernel variants at configs[1] size on one GPU: patchify v2 vs v3 (CTCLIP_PATCHIFY_V3) and l2norm_bwd
-one vs two items per thread (CTCLIP_L2NORM_V2). Checks that the variants agree and prints median times."""
+"""A/B of the patchify kernels at configs[1] size on one GPU: v2 vs v3 (CTCLIP_PATCHIFY_V3=0/1). Checks that they agree
+and prints median times."""
 import os
 import sys
 from pathlib import Path
@@ -54,26 +54,3 @@ ops.patchify(volf, o1, B=1, Cc=1, F=Fr, H=H, W=W, pt=10, p1=20, p2=20)
 print("patchify fp32 input max diff =", (o0.float() - o1.float()).abs().max().item())
 del vol, outs, out
 
-# ---- l2norm_bwd (k-projection call of a layer: strided [M, 512] buffers, in place)
-Mr, heads, dh = 110592, 8, 32
-I = heads * dh
-x = torch.randn(Mr, 2 * I, device=dev).to(torch.bfloat16)
-gsrc = torch.randn(Mr, 2 * I, device=dev).to(torch.bfloat16)
-scale = 1 + 0.1 * torch.randn(dh, device=dev)
-res = {}
-for v in ("0", "1"):
-    os.environ["CTCLIP_L2NORM_V2"] = v
-    gbuf = gsrc.clone()
-    dsc = torch.zeros(dh, device=dev)
-
-    def fn():
-        ops.l2norm_bwd(gbuf, 2 * I, x, 2 * I, scale, gbuf, 2 * I, dsc, Mr, heads)
-    gbuf.copy_(gsrc)
-    dsc.zero_()
-    fn()
-    torch.cuda.synchronize()
-    res[v] = (gbuf.clone(), dsc.clone())
-    t = timeit(fn)
-    print(f"l2norm_bwd two={v}: {t:8.1f} us  ({Mr * I * 6 / t / 1e3:.0f} GB/s algorithmic)", flush=True)
-print("l2norm_bwd dx equal:", torch.equal(res["0"][0], res["1"][0]), " dscale rel diff:",
-      ((res["0"][1] - res["1"][1]).abs().max() / res["0"][1].abs().max()).item())
