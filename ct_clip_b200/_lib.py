@@ -94,6 +94,7 @@ SIGNATURES = {
     "ctclip_peg_bwd_weight": [C.POINTER(PegArgs), P],
     "ctclip_attn_fwd": [C.POINTER(AttnArgs), P],
     "ctclip_attn_bwd": [C.POINTER(AttnArgs), P],
+    "ctclip_attn_fwd_tc": [C.POINTER(AttnArgs), P],
     "ctclip_l2norm_bwd": [P, I64, P, I64, P, P, I64, P, I64, I32, I32, P],
     "ctclip_sgemm_f32": [C.POINTER(SgemmArgs), P],
     "ctclip_colsum": [P, I32, I64, I64, I32, P, P],

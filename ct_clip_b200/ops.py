@@ -162,6 +162,12 @@ def attn_fwd(q, k, v, o, lse, **kw):
          work=("F", _attn_flops(kw)))
 
 
+def attn_fwd_tc(q, k, v, o, lse, **kw):
+    """EXPERIMENTAL tcgen05 / TMEM forward (csrc/attention_tc.cu): not part of the default path."""
+    call("ctclip_attn_fwd_tc", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream(), tag=f"tc n{kw['n']}",
+         work=("F", _attn_flops(kw)))
+
+
 def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, ds_scratch=None, **kw):
     a = _attn_args(q, k, v, o, lse, **kw)
     a.ds_scratch = _ptr(ds_scratch)

@@ -220,6 +220,9 @@ typedef struct {
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
+/* EXPERIMENTAL (not used by the default path, not yet run on hardware -- see csrc/attention_tc.cu): the same forward
+ * with tcgen05.mma / TMEM for both contractions; dim_head 32, n % 64 == 0, n <= 768, natural-layout bias, no key mask. */
+int ctclip_attn_fwd_tc(const ctclip_attn_args* args, void* stream);
 
 /* Backward of x_hat = x/max(||x||,1e-12)*scale per (row, head) (attention.py:152-154):
  * dxh, xraw, dx: bf16 [rows, heads*32]; dscale[32] accumulated. */
