@@ -155,10 +155,17 @@ class CTCLIP(nn.Module):
         self.mark_weights_dirty()
         return super().load_state_dict(sd, *args, **kwargs)
 
-    def load(self, path):
+    def load(self, path, tolerant=True):
+        """ct_clip.py:593-597 (torch.load + strict load_state_dict). tolerant=True first normalises wrapper prefixes, the
+        position_ids buffer of old transformers releases, absent *_extra copies and foreign GenerateCT keys
+        (ct_clip_b200.checkpoint.tolerant_state_dict); the load itself stays strict."""
         path = Path(path)
         assert path.exists()
-        self.load_state_dict(torch.load(str(path), map_location="cpu"))
+        sd = torch.load(str(path), map_location="cpu")
+        if tolerant:
+            from .checkpoint import tolerant_state_dict
+            sd, self.last_load_report = tolerant_state_dict(sd, super().state_dict())
+        self.load_state_dict(sd)
 
     def mark_weights_dirty(self):
         self._wv_version = None

@@ -101,7 +101,7 @@ class CTClipTrainer(nn.Module):
                  train_meta_file="meta_data.csv", valid_meta_file="meta_data.csv", labels="labels.csv", tokenizer=None,
                  lr=1.25e-6, wd=0., max_grad_norm=0.5, save_results_every=1, save_model_every=1,
                  results_folder='./ctclip/', num_workers=8, accelerate_kwargs: dict = dict(),
-                 train_dataset=None, valid_dataset=None, text_max_length=512):
+                 train_dataset=None, valid_dataset=None, text_max_length=512, async_checkpoints=False):
         super().__init__()
         assert wd == 0., "the reference trains with wd=0 (Adam, optimizer.py:23-24); AdamW is not part of this build"
         if not torch.cuda.is_available():
@@ -118,6 +118,7 @@ class CTClipTrainer(nn.Module):
         self.num_train_steps, self.batch_size = num_train_steps, batch_size
         self.max_grad_norm, self.lr = max_grad_norm, lr
         self.save_model_every, self.save_results_every = save_model_every, save_results_every
+        self.async_checkpoints = async_checkpoints
 
         # ---- data (scripts/data.py output contract: (1,F,H,W) fp32 in [-1,1] or int16 HU + report text / token ids)
         if train_dataset is None:
@@ -212,6 +213,10 @@ class CTClipTrainer(nn.Module):
                 work.wait()
             else:
                 dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)
+        ev = getattr(self, "_ckpt_event", None)
+        if ev is not None:       # an asynchronous checkpoint copy may still be reading the parameters
+            torch.cuda.current_stream().wait_event(ev)
+            self._ckpt_event = None
         self.arena.adam_step(lr=self.lr, max_norm=self.max_grad_norm)
         self.CTClip.mark_weights_dirty()
         return loss
@@ -226,16 +231,39 @@ class CTClipTrainer(nn.Module):
         logs['loss'] = loss.item()                      # device->host sync, as the reference (:258)
         self.print(f"{steps}: loss: {logs['loss']}")
         if self.is_main and self.save_model_every and not (steps % self.save_model_every):
+            # CTCLIPTrainer.py:331-337 writes 1.75 GB synchronously here. async_checkpoints=True (opt-in, not yet exercised
+            # on a GPU): copy to pinned memory on a side stream + torch.save on a background thread
             model_path = str(self.results_folder / f'CTClip.{steps}.pt')
-            torch.save(self.CTClip.state_dict(), model_path)
+            if self.async_checkpoints:
+                self._save_async(model_path)
+            else:
+                torch.save(self.CTClip.state_dict(), model_path)
             self.print(f'{steps}: saving model to {str(self.results_folder)}')
         self.steps += 1
         return logs
+
+    def _ckpt_writer(self):
+        if getattr(self, "_writer", None) is None:
+            from .checkpoint import AsyncCheckpointWriter
+            self._writer = AsyncCheckpointWriter()
+        return self._writer
+
+    def _save_async(self, path):
+        """Parameters are views into the arena: the next Adam step must not overwrite them while the device-to-host copy is in
+        flight (step_on_batch waits for the writer's copy event before the optimiser kernels); buffers that the next FORWARD
+        mutates (code-book EMA) are cloned on the compute stream first."""
+        live = set(self.arena.names)
+        sd = {k: (v if k in live else v.clone()) for k, v in self.CTClip.state_dict().items()}
+        w = self._ckpt_writer()
+        w.save(sd, path)
+        self._ckpt_event = w.copy_event
 
     def train(self, log_fn=lambda logs: None):
         while self.steps < self.num_train_steps:
             logs = self.train_step()
             log_fn(logs)
+        if getattr(self, "_writer", None) is not None:
+            self._writer.wait()          # the last checkpoint is on disk before train() returns
         self.print('training complete')
 
 

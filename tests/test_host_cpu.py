@@ -186,3 +186,43 @@ def test_data_parallel_global_loss_two_ranks_gloo():
         assert abs(l_r - loss.item()) < 1e-6
         assert torch.allclose(dt_r, T.grad[r * b:(r + 1) * b], atol=1e-6)
         assert torch.allclose(gw_r, W.grad, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_tolerant_state_dict_and_async_writer(tmp_path):
+    """SURVEY 8(f) row 4: checkpoints written by other wrappers / library versions load strictly after normalisation;
+    the asynchronous writer produces a loadable file (CPU tensors here; the CUDA path adds pinned buffers + a side stream)."""
+    from transformers import BertConfig, BertModel
+
+    from ct_clip_b200 import CTCLIP, CTViT
+    from ct_clip_b200.checkpoint import AsyncCheckpointWriter, tolerant_state_dict
+    vit = CTViT(dim=128, codebook_size=64, image_size=16, patch_size=8, temporal_patch_size=2, spatial_depth=1, temporal_depth=1,
+                dim_head=32, heads=4)
+    bert = BertModel(BertConfig(num_hidden_layers=1, hidden_size=64, num_attention_heads=2, intermediate_size=128))
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=64, dim_image=4 * 128, dim_latent=32)
+    ref = {k: v.clone() for k, v in clip.state_dict().items()}
+    # a checkpoint as accelerate(unwrap=False) + transformers 4.30 + a GenerateCT-era CTViT would have written it
+    old = {"module." + k: v for k, v in ref.items() if not k.startswith(("to_text_latent_extra", "to_visual_latent_extra"))}
+    old["module.text_transformer.embeddings.position_ids"] = torch.arange(512)[None]
+    old["module.visual_transformer.discr.layers.0.weight"] = torch.zeros(3, 3)
+    clean, report = tolerant_state_dict(old, clip.state_dict())
+    assert set(clean) == set(ref) and all(torch.equal(clean[k], ref[k]) for k in ref if not k.endswith("_extra.weight"))
+    assert "stripped 'module.'" in report["renamed"] and len(report["dropped"]) == 2 and len(report["filled"]) == 2
+    clip.load_state_dict(clean, strict=True)
+    # a genuinely different architecture still fails loudly
+    bad = dict(ref)
+    bad["visual_transformer.to_patch_emb.2.weight"] = torch.zeros(7, 7)
+    with pytest.raises(RuntimeError):
+        clip.load_state_dict(tolerant_state_dict(bad, clip.state_dict())[0], strict=True)
+    # asynchronous writer + CTCLIP.load round trip
+    w = AsyncCheckpointWriter()
+    w.save(clip.state_dict(), tmp_path / "a.pt")
+    w.save({k: v + 1 if v.is_floating_point() else v for k, v in clip.state_dict().items()}, tmp_path / "b.pt")   # joins the first
+    w.wait()
+    a, b = torch.load(tmp_path / "a.pt"), torch.load(tmp_path / "b.pt")
+    assert all(torch.equal(a[k], ref[k]) for k in ref)
+    k0 = "to_text_latent.weight"
+    assert torch.equal(b[k0], ref[k0] + 1) and not (tmp_path / "b.pt.tmp").exists()
+    torch.save({"module." + k: v for k, v in ref.items()}, tmp_path / "wrapped.pt")
+    clip.load(tmp_path / "wrapped.pt")
+    assert clip.last_load_report["renamed"] == ["stripped 'module.'"]
