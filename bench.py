@@ -111,12 +111,18 @@ def stage_table(rec, peaks):
     agg = {}
     for name, tag, work, e0, e1 in rec:
         key = (name.replace("ctclip_", ""), tag or "", work[0] if work else "")
-        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
         a[0] += 1
         a[1] += e0.elapsed_time(e1)
         a[2] += work[1] if work else 0.0
+        a[3] += work[2] if work and len(work) > 2 else 0.0
     rows = []
-    for (name, tag, kind), (n, t_ms, w) in agg.items():
+    for (name, tag, kind), (n, t_ms, w, w2) in agg.items():
+        if kind == "FB":   # GEMMs carry both: rate the launch against whichever roofline bounds it (K = 512 residual
+            # epilogues move 8 bytes per output and are HBM-bound, the wide-K shapes are tensor-bound)
+            kind = "B" if w2 / (peaks["hbm"] * 1e9) > w / (peaks["tf_sus"] * 1e12) else "F"
+            if kind == "B":
+                w = w2
         if kind == "B":
             ach, unit, peak, bound = w / (t_ms * 1e-3) / 1e9, "GB/s", peaks["hbm"], "hbm"
         elif kind == "F":

@@ -53,13 +53,23 @@ def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, 
     a.colsum = _ptr(colsum)
     if GEMM_TIMER is None:
         call("ctclip_gemm_bf16", C.byref(a), _stream(), tag=f"{M}x{N}x{K} a{a_major}b{b_major} epi{epilogue} s{splits}",
-             work=("F", 2.0 * M * N * K))
+             work=("FB", 2.0 * M * N * K, _gemm_bytes(M, N, K, epilogue, norm_cols, C_out is not None)))
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         call("ctclip_gemm_bf16", C.byref(a), _stream())
         e1.record()
         GEMM_TIMER.append((e0, e1, 2.0 * M * N * K, (M, N, K, a_major, b_major, epilogue, splits)))
+
+
+def _gemm_bytes(M, N, K, epilogue, norm_cols, has_c):
+    """Algorithmic HBM bytes of one GEMM launch: both bf16 operands once + what the epilogue reads / writes."""
+    ops_b = 2.0 * K * (M + N)
+    mn = float(M) * N
+    out = {EPI_BF16: 2 * mn, EPI_F32: 4 * mn, EPI_RESID_F32: 8 * mn, EPI_GEGLU: (2 * mn if has_c else 0) + mn,
+           EPI_ATOMIC_F32: 4 * mn, EPI_ARGMAX: 4.0 * M, EPI_L2NORM: (2 * mn if has_c else 0) + 2.0 * M * norm_cols,
+           EPI_BIAS_GELU: 4 * mn, EPI_GEGLU_BWD: 8 * mn}.get(epilogue, 2 * mn)
+    return ops_b + out
 
 
 def wgrad_splits(k_red: int, out_tiles: int, sms: int = 148) -> int:

@@ -226,3 +226,27 @@ def test_tolerant_state_dict_and_async_writer(tmp_path):
     torch.save({"module." + k: v for k, v in ref.items()}, tmp_path / "wrapped.pt")
     clip.load(tmp_path / "wrapped.pt")
     assert clip.last_load_report["renamed"] == ["stripped 'module.'"]
+
+
+def test_bench_stage_table_rates_each_stage_against_its_roofline():
+    """bench.stage_table: HBM stages vs the copy bandwidth, tensor stages vs the sustained GEMM rate, GEMMs against whichever
+    of the two bounds the launch (fake events: no GPU needed)."""
+    import bench
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+    peaks = dict(hbm=6000.0, tf_sus=1500.0)
+    M = 110592
+    rec = [("ctclip_ln_fwd", "D512", ("B", 6.0e8), Ev(0.0), Ev(0.2)),                       # 600 MB in 0.2 ms = 3000 GB/s
+           ("ctclip_gemm_bf16", "big-K", ("FB", 2.0 * M * 512 * 2816, 1.0e9), Ev(0.0), Ev(0.25)),
+           ("ctclip_gemm_bf16", "resid", ("FB", 2.0 * M * 512 * 256, 5.1e8), Ev(0.0), Ev(0.1)),
+           ("ctclip_cpb_expand", None, None, Ev(0.0), Ev(0.01))]
+    rows = {r[0]: r for r in bench.stage_table(rec, peaks)}
+    assert rows["ln_fwd [D512]"][3] == "hbm" and abs(rows["ln_fwd [D512]"][6] - 0.5) < 1e-6
+    assert rows["gemm_bf16 [big-K]"][3] == "tensor" and rows["gemm_bf16 [big-K]"][5] == "TFLOP/s"
+    assert rows["gemm_bf16 [resid]"][3] == "hbm" and abs(rows["gemm_bf16 [resid]"][4] - 5100.0) < 1e-6
+    assert rows["cpb_expand"][3] == "latency"
