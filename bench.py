@@ -258,16 +258,19 @@ def run_b200(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     # ---- per-stage pass (untimed for the headline): CUDA events around every C-ABI call of ONE extra step
+    # EVERY rank runs the extra step (it contains the embedding all-gather and the gradient all-reduce: a rank-0-only step would
+    # dead-lock at N > 1); only rank 0 records events.
     stage_rows = None
-    if rank == 0 and not args.no_stages:
-        rec = []
+    if not args.no_stages:
+        rec = [] if rank == 0 else None
         _lib.STAGE_TIMER = rec
         trainer.step_on_batch(*dev[0])
-        torch.cuda.synchronize()
+        barrier()
         _lib.STAGE_TIMER = None
-        stage_rows = stage_table(rec, load_peaks())
-        if os.environ.get("CTCLIP_BENCH_STAGE_TABLE"):
-            write_stage_table(os.environ["CTCLIP_BENCH_STAGE_TABLE"], stage_rows, ms / args.steps)
+        if rank == 0:
+            stage_rows = stage_table(rec, load_peaks())
+            if os.environ.get("CTCLIP_BENCH_STAGE_TABLE"):
+                write_stage_table(os.environ["CTCLIP_BENCH_STAGE_TABLE"], stage_rows, ms / args.steps)
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
