@@ -61,7 +61,8 @@ class AttnArgs(C.Structure):
                 ("seq_outer_stride", I64), ("tok_stride", I64), ("scale", F32),
                 ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
                 ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P),
-                ("bias_frag", P), ("bias_t_frag", P), ("ds_scratch", P)]
+                ("bias_frag", P), ("bias_t_frag", P), ("ds_scratch", P),
+                ("cpb_table", P), ("grid_h", I32), ("grid_w", I32), ("qk_bound", P), ("dcpb_table", P)]
 
 
 class SgemmArgs(C.Structure):
@@ -94,7 +95,8 @@ SIGNATURES = {
     "ctclip_peg_bwd_weight": [C.POINTER(PegArgs), P],
     "ctclip_attn_fwd": [C.POINTER(AttnArgs), P],
     "ctclip_attn_bwd": [C.POINTER(AttnArgs), P],
-    "ctclip_attn_fwd_tc": [C.POINTER(AttnArgs), P],
+    "ctclip_attn_tc_supported": [I32, I32, I32, I32],
+    "ctclip_qk_bound": [P, P, I32, P, P],
     "ctclip_l2norm_bwd": [P, I64, P, I64, P, P, I64, P, I64, I32, I32, P],
     "ctclip_sgemm_f32": [C.POINTER(SgemmArgs), P],
     "ctclip_colsum": [P, I32, I64, I64, I32, P, P],

@@ -1187,6 +1187,10 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
 
 using namespace ctb;
 
+// tcgen05 / TMEM path (attention_tc.cu), selected by args->cpb_table
+int ctb_attn_fwd_tc(const ctclip_attn_args* a, cudaStream_t stream);
+int ctb_attn_bwd_tc(const ctclip_attn_args* a, cudaStream_t stream);
+
 static int attn_check(const ctclip_attn_args* a, const char* who) {
   CTB_CHECK_ARG(a != nullptr, "%s: null args", who);
   CTB_CHECK_ARG(a->dim_head == 32 || a->dim_head == 64, "%s: dim_head must be 32 or 64 (got %d)", who, a->dim_head);
@@ -1255,6 +1259,7 @@ extern "C" int ctclip_attn_fwd(const ctclip_attn_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = attn_check(a, "attn_fwd")) return rc;
   CTB_CHECK_ARG(a->o != nullptr && a->ldo % 8 == 0, "attn_fwd: bad o");
+  if (a->cpb_table != nullptr) return ctb_attn_fwd_tc(a, stream);
   if (attn_is_short(a)) {
     const size_t smem = (size_t)SH_FWD_WARPS * 2 * 3 * SH_TILE * 2;
     CTB_CUDA(cudaFuncSetAttribute(attn_short_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1285,6 +1290,7 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_args* a, void* stream_) {
       attn_delta_kernel<64><<<(int)((items + 31) / 32), 256, 0, stream>>>(o, d_o, a->ldo, a->delta, rows, a->heads);
     CTB_LAUNCH_CHECK();
   }
+  if (a->cpb_table != nullptr) return ctb_attn_bwd_tc(a, stream);
   if (attn_is_short(a) && a->dbias == nullptr) {
     const size_t smem = (size_t)SH_BWD_WARPS * (2 * 4 * SH_TILE + 128) * 2;
     CTB_CUDA(cudaFuncSetAttribute(attn_short_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,33 +1,27 @@
-// EXPERIMENTAL -- tcgen05 / TMEM attention forward (dim_head 32, no key mask, n % 64 == 0).
+// Spatial attention core on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), forward and backward.
+// Replaces attention.py:152-178 of the reference for the spatial stack of CTViT (ctvit.py:291-297):
+//     sim = q_hat k_hat^T * scale + cpb_bias[h, i, j];  attn = softmax(sim);  out = attn v       (+ its autograd backward)
+// where q_hat / k_hat are the l2-normalised, per-channel-scaled projections, dim_head = 32, the tokens of one sequence are
+// the H x W grid of one frame (n = H*W = 576 at configs[1]) and cpb_bias[h,i,j] = table[rel(i,j), h] is the continuous
+// position bias (attention.py:245-282) -- (2H-1)(2W-1) distinct values per head, kept as a TABLE in shared memory
+// instead of the 5.3 MB [heads,n,n] tensor the mma.sync kernels (attention.cu) stream from L2.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent: it COMPILES for sm_100a but has NOT run on
-// hardware yet. It is not called by any default path (the product uses the mma.sync kernels of attention.cu); the only
-// caller is tests/test_attention_tc_gpu.py, which is skipped unless CTCLIP_EXPERIMENTAL=1. Round 2 starts by bringing it
-// up. Every tcgen05 / mbarrier / descriptor idiom below is the one gemm_tcgen05.cu uses and
-// has validated on B200; what is new here is listed under "unverified" at the end of this comment.
+// Why the cosine attention permits a FIXED softmax reference (no online max, no rescaling of O):
+//   |q_hat . k_hat| <= max_d |q_scale_d k_scale_d| =: qk_bound  (both are unit vectors times a per-channel scale), so every
+//   logit of head h is <= M_h := scale*qk_bound + max_r table[r,h]. exp(logit - M_h) can neither overflow nor -- the
+//   logits span at most 2*scale*qk_bound + range(table) ~ 25 nats -- underflow in fp32/bf16, so P = exp2(x - M_h) is
+//   formed in ONE pass over the scores, O accumulates in TMEM over all key chunks, and lse = M_h + log2(sum P).
 //
-// Replaces (once validated) attention.py:156-178 for the spatial stack:  out = softmax(q_hat k_hat^T * scale + bias) v.
-//
-// Structure (correctness-first, fully serialised; the overlap comes later):
-//   CTA = one (sequence, head); 160 threads: warps 0-3 = softmax (thread r owns query row r of the current 128-row tile =
-//   TMEM lane r), warp 4 = TMEM owner + single-thread MMA issuer.
-//   Shared memory (SWIZZLE_128B K-major tiles, exactly the layout TMA writes for the GEMM kernel, produced here with
-//   st.shared: 16-byte chunk c of row r lands at chunk c ^ (r & 7)):
-//     sQ  [128 rows][128 B]   query tile, d in bytes 0..63 of a row (bytes 64..127 never read: only 2 of 4 UMMA_K steps issued)
-//     sK  [n rows][128 B]     keys, same row format                                      (B operand of S = Q K^T)
-//     sVt [n/64][32 rows = d][128 B = 64 keys]   V transposed per 64-key block              (B operand of O = P V)
-//     sP  [NCH/64][128 rows][128 B = 64 keys]    probabilities of the current key chunk     (A operand of O = P V)
-//   TMEM: columns [0, NCH) = S chunk (128 x NCH fp32), [NCH, NCH+32) = O chunk (128 x 32 fp32); 256 columns allocated.
-//   Per query tile and key chunk (NCH = 192 keys when 192 | n, else 128 or 64):
-//     MMA:      S = Q K_chunk^T                      (tcgen05.mma M=128, N=NCH, 2 x K=16)   -> commit
-//     softmax:  tcgen05.ld S, x = S*scale*log2e + bias*log2e, online max / sum, P = exp2(x - m) -> bf16 -> sP
-//     MMA:      Oc = P V_chunk                       (M=128, N=32, NCH/16 x K=16, fresh accumulator) -> commit
-//     softmax:  tcgen05.ld Oc, o = o*alpha + Oc      (the running output lives in 32 registers per row, FA2-style)
-//   then o / l -> bf16, lse = m + log2(l) (log2 domain, same convention as attention.cu).
-//
-// Unverified on hardware (bring-up checklist): (1) the manual SWIZZLE_128B placement of sQ / sK / sVt / sP against the
-// UMMA descriptors; (2) N = 192 and N = 32 instruction descriptors; (3) generic-proxy writes -> fence.proxy.async ->
-// tcgen05.mma reads; (4) the S / O TMEM column split and the lane mapping of tcgen05.ld for warps 0-3.
+// Forward  (attn_tc_fwd_kernel): CTA = one (sequence, head); 2 CTAs / SM (103 KB smem, 256 TMEM columns each).
+//   warp 8   TMA producer: K, V of the item (SWIZZLE_64B tiles, 64-byte rows = the head's slice of a token row), Q tiles ring
+//   warp 9   MMA issuer (one thread): S = Q_tile K_chunk^T (SS, M=128, N=NCH, K=32) into a 2-stage TMEM ring; after the
+//            softmax warps have overwritten S with P (bf16, tcgen05.st): O += P V_chunk (TS: A from TMEM, V MN-major)
+//   warps 0-7 softmax: warp w owns TMEM lanes 32*(w&3).. (= query rows) and the column half (w>>2) of the chunk:
+//            tcgen05.ld -> x = s*scale*log2e + table'[rel] -> ex2 -> row sum, bf16 pack -> tcgen05.st over its own S columns.
+//   The bias look-up is ONE conflict-free LDS per score: table rows are padded to STR = W + 32 floats, so that the 32
+//   consecutive queries of a warp (which may wrap to the next grid row) hit 32 different banks, and the key offset of a
+//   column is a compile-time immediate because every warp's column range covers whole grid rows (NCH/2 = 2W or W).
+// Backward (attn_tc_bwd_kernel): see the comment above that kernel.
 #include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -35,238 +29,769 @@
 
 namespace ctb {
 
-constexpr int TCA_THREADS = 160;
-constexpr int TCA_DH = 32;
-constexpr float kTcaLog2e = 1.4426950408889634f;
+constexpr float kTcLog2e = 1.4426950408889634f;
+constexpr uint32_t SW64 = 4;   // cute::UMMA::LayoutType::SWIZZLE_64B
 
-struct TcaGeom {
-  int n, heads, seq_inner;
-  long long seq_outer_stride, tok_stride;
-  __device__ __forceinline__ long long row(int seq, int i) const {
-    return (long long)(seq / seq_inner) * seq_outer_stride + (seq % seq_inner) + (long long)i * tok_stride;
-  }
-};
-
-__device__ __forceinline__ float tca_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// byte offset of 16-byte chunk `c` of row `r` inside a [rows][128 B] SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t tca_swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+struct TcFwdParams {
+  int n, heads, H, num_seqs;
+  const float* table;      // [(2H-1)(2W-1), heads] fp32 (may be null: no bias)
+  const float* qk_bound;   // device scalar: max_d |q_scale_d * k_scale_d| (null: 1)
+  float scale;
+  __nv_bfloat16* o;
+  long long ldo;
+  float* lse;
+};
 
-__global__ void __launch_bounds__(TCA_THREADS, 1) attn_tc_fwd_kernel(ctclip_attn_args a, int nch) {
-  extern __shared__ uint8_t tca_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tca_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const TcaGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
-  const int n = a.n;
-  uint8_t* sQ = smem;                                   // 16 KB
-  uint8_t* sK = sQ + 128 * 128;                         // n * 128 B
-  uint8_t* sVt = sK + (size_t)n * 128;                  // (n / 64) * 4 KB
-  uint8_t* sP = sVt + (size_t)(n / 64) * 4096;          // (nch / 64) * 16 KB
-  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(sP + (size_t)(nch / 64) * 16384);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_mma + 1);
+template <int W>
+struct TcGeom {
+  static constexpr int STR = W + 32;   // padded table row: >= 2W-1 and == W (mod 32)
+  static_assert(W == 24 || W == 32, "supported grid widths");
+  __host__ __device__ static constexpr int off(int cc) { return (cc / W) * STR + (cc % W); }   // key cc of a row-aligned range
+};
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int item = blockIdx.x;
-  const int head = item % a.heads, seq = item / a.heads;
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
-  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
-  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
-  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.o);
-
-  if (tid == 128) {
-    mbar_init(bar_mma, 1);
-    fence_barrier_init();
+// table'[dy][dx] = table[...] * log2e - M_h for one head, rows padded to STR; returns M_h (log2 domain) to every thread.
+// Called by ALL threads of the CTA (contains __syncthreads).
+template <int W>
+__device__ __forceinline__ float tc_load_table(float* sTab, float* sRed, const float* table, const float* qk_bound, float scale, int H,
+                                               int heads, int head, int tid, int nthreads) {
+  constexpr int STR = TcGeom<W>::STR;
+  const int elems = (2 * H - 1) * STR;
+  float m = -INFINITY;
+  for (int e = tid; e < elems; e += nthreads) {
+    const int dyi = e / STR, dxi = e % STR;
+    float v = 0.f;
+    if (dxi < 2 * W - 1) {
+      v = (table != nullptr) ? __ldg(table + ((long long)dyi * (2 * W - 1) + dxi) * heads + head) * kTcLog2e : 0.f;
+      m = fmaxf(m, v);
+    }
+    sTab[e] = v;
   }
-  if (warp == 4) {
-    tmem_alloc(tmem_holder, 256);
+  m = warp_max(m);
+  if ((tid & 31) == 0) sRed[tid >> 5] = m;
+  __syncthreads();
+  float mh = -INFINITY;
+  for (int w = 0; w < nthreads / 32; w++) mh = fmaxf(mh, sRed[w]);
+  const float qkb = (qk_bound != nullptr) ? __ldg(qk_bound) : 1.0f;
+  mh += scale * kTcLog2e * qkb;
+  return mh;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------
+template <int NCH, int W>
+__global__ void __launch_bounds__(320, (NCH == 96) ? 2 : 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const TcFwdParams p) {
+  constexpr int HALF = NCH / 2;
+  constexpr int STR = TcGeom<W>::STR;
+  constexpr int OCOL = 2 * NCH;
+  static_assert(HALF % W == 0 && HALF % 16 == 0, "a softmax warp's column range must cover whole grid rows");
+  extern __shared__ uint8_t tc_smem_raw[];
+  // (offset arithmetic on the __shared__ array keeps the address space known to the compiler: LDS / STS, not generic LD / ST)
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  const int n = p.n;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + (size_t)n * 64;
+  uint8_t* sQ = sV + (size_t)n * 64;                       // 2 x [128][64 B]
+  float* sTab = reinterpret_cast<float*>(sQ + 2 * 8192);
+  const int tab_elems = ((2 * p.H - 1) * STR + 31) & ~31;
+  float* sL = sTab + tab_elems;                            // [2 tile parities][2 halves][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 512);
+  uint64_t* k_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* q_full = bars + 2;    // [2]
+  uint64_t* q_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;    // [2]
+  uint64_t* p_full = bars + 8;    // [2]
+  uint64_t* o_full = bars + 10;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 12);
+  float* sRed = reinterpret_cast<float*>(holder + 2);      // [10]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.x;
+  const int head = item % p.heads, seq = item / p.heads;
+  const int NT = (n + 127) / 128, NC = n / NCH, NB = NT * NC;
+  const long long row0 = (long long)seq * n;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tq);
+    tma_prefetch_desc(&tk);
+    tma_prefetch_desc(&tv);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    // the loads of this item do not depend on anything else: start them before the table set-up
+    mbar_arrive_expect_tx(k_full, (uint32_t)n * 64);
+    for (int r = 0; r < n; r += 64) tma_load_2d(sK + (size_t)r * 64, &tk, k_full, head * 32, (int)(row0 + r));
+    mbar_arrive_expect_tx(&q_full[0], 8192);
+    tma_load_2d(sQ, &tq, &q_full[0], head * 32, (int)row0);
+    mbar_arrive_expect_tx(v_full, (uint32_t)n * 64);
+    for (int r = 0; r < n; r += 64) tma_load_2d(sV + (size_t)r * 64, &tv, v_full, head * 32, (int)(row0 + r));
+  }
+  if (warp == 9) {
+    tmem_alloc(holder, 256);
     tmem_relinquish();
   }
-  // ---- K and V^T tiles of this (sequence, head): all 160 threads
-  for (int idx = tid; idx < n * 4; idx += TCA_THREADS) {
-    const int r = idx >> 2, c = idx & 3;
-    const uint4 kv = *reinterpret_cast<const uint4*>(k + g.row(seq, r) * a.ldk + head * TCA_DH + c * 8);
-    *reinterpret_cast<uint4*>(sK + tca_swz(r, c)) = kv;
-    const uint4 vv = *reinterpret_cast<const uint4*>(v + g.row(seq, r) * a.ldv + head * TCA_DH + c * 8);
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-    uint8_t* blk = sVt + (size_t)(r >> 6) * 4096;          // 64-key block
-    const int kc = (r & 63) >> 3, kb = (r & 7) * 2;        // 16-byte chunk and byte inside it of key r within a d-row
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      const int d = c * 8 + e;
-      *reinterpret_cast<__nv_bfloat16*>(blk + tca_swz(d, kc) + kb) = ve[e];
-    }
-  }
-  fence_proxy_async_smem();
+  const float sc2 = p.scale * kTcLog2e;
   tc_fence_before();
-  __syncthreads();
+  const float Mh = tc_load_table<W>(sTab, sRed, p.table, p.qk_bound, p.scale, p.H, p.heads, head, tid, 320);   // contains __syncthreads
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sVt_u = smem_u32(sVt), sP_u = smem_u32(sP);
-  const uint32_t idesc_qk = umma_idesc(1, 0, 0, 128, nch);
-  const uint32_t idesc_pv = umma_idesc(1, 0, 0, 128, 32);
-  const float sc2 = a.scale * kTcaLog2e;
-  const int n_chunks = n / nch;
-  const int kblk = nch / 64;      // 64-key blocks per chunk
-  uint32_t ph = 0;                // parity of bar_mma
+  const uint32_t tmem_base = *holder;
 
-  for (int q0 = 0; q0 < n; q0 += 128) {
-    const int row_i = q0 + tid;    // query row of this softmax thread
-    const bool row_ok = tid < 128 && row_i < n;
-    // ---- Q tile (softmax threads: one 64-byte row each, zero beyond n)
-    if (tid < 128) {
+  if (warp < 8) {
+    // ===================== softmax warps =====================
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int e = tid; e < (2 * p.H - 1) * STR; e += 256) sTab[e] -= Mh;   // fold the softmax reference into the table
+    named_bar_sync(1, 256);
+    for (int t = 0; t < NT; t++) {
+      const int i = t * 128 + r;
+      const bool warp_valid = (t * 128 + q * 32) < n;      // n % 32 == 0: a warp is valid or idle as a whole
+      const int ic = i < n ? i : n - 1;
+      const int qi = (ic / W + p.H - 1) * STR + (ic % W) + (W - 1);
+      float l0 = 0.f, l1 = 0.f;
+      for (int c = 0; c < NC; c++) {
+        const int b = t * NC + c, st = b & 1;
+        mbar_wait_tag(&s_full[st], (b >> 1) & 1, 10 + st);
+        if (warp_valid) {
+          tc_fence_after();
+          const uint32_t scol = lane_base + st * NCH + hf * HALF;
+          uint32_t sv[HALF];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        uint4 qv = make_uint4(0, 0, 0, 0);
-        if (row_ok) qv = *reinterpret_cast<const uint4*>(q + g.row(seq, row_i) * a.ldq + head * TCA_DH + c * 8);
-        *reinterpret_cast<uint4*>(sQ + tca_swz(tid, c)) = qv;
+          for (int g = 0; g < HALF / 16; g++) tmem_ld_32x16(scol + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[g * 16]));
+          tmem_ld_wait();
+          const int j0 = c * NCH + hf * HALF;              // multiple of W
+          const float* tp = sTab + (qi - (j0 / W) * STR);
+#pragma unroll
+          for (int g = 0; g < HALF / 16; g++) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const int cc = g * 16 + e;
+              const float x0 = fmaf(__uint_as_float(sv[cc]), sc2, tp[-TcGeom<W>::off(cc)]);
+              const float x1 = fmaf(__uint_as_float(sv[cc + 1]), sc2, tp[-TcGeom<W>::off(cc + 1)]);
+              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+              l0 += p0;
+              l1 += p1;
+              pk[e / 2] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x8(scol + g * 8, pk);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
       }
-      fence_proxy_async_smem();
+      // ---- tile epilogue: o = O / l, lse = M_h + log2 l
+      const int lp = t & 1;
+      if (warp_valid) sL[(lp * 2 + hf) * 128 + r] = l0 + l1;
+      named_bar_sync(1, 256);
+      mbar_wait_tag(o_full, t & 1, 12);
+      if (warp_valid) {
+        tc_fence_after();
+        const float lt = sL[(lp * 2) * 128 + r] + sL[(lp * 2 + 1) * 128 + r];
+        const float inv = 1.f / lt;
+        uint32_t ov[16];
+        tmem_ld_32x16(lane_base + OCOL + hf * 16, ov);
+        tmem_ld_wait();
+        if (i < n) {
+          const long long grow = row0 + i;
+          uint4 u0, u1;
+          u0.x = pack_bf16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv);
+          u0.y = pack_bf16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv);
+          u0.z = pack_bf16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv);
+          u0.w = pack_bf16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv);
+          u1.x = pack_bf16x2(__uint_as_float(ov[8]) * inv, __uint_as_float(ov[9]) * inv);
+          u1.y = pack_bf16x2(__uint_as_float(ov[10]) * inv, __uint_as_float(ov[11]) * inv);
+          u1.z = pack_bf16x2(__uint_as_float(ov[12]) * inv, __uint_as_float(ov[13]) * inv);
+          u1.w = pack_bf16x2(__uint_as_float(ov[14]) * inv, __uint_as_float(ov[15]) * inv);
+          uint4* dst = reinterpret_cast<uint4*>(p.o + grow * p.ldo + head * 32 + hf * 16);
+          dst[0] = u0;
+          dst[1] = u1;
+          if (hf == 0 && p.lse != nullptr) p.lse[grow * p.heads + head] = Mh + log2f(lt);
+        }
+      }
     }
-    tc_fence_before();
-    __syncthreads();
-    float m_run = -INFINITY, l_run = 0.f;
-    float oacc[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) oacc[i] = 0.f;
-    for (int ck = 0; ck < n_chunks; ck++) {
-      // ---- S = Q K_chunk^T
-      if (tid == 128) {
+  } else if (warp == 8) {
+    // ===================== TMA producer: remaining Q tiles =====================
+    if (lane == 0) {
+      for (int t = 1; t < NT; t++) {
+        const int slot = t & 1;
+        mbar_wait_tag(&q_empty[slot], ((t >> 1) & 1) ^ 1, 20 + slot);
+        mbar_arrive_expect_tx(&q_full[slot], 8192);
+        tma_load_2d(sQ + slot * 8192, &tq, &q_full[slot], head * 32, (int)(row0 + t * 128));
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, NCH);
+      constexpr uint32_t idesc_pv = umma_idesc(1, 0, 1, 128, 32);     // A = P from TMEM (K-major), B = V MN-major
+      const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+      auto issue_s = [&](int b) {
+        const int t = b / NC, c = b % NC, st = b & 1;
+        if (c == 0) mbar_wait_tag(&q_full[t & 1], (t >> 1) & 1, 30 + (t & 1));
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 2; ks++) {
-          const uint64_t ad = umma_smem_desc(sQ_u + ks * 32, 16, 1024);
-          const uint64_t bd = umma_smem_desc(sK_u + (uint32_t)ck * nch * 128 + ks * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc_qk, ks > 0 ? 1u : 0u);
+          const uint64_t ad = umma_smem_desc_sw(sQ_u + (t & 1) * 8192 + ks * 32, 16, 512, SW64);
+          const uint64_t bd = umma_smem_desc_sw(sK_u + (uint32_t)c * NCH * 64 + ks * 32, 16, 512, SW64);
+          umma_bf16(tmem_base + st * NCH, ad, bd, idesc_s, ks > 0 ? 1u : 0u);
         }
-        umma_commit(bar_mma);
-      }
-      float alpha = 1.f;
-      if (tid < 128) {
-        mbar_wait(bar_mma, ph);
+        umma_commit(&s_full[st]);
+        if (c == NC - 1) umma_commit(&q_empty[t & 1]);   // every S MMA of this Q tile has been issued
+      };
+      mbar_wait_tag(k_full, 0, 32);
+      issue_s(0);
+      for (int b = 0; b < NB; b++) {
+        if (b + 1 < NB) issue_s(b + 1);
+        const int c = b % NC, st = b & 1;
+        if (b == 0) mbar_wait_tag(v_full, 0, 33);
+        mbar_wait_tag(&p_full[st], (b >> 1) & 1, 34 + st);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const __nv_bfloat16* brow = (bias != nullptr && row_ok) ? bias + ((long long)head * n + row_i) * n + (long long)ck * nch : nullptr;
-        // pass 1: row maximum of the chunk
-        float mloc = -INFINITY;
-        for (int s32 = 0; s32 < nch / 32; s32++) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + s32 * 32, raw);
-          uint4 bq[4];
 #pragma unroll
-          for (int j = 0; j < 4; j++) bq[j] = brow ? __ldg(reinterpret_cast<const uint4*>(brow + s32 * 32) + j) : make_uint4(0, 0, 0, 0);
-          tmem_ld_wait();
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(bq);
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const float2 bb = unpack_bf16x2(bw[j]);
-            mloc = fmaxf(mloc, fmaf(__uint_as_float(raw[2 * j]), sc2, bb.x * kTcaLog2e));
-            mloc = fmaxf(mloc, fmaf(__uint_as_float(raw[2 * j + 1]), sc2, bb.y * kTcaLog2e));
-          }
+        for (int ks = 0; ks < NCH / 16; ks++) {
+          const int k0 = ks * 16;
+          const uint32_t acol = st * NCH + (k0 / HALF) * HALF + (k0 % HALF) / 2;
+          const uint64_t bd = umma_smem_desc_sw(sV_u + (uint32_t)(c * NCH + k0) * 64, 512, 512, SW64);
+          umma_bf16_ts(tmem_base + OCOL, tmem_base + acol, bd, idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
         }
-        const float m_new = fmaxf(m_run, mloc);
-        alpha = tca_exp2(m_run - m_new);     // first chunk: exp2(-inf) = 0
-        // pass 2: P = exp2(x - m_new) -> bf16 -> sP (row = tid, 64-key blocks)
-        float lsum = 0.f;
-        for (int s32 = 0; s32 < nch / 32; s32++) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + s32 * 32, raw);
-          uint4 bq[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) bq[j] = brow ? __ldg(reinterpret_cast<const uint4*>(brow + s32 * 32) + j) : make_uint4(0, 0, 0, 0);
-          tmem_ld_wait();
-          const uint32_t* bw = reinterpret_cast<const uint32_t*>(bq);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const float2 bb = unpack_bf16x2(bw[j]);
-            const float p0 = tca_exp2(fmaf(__uint_as_float(raw[2 * j]), sc2, bb.x * kTcaLog2e) - m_new);
-            const float p1 = tca_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), sc2, bb.y * kTcaLog2e) - m_new);
-            lsum += p0 + p1;
-            pk[j] = pack_bf16x2(p0, p1);
-          }
-          // 32 keys = 4 chunks of 16 B inside 64-key block (s32 / 2), chunk index (s32 & 1) * 4 + j
-          uint8_t* pblk = sP + (size_t)(s32 >> 1) * 16384;
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            *reinterpret_cast<uint4*>(pblk + tca_swz(tid, (s32 & 1) * 4 + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
-        l_run = l_run * alpha + lsum;
-        m_run = m_new;
-        fence_proxy_async_smem();
+        if (c == NC - 1) umma_commit(o_full);
       }
-      ph ^= 1;
-      tc_fence_before();
-      __syncthreads();
-      // ---- Oc = P V_chunk (fresh accumulator)
-      if (tid == 128) {
-        tc_fence_after();
-        for (int kb_ = 0; kb_ < kblk; kb_++) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
-            const uint64_t ad = umma_smem_desc(sP_u + (uint32_t)kb_ * 16384 + ks * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc(sVt_u + (uint32_t)(ck * kblk + kb_) * 4096 + ks * 32, 16, 1024);
-            umma_bf16(tmem_base + nch, ad, bd, idesc_pv, (kb_ > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(bar_mma);
-      }
-      if (tid < 128) {
-        mbar_wait(bar_mma, ph);
-        tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + nch, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) oacc[i] = fmaf(oacc[i], alpha, __uint_as_float(raw[i]));
-      }
-      ph ^= 1;
-      tc_fence_before();
-      __syncthreads();
-    }
-    // ---- normalise and store this query tile
-    if (row_ok) {
-      const float inv = 1.f / l_run;
-      const long long grow = g.row(seq, row_i);
-      __nv_bfloat16* orow = o + grow * a.ldo + head * TCA_DH;
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        uint4 u;
-        u.x = pack_bf16x2(oacc[8 * c + 0] * inv, oacc[8 * c + 1] * inv);
-        u.y = pack_bf16x2(oacc[8 * c + 2] * inv, oacc[8 * c + 3] * inv);
-        u.z = pack_bf16x2(oacc[8 * c + 4] * inv, oacc[8 * c + 5] * inv);
-        u.w = pack_bf16x2(oacc[8 * c + 6] * inv, oacc[8 * c + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + c * 8) = u;
-      }
-      if (a.lse != nullptr) a.lse[grow * a.heads + head] = m_run + log2f(l_run);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward: ONE pass, 5 contractions + 1 exponential per score (the mma.sync path of attention.cu runs two recomputing
+// passes: 7 contractions + 2 exponentials). Persistent, one CTA per SM, TMEM 480 / 512 columns.
+//
+// Orientation: KEYS on the TMEM lanes. Per (sequence, head) item, per block of 128 keys (kb) and half-block of 64 queries (qc):
+//   MMA      S^T  = K_blk  Q_c^T      (SS, M=128 keys, N=64 queries, K=32)        -> stage columns [0, 64)
+//   MMA      dP^T = V_blk dO_c^T      (SS)                                         -> stage columns [64, 128)
+//   warps0-7 P^T = exp2(S^T*scale*log2e + table'[rel] - lse_i),  dS^T = P^T o (dP^T - delta_i)   (thread = key row, warp = 32 keys x 32 queries)
+//            P^T  -> bf16 -> TMEM over its own S^T columns (tcgen05.st)
+//            dS^T -> bf16 -> (a) shared tile [key][query] (SWIZZLE_128B), (b) the global spill for the table gradient
+//   MMA      dV_blk += P^T dO_c       (TS: A from TMEM; B = the dO chunk read MN-major)
+//   MMA      dK_blk += dS^T Q_c       (SS: A = the shared dS tile read K-major; B = the Q chunk read MN-major)
+//   MMA      dQ_pair += dS K_blk      (SS: A = the SAME shared dS tile read MN-major, 128 queries = two half-blocks; B = K_blk MN-major)
+// dV/dK accumulate over the query chunks of one key block, dQ (5 tiles of 128 queries = 160 columns) over the key blocks of
+// the item; both are drained by the softmax warps one block later, while the tensor pipe already works on the next block.
+// Operands stream through TMA rings that run across item boundaries (K/V block ring of 2, Q/dO chunk ring of 4 -- each
+// chunk is re-read once per key block from L2), so there is no per-item prologue bubble.
+// The gradient of the position-bias table needs sum over sequences of dS: the bf16 dS^T tiles are spilled (the kernel is
+// exp/issue bound, the writes ride along) and attn_dtab_reduce_kernel sums them over the sequences straight into the
+// (2H-1)(2W-1) table bins -- the [heads, n, n] dbias tensor of the mma.sync path never exists.
+// ------------------------------------------------------------------------------------------------------------------
+struct TcBwdParams {
+  int n, heads, H, num_seqs;
+  const float* table;
+  float scale;
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* dq; long long ld_dq;
+  __nv_bfloat16* dk; long long ld_dk;
+  __nv_bfloat16* dv; long long ld_dv;
+  __nv_bfloat16* ds_spill;   // [num_seqs*heads][n keys][n queries] or null
+};
+
+constexpr int TCB_QD_SLOTS = 4;
+constexpr int TCB_QD_BYTES = 4096 + 4096 + 64 * 16;   // Q chunk, dO chunk, per-query records {lse, delta, ci}
+constexpr int TCB_COL_DV = 256, TCB_COL_DK = 288, TCB_COL_DQ = 320;
+constexpr uint32_t SW128 = 2;
+
+template <int W>
+__global__ void __launch_bounds__(320, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
+                   const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv, const TcBwdParams p) {
+  constexpr int STR = TcGeom<W>::STR;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  const int n = p.n;
+  uint8_t* sKV = smem;                                   // 2 slots x (K block 8 KB + V block 8 KB)
+  uint8_t* sDS = sKV + 2 * 16384;                        // 2 buffers x [2 query groups][128 keys][128 B]
+  uint8_t* sQD = sDS + 2 * 32768;                        // 4 slots x TCB_QD_BYTES
+  float* sTab = reinterpret_cast<float*>(sQD + TCB_QD_SLOTS * TCB_QD_BYTES);
+  const int tab_elems = ((2 * p.H - 1) * STR + 31) & ~31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTab + tab_elems);
+  uint64_t* kv_full = bars + 0;     // [2]
+  uint64_t* kv_empty = bars + 2;    // [2]
+  uint64_t* qd_full = bars + 4;     // [4]
+  uint64_t* qd_empty = bars + 8;    // [4]
+  uint64_t* s_full = bars + 12;     // [2]
+  uint64_t* p_full = bars + 14;     // [2]
+  uint64_t* ds_free = bars + 16;    // [2]
+  uint64_t* acc_full = bars + 18;
+  uint64_t* dq_full = bars + 19;
+  uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 20);
+  float* sRed = reinterpret_cast<float*>(holder + 2);    // [10]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NKB = (n + 127) / 128, NQC = n / 64;
+  const int BPI = NKB * NQC;                             // half-blocks per item
+  const int items = p.num_seqs * p.heads;
+  const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long total_blocks = (long long)my_items * BPI;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tq);
+    tma_prefetch_desc(&tdo);
+    tma_prefetch_desc(&tk);
+    tma_prefetch_desc(&tv);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&ds_free[i], 1);
+    }
+    for (int i = 0; i < TCB_QD_SLOTS; i++) {
+      mbar_init(&qd_full[i], 33);      // 1 expect_tx arrival (TMA bytes) + 32 lanes that wrote the per-query records
+      mbar_init(&qd_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(dq_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(holder, 512);
+    tmem_relinquish();
+  }
+  // NOTE: the table of head h is only valid for items of head h: a CTA walks items blockIdx.x + k*gridDim.x, so with
+  // gridDim.x % heads == 0 (enforced by the launcher) every item of this CTA has the same head.
+  const int head = (int)blockIdx.x % p.heads;
+  tc_fence_before();
+  (void)tc_load_table<W>(sTab, sRed, p.table, nullptr, 0.f, p.H, p.heads, head, tid, 320);   // table * log2e (no reference shift: lse is subtracted)
+  tc_fence_after();
+  const uint32_t tmem_base = *holder;
+  const float sc2 = p.scale * kTcLog2e;
+
+  if (warp < 8) {
+    // ===================== softmax-backward warps =====================
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;                          // key row inside the block = TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    int u = 0, v = 0, m = 0;                              // key blocks, query pairs, items completed so far (ring parities)
+    int prev_item = 0, prev_kb = 0;
+    long long g = 0;
+    auto drain_dvdk = [&](int item_, int kb_, uint32_t parity) {   // dV / dK of key block (item_, kb_): TMEM -> bf16 -> global
+      mbar_wait_tag(acc_full, parity, 40);
+      tc_fence_after();
+      const int key = kb_ * 128 + r;
+      uint32_t a[16], b[16];
+      tmem_ld_32x16(lane_base + TCB_COL_DV + hf * 16, a);
+      tmem_ld_32x16(lane_base + TCB_COL_DK + hf * 16, b);
+      tmem_ld_wait();
+      if (key < n) {
+        const int hd = item_ % p.heads;
+        const long long row = (long long)(item_ / p.heads) * n + key;
+        uint32_t x[8], y[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          x[e] = pack_bf16x2(__uint_as_float(a[2 * e]), __uint_as_float(a[2 * e + 1]));
+          y[e] = pack_bf16x2(__uint_as_float(b[2 * e]) * p.scale, __uint_as_float(b[2 * e + 1]) * p.scale);
+        }
+        uint4* pv = reinterpret_cast<uint4*>(p.dv + row * p.ld_dv + hd * 32 + hf * 16);
+        uint4* pk = reinterpret_cast<uint4*>(p.dk + row * p.ld_dk + hd * 32 + hf * 16);
+        pv[0] = make_uint4(x[0], x[1], x[2], x[3]);
+        pv[1] = make_uint4(x[4], x[5], x[6], x[7]);
+        pk[0] = make_uint4(y[0], y[1], y[2], y[3]);
+        pk[1] = make_uint4(y[4], y[5], y[6], y[7]);
+      }
+    };
+    auto drain_dq = [&](int item_, uint32_t parity) {     // dQ of a finished item: NKB tiles of 128 queries
+      mbar_wait_tag(dq_full, parity, 41);
+      tc_fence_after();
+      const int hd = item_ % p.heads;
+      for (int t = 0; t < NKB; t++) {
+        const int qi = t * 128 + r;
+        uint32_t a[16];
+        tmem_ld_32x16(lane_base + TCB_COL_DQ + t * 32 + hf * 16, a);
+        tmem_ld_wait();
+        if (qi < n) {
+          const long long row = (long long)(item_ / p.heads) * n + qi;
+          uint32_t x[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) x[e] = pack_bf16x2(__uint_as_float(a[2 * e]) * p.scale, __uint_as_float(a[2 * e + 1]) * p.scale);
+          uint4* pq = reinterpret_cast<uint4*>(p.dq + row * p.ld_dq + hd * 32 + hf * 16);
+          pq[0] = make_uint4(x[0], x[1], x[2], x[3]);
+          pq[1] = make_uint4(x[4], x[5], x[6], x[7]);
+        }
+      }
+    };
+    for (int il = 0; il < my_items; il++) {
+      const int item = (int)blockIdx.x + il * (int)gridDim.x;
+      for (int kb = 0; kb < NKB; kb++) {
+        const int key = kb * 128 + r;
+        const bool warp_valid = (kb * 128 + q * 32) < n;
+        const int kc = key < n ? key : n - 1;
+        const int tj = (p.H - 1 - kc / W) * STR + (W - 1 - kc % W);     // table index = tj + ci(query)
+        for (int qc = 0; qc < NQC; qc++, g++) {
+          const int st = (int)(g & 1), slot = (int)(g % TCB_QD_SLOTS);
+          const int buf = v & 1, grp = qc & 1;
+          uint8_t* tile_row = sDS + buf * 32768 + grp * 16384 + r * 128;
+          mbar_wait_tag(&qd_full[slot], (uint32_t)((g / TCB_QD_SLOTS) & 1), 42);
+          mbar_wait_tag(&s_full[st], (uint32_t)((g >> 1) & 1), 43);
+          if (grp == 0) mbar_wait_tag(&ds_free[buf], (uint32_t)(((v >> 1) & 1) ^ 1), 44);
+          if (warp_valid) {
+            tc_fence_after();
+            const uint32_t scol = lane_base + st * 128 + hf * 32;
+            uint32_t sv[32], dp[32];
+            tmem_ld_32x32(scol, sv);
+            tmem_ld_32x32(scol + 64, dp);
+            tmem_ld_wait();
+            const float4* rec = reinterpret_cast<const float4*>(sQD + slot * TCB_QD_BYTES + 8192) + hf * 32;
+            const float* tp = sTab + tj;
+            uint32_t pk[16], dk_[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float4 r0 = rec[e], r1 = rec[e + 1];            // {lse_i, delta_i, ci}: broadcast LDS.128
+              const float x0 = fmaf(__uint_as_float(sv[e]), sc2, tp[__float_as_int(r0.z)]) - r0.x;
+              const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, tp[__float_as_int(r1.z)]) - r1.x;
+              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+              const float d0 = p0 * (__uint_as_float(dp[e]) - r0.y), d1 = p1 * (__uint_as_float(dp[e + 1]) - r1.y);
+              pk[e / 2] = pack_bf16x2(p0, p1);
+              dk_[e / 2] = pack_bf16x2(d0, d1);
+            }
+            tmem_st_32x16(scol, pk);                                 // P^T over this warp's own S^T columns
+            __nv_bfloat16* sp = (p.ds_spill != nullptr)
+                                    ? p.ds_spill + ((long long)item * n + key) * n + qc * 64 + hf * 32 : nullptr;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+              const uint4 val = make_uint4(dk_[4 * c4], dk_[4 * c4 + 1], dk_[4 * c4 + 2], dk_[4 * c4 + 3]);
+              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) = val;
+              if (sp != nullptr) __stcs(reinterpret_cast<uint4*>(sp) + c4, val);
+            }
+            tmem_st_wait();
+          } else {
+            // key rows beyond the sequence: their dS must be ZERO in the shared tile (dQ contracts over all 128 keys)
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++)
+              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+          // drain the accumulators of the previous key block / item before this block's MMAs may overwrite them
+          if (qc == 0 && u > 0) drain_dvdk(prev_item, prev_kb, (uint32_t)((u - 1) & 1));
+          if (qc == 0 && kb == 0 && m > 0) drain_dq(prev_item, (uint32_t)((m - 1) & 1));
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[st]);
+          if (grp == 1 || qc == NQC - 1) v++;
+        }
+        u++;
+        prev_item = item;
+        prev_kb = kb;
+      }
+      m++;
+    }
+    if (my_items > 0) {
+      drain_dvdk(prev_item, prev_kb, (uint32_t)((u - 1) & 1));
+      drain_dq(prev_item, (uint32_t)((m - 1) & 1));
+    }
+  } else if (warp == 8) {
+    // ===================== producer (whole warp: lane 0 drives TMA, all lanes write the per-query records) =====================
+    long long g = 0;
+    int u = 0;
+    for (int il = 0; il < my_items; il++) {
+      const int item = (int)blockIdx.x + il * (int)gridDim.x;
+      const int hd = item % p.heads;
+      const long long row0 = (long long)(item / p.heads) * n;
+      for (int kb = 0; kb < NKB; kb++, u++) {
+        if (lane == 0) {
+          const int ks = u & 1;
+          mbar_wait_tag(&kv_empty[ks], (uint32_t)(((u >> 1) & 1) ^ 1), 50);
+          mbar_arrive_expect_tx(&kv_full[ks], 16384);
+          tma_load_2d(sKV + ks * 16384, &tk, &kv_full[ks], hd * 32, (int)(row0 + kb * 128));
+          tma_load_2d(sKV + ks * 16384 + 8192, &tv, &kv_full[ks], hd * 32, (int)(row0 + kb * 128));
+        }
+        for (int qc = 0; qc < NQC; qc++, g++) {
+          const int slot = (int)(g % TCB_QD_SLOTS);
+          uint8_t* sl = sQD + slot * TCB_QD_BYTES;
+          if (lane == 0) mbar_wait_tag(&qd_empty[slot], (uint32_t)(((g / TCB_QD_SLOTS) & 1) ^ 1), 51);
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&qd_full[slot], 8192);
+            tma_load_2d(sl, &tq, &qd_full[slot], hd * 32, (int)(row0 + qc * 64));
+            tma_load_2d(sl + 4096, &tdo, &qd_full[slot], hd * 32, (int)(row0 + qc * 64));
+          }
+          float4* rec = reinterpret_cast<float4*>(sl + 8192);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            const int i = qc * 64 + h2 * 32 + lane;          // < n (n % 64 == 0)
+            const long long idx = (row0 + i) * p.heads + hd;
+            rec[h2 * 32 + lane] = make_float4(__ldg(p.lse + idx), __ldg(p.delta + idx), __int_as_float((i / W) * STR + (i % W)), 0.f);
+          }
+          mbar_arrive(&qd_full[slot]);
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && total_blocks > 0) {
+      constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, 64);     // S^T, dP^T : A, B K-major
+      constexpr uint32_t idesc_dv = umma_idesc(1, 0, 1, 128, 32);    // dV (A TMEM), dK (A smem K-major): B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc(1, 1, 1, 128, 32);    // dQ: A, B MN-major
+      const uint32_t sKV_u = smem_u32(sKV), sDS_u = smem_u32(sDS), sQD_u = smem_u32(sQD);
+      // look-ahead issue of S^T / dP^T for flat block f (0 .. total_blocks): needs its K/V block and its Q/dO chunk
+      auto issue_s = [&](long long f) {
+        const int qc = (int)(f % NQC);
+        const long long ub = f / NQC;                               // running key-block index of this CTA
+        const int ks = (int)(ub & 1), slot = (int)(f % TCB_QD_SLOTS), st = (int)(f & 1);
+        if (qc == 0) mbar_wait_tag(&kv_full[ks], (uint32_t)((ub >> 1) & 1), 60);
+        mbar_wait_tag(&qd_full[slot], (uint32_t)((f / TCB_QD_SLOTS) & 1), 61);
+        tc_fence_after();
+        const uint32_t kA = sKV_u + ks * 16384, vA = kA + 8192, qB = sQD_u + slot * TCB_QD_BYTES, dB = qB + 4096;
+        const uint32_t d0 = tmem_base + st * 128;
+#pragma unroll
+        for (int k2 = 0; k2 < 2; k2++)
+          umma_bf16(d0, umma_smem_desc_sw(kA + k2 * 32, 16, 512, SW64), umma_smem_desc_sw(qB + k2 * 32, 16, 512, SW64), idesc_s, k2);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; k2++)
+          umma_bf16(d0 + 64, umma_smem_desc_sw(vA + k2 * 32, 16, 512, SW64), umma_smem_desc_sw(dB + k2 * 32, 16, 512, SW64), idesc_s, k2);
+        umma_commit(&s_full[st]);
+      };
+      issue_s(0);
+      int v = 0;
+      for (long long f = 0; f < total_blocks; f++) {
+        if (f + 1 < total_blocks) issue_s(f + 1);
+        const int qc = (int)(f % NQC);
+        const long long ub = f / NQC;
+        const int kb = (int)(ub % NKB);
+        const int ks = (int)(ub & 1), slot = (int)(f % TCB_QD_SLOTS), st = (int)(f & 1);
+        const int buf = v & 1, grp = qc & 1;
+        mbar_wait_tag(&p_full[st], (uint32_t)((f >> 1) & 1), 62);
+        tc_fence_after();
+        const uint32_t kA = sKV_u + ks * 16384, qB = sQD_u + slot * TCB_QD_BYTES, dB = qB + 4096;
+        const uint32_t tile = sDS_u + buf * 32768;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {     // dV += P^T dO_c : K = 64 queries
+          const uint32_t acol = st * 128 + (k4 >> 1) * 32 + (k4 & 1) * 8;
+          umma_bf16_ts(tmem_base + TCB_COL_DV, tmem_base + acol, umma_smem_desc_sw(dB + k4 * 1024, 512, 512, SW64), idesc_dv,
+                       (qc > 0 || k4 > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++)       // dK += dS^T Q_c : A = dS tile group grp, K-major
+          umma_bf16(tmem_base + TCB_COL_DK, umma_smem_desc_sw(tile + grp * 16384 + k4 * 32, 16, 1024, SW128),
+                    umma_smem_desc_sw(qB + k4 * 1024, 512, 512, SW64), idesc_dv, (qc > 0 || k4 > 0) ? 1u : 0u);
+        umma_commit(&qd_empty[slot]);
+        if (grp == 1 || qc == NQC - 1) {     // dQ tile (qc/2) += dS K_blk : A = both groups of the tile, MN-major, K = 128 keys
+#pragma unroll
+          for (int k8 = 0; k8 < 8; k8++)
+            umma_bf16(tmem_base + TCB_COL_DQ + (qc >> 1) * 32, umma_smem_desc_sw(tile + k8 * 2048, 16384, 1024, SW128),
+                      umma_smem_desc_sw(kA + k8 * 1024, 512, 512, SW64), idesc_dq, (kb > 0 || k8 > 0) ? 1u : 0u);
+          umma_commit(&ds_free[buf]);
+          v++;
+        }
+        if (qc == NQC - 1) {
+          umma_commit(&kv_empty[ks]);
+          umma_commit(acc_full);
+          if (kb == NKB - 1) umma_commit(dq_full);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dtable[rel(i,j), h] += sum over sequences of dS^T[seq, h][j][i]   (the spill of attn_tc_bwd_kernel).
+// thread = 8 consecutive queries of one (head, key); block = 256 threads; bins of the block in shared memory, then one
+// global atomic per touched bin.
+__global__ void __launch_bounds__(256) attn_dtab_reduce_kernel(const __nv_bfloat16* __restrict__ ds, float* __restrict__ dtable,
+                                                               int num_seqs, int heads, int H, int W) {
+  extern __shared__ float s_bins[];
+  const int n = H * W, R = (2 * H - 1) * (2 * W - 1);
+  for (int i = threadIdx.x; i < R; i += 256) s_bins[i] = 0.f;
+  __syncthreads();
+  const int groups_per_head = n * (n / 8);
+  const int blocks_per_head = (groups_per_head + 255) / 256;
+  const int h = blockIdx.x / blocks_per_head;
+  const int gidx = (blockIdx.x % blocks_per_head) * 256 + threadIdx.x;
+  if (gidx < groups_per_head) {
+    const int j = gidx / (n / 8), i0 = (gidx % (n / 8)) * 8;
+    const long long nn = (long long)n * n;
+    const __nv_bfloat16* src = ds + (long long)h * nn + (long long)j * n + i0;
+    const long long stride = (long long)heads * nn;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+#pragma unroll 8
+    for (int sq = 0; sq < num_seqs; sq++) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(src + (long long)sq * stride));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 f = unpack_bf16x2(w[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+    const int yj = j / W, xj = j % W;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int i = i0 + e;
+      const int rr = (i / W - yj + H - 1) * (2 * W - 1) + (i % W - xj + W - 1);
+      atomicAdd(&s_bins[rr], acc[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R; i += 256) {
+    const float vv = s_bins[i];
+    if (vv != 0.f) atomicAdd(dtable + (long long)i * heads + h, vv);
+  }
+}
+
+__global__ void qk_bound_kernel(const float* __restrict__ qs, const float* __restrict__ ks, int dh, float* __restrict__ out) {
+  float m = 0.f;
+  for (int d = threadIdx.x; d < dh; d += 32) m = fmaxf(m, fabsf(qs[d] * ks[d]));
+  m = warp_max(m);
+  if (threadIdx.x == 0) out[0] = m;
 }
 
 }  // namespace ctb
 
 using namespace ctb;
 
-extern "C" int ctclip_attn_fwd_tc(const ctclip_attn_args* a, void* stream_) {
+extern "C" int ctclip_qk_bound(const float* q_scale, const float* k_scale, int32_t dim_head, float* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  CTB_CHECK_ARG(a != nullptr && a->q && a->k && a->v && a->o, "attn_fwd_tc: null pointer");
-  CTB_CHECK_ARG(a->dim_head == 32 && a->key_mask == nullptr, "attn_fwd_tc: dim_head 32 without key mask only");
-  CTB_CHECK_ARG(a->n >= 64 && a->n % 64 == 0 && a->n <= 768, "attn_fwd_tc: n must be a multiple of 64 in [64, 768] (got %d)", a->n);
-  CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "attn_fwd_tc: rows must be 16B aligned");
-  const int nch = (a->n % 192 == 0) ? 192 : ((a->n % 128 == 0) ? 128 : 64);
-  const size_t smem = 1024 + 128 * 128 + (size_t)a->n * 128 + (size_t)(a->n / 64) * 4096 + (size_t)(nch / 64) * 16384 + 64;
-  CTB_CHECK_ARG(smem <= 227 * 1024, "attn_fwd_tc: %zu B of shared memory needed", smem);
-  CTB_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_tc_fwd_kernel<<<a->num_seqs * a->heads, TCA_THREADS, smem, stream>>>(*a, nch);
+  CTB_CHECK_ARG(q_scale && k_scale && out && dim_head > 0, "qk_bound: bad args");
+  qk_bound_kernel<<<1, 32, 0, stream>>>(q_scale, k_scale, dim_head, out);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
+}
+
+static int tc_grid_w(const ctclip_attn_args* a) { return a->grid_w; }
+
+extern "C" int ctclip_attn_tc_supported(int32_t n, int32_t grid_h, int32_t grid_w, int32_t dim_head) {
+  if (dim_head != 32 || grid_h <= 0 || grid_w <= 0 || n != grid_h * grid_w) return 0;
+  // bit 0: forward kernel, bit 1: backward kernel (its dQ accumulators need ceil(n/128)*32 <= 192 TMEM columns)
+  if (grid_w == 24 && n % 96 == 0 && n <= 1152) return 1 | ((n % 64 == 0 && (n + 127) / 128 * 32 <= 192) ? 2 : 0);
+  if (grid_w == 32 && n % 64 == 0 && n <= 1024) return 1;
+  return 0;
+}
+
+template <int NCH, int W>
+static int launch_tc_fwd(const ctclip_attn_args* a, cudaStream_t stream) {
+  const long long rows = (long long)a->num_seqs * a->n;
+  CUtensorMap tq, tk, tv;
+  const uint64_t inner = (uint64_t)a->heads * 32;
+  if (int rc = encode_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->q, inner, (uint64_t)rows, (uint64_t)a->ldq * 2, 32, 128,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  if (int rc = encode_tmap_2d(&tk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->k, inner, (uint64_t)rows, (uint64_t)a->ldk * 2, 32, 64,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  if (int rc = encode_tmap_2d(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->v, inner, (uint64_t)rows, (uint64_t)a->ldv * 2, 32, 64,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  TcFwdParams p;
+  p.n = a->n; p.heads = a->heads; p.H = a->grid_h; p.num_seqs = a->num_seqs;
+  p.table = a->cpb_table; p.qk_bound = a->qk_bound; p.scale = a->scale;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo; p.lse = a->lse;
+  const int tab_elems = ((2 * a->grid_h - 1) * TcGeom<W>::STR + 31) & ~31;
+  const size_t smem = 1024 + (size_t)a->n * 128 + 2 * 8192 + (size_t)tab_elems * 4 + 512 * 4 + 12 * 8 + 8 + 16 * 4 + 64;
+  CTB_CHECK_ARG(smem <= 227 * 1024, "attn_fwd(tc): %zu B of shared memory needed", smem);
+  auto kern = attn_tc_fwd_kernel<NCH, W>;
+  CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<a->num_seqs * a->heads, 320, smem, stream>>>(tq, tk, tv, p);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+// Forward on the tcgen05 path. Called by ctclip_attn_fwd when args->cpb_table (or args->tc_path) selects it.
+int ctb_attn_fwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
+  CTB_CHECK_ARG(a->q && a->k && a->v && a->o, "attn_fwd(tc): null pointer");
+  CTB_CHECK_ARG(ctclip_attn_tc_supported(a->n, a->grid_h, a->grid_w, a->dim_head),
+                "attn_fwd(tc): unsupported geometry n=%d grid=%dx%d dim_head=%d", a->n, a->grid_h, a->grid_w, a->dim_head);
+  CTB_CHECK_ARG(a->key_mask == nullptr, "attn_fwd(tc): no key mask on this path");
+  CTB_CHECK_ARG(a->seq_inner == 1 && a->tok_stride == 1 && a->seq_outer_stride == a->n, "attn_fwd(tc): sequences must be contiguous");
+  CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "attn_fwd(tc): rows must be 16B aligned");
+  CTB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
+                 reinterpret_cast<uintptr_t>(a->o)) % 16 == 0, "attn_fwd(tc): q/k/v/o must be 16B aligned");
+  if (tc_grid_w(a) == 24) return launch_tc_fwd<96, 24>(a, stream);
+  return launch_tc_fwd<64, 32>(a, stream);
+}
+
+static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {
+  const long long rows = (long long)a->num_seqs * a->n;
+  CUtensorMap tq, tdo, tk, tv;
+  const uint64_t inner = (uint64_t)a->heads * 32;
+  if (int rc = encode_tmap_2d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->q, inner, (uint64_t)rows, (uint64_t)a->ldq * 2, 32, 64,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  if (int rc = encode_tmap_2d(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->d_o, inner, (uint64_t)rows, (uint64_t)a->ldo * 2, 32, 64,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  if (int rc = encode_tmap_2d(&tk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->k, inner, (uint64_t)rows, (uint64_t)a->ldk * 2, 32, 128,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  if (int rc = encode_tmap_2d(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->v, inner, (uint64_t)rows, (uint64_t)a->ldv * 2, 32, 128,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  TcBwdParams p;
+  p.n = a->n; p.heads = a->heads; p.H = a->grid_h; p.num_seqs = a->num_seqs;
+  p.table = a->cpb_table; p.scale = a->scale; p.lse = a->lse; p.delta = a->delta;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.ld_dq = a->ld_dq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.ld_dk = a->ld_dk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.ld_dv = a->ld_dv;
+  p.ds_spill = (a->dcpb_table != nullptr) ? reinterpret_cast<__nv_bfloat16*>(a->ds_scratch) : nullptr;
+  const int tab_elems = ((2 * a->grid_h - 1) * TcGeom<24>::STR + 31) & ~31;
+  const size_t smem = 1024 + 2 * 16384 + 2 * 32768 + (size_t)TCB_QD_SLOTS * TCB_QD_BYTES + (size_t)tab_elems * 4 + 20 * 8 + 8 + 16 * 4 + 64;
+  CTB_CHECK_ARG(smem <= 227 * 1024, "attn_bwd(tc): %zu B of shared memory needed", smem);
+  auto kern = attn_tc_bwd_kernel<24>;
+  CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent grid: a multiple of `heads` CTAs so that every item a CTA walks (blockIdx.x + k*gridDim.x) has the same head
+  const int items = a->num_seqs * a->heads;
+  int grid = (num_sms() / a->heads) * a->heads;
+  if (grid < a->heads) grid = a->heads;
+  if (grid > items) grid = items;
+  kern<<<grid, 320, smem, stream>>>(tq, tdo, tk, tv, p);
+  CTB_LAUNCH_CHECK();
+  if (a->dcpb_table != nullptr) {
+    const int n = a->n, R = (2 * a->grid_h - 1) * (2 * a->grid_w - 1);
+    const int blocks_per_head = (n * (n / 8) + 255) / 256;
+    attn_dtab_reduce_kernel<<<blocks_per_head * a->heads, 256, R * sizeof(float), stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->ds_scratch), a->dcpb_table, a->num_seqs, a->heads, a->grid_h, a->grid_w);
+    CTB_LAUNCH_CHECK();
+  }
+  return CTCLIP_OK;
+}
+
+// Backward on the tcgen05 path (delta already computed by the caller, ctclip_attn_bwd).
+int ctb_attn_bwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
+  CTB_CHECK_ARG(a->q && a->k && a->v && a->d_o && a->lse && a->delta && a->dq && a->dk && a->dv, "attn_bwd(tc): null pointer");
+  CTB_CHECK_ARG((ctclip_attn_tc_supported(a->n, a->grid_h, a->grid_w, a->dim_head) & 2) != 0,
+                "attn_bwd(tc): unsupported geometry n=%d grid=%dx%d dim_head=%d", a->n, a->grid_h, a->grid_w, a->dim_head);
+  CTB_CHECK_ARG(a->key_mask == nullptr, "attn_bwd(tc): no key mask on this path");
+  CTB_CHECK_ARG(a->seq_inner == 1 && a->tok_stride == 1 && a->seq_outer_stride == a->n, "attn_bwd(tc): sequences must be contiguous");
+  CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && a->ld_dq % 8 == 0 && a->ld_dk % 8 == 0 &&
+                    a->ld_dv % 8 == 0, "attn_bwd(tc): rows must be 16B aligned");
+  CTB_CHECK_ARG(a->dcpb_table == nullptr || a->ds_scratch != nullptr, "attn_bwd(tc): dcpb_table needs ds_scratch");
+  CTB_CHECK_ARG(a->dbias == nullptr, "attn_bwd(tc): the table path produces dcpb_table, not dbias");
+  return launch_tc_bwd(a, stream);
 }

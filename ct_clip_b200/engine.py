@@ -63,7 +63,7 @@ class ViTGeom:
 
 class _LayerW:
     """bf16 GEMM operands + fp32 side vectors of one transformer layer (rebuilt after every optimiser step)."""
-    __slots__ = ("wq", "bq", "wkv", "wo", "w1", "b1", "w2")
+    __slots__ = ("wq", "bq", "wkv", "wo", "w1", "b1", "w2", "qkb")
 
 
 class _Saved:
@@ -95,6 +95,11 @@ class CTViTEngine:
         self._canon = {}
         self._prep = ops.PrepBatch()
         self.fused_geglu_bwd = False
+        # spatial attention on tcgen05 / TMEM (csrc/attention_tc.cu) whenever the token grid allows it (bit 0 forward, bit 1 backward);
+        # CTCLIP_ATTN_TC=0 keeps the mma.sync kernels of csrc/attention.cu (A/B measurements, debugging)
+        import os
+        tc = ops.attn_tc_supported(g.S, g.H, g.W, g.dim_head) if os.environ.get("CTCLIP_ATTN_TC", "1") != "0" else 0
+        self.tc_fwd, self.tc_bwd = bool(tc & 1), bool(tc & 2)
 
     def _canon_table(self, T):
         """canon(f) of the temporal stack's PEG (SURVEY trap T1) as an int32 lookup table (index prep, built once per T)."""
@@ -117,6 +122,7 @@ class CTViTEngine:
             lw.w1 = torch.empty(2 * g.ff_pad, g.dim, **bf)
             lw.b1 = torch.empty(2 * g.ff_pad, device=dev)
             lw.w2 = torch.empty(g.dim, g.ff_pad, **bf)
+            lw.qkb = torch.empty(1, device=dev)
         self.wp = torch.empty(g.dim, g.patch_voxels, **bf)
         self.bp = torch.empty(g.dim, device=dev)
         self.ehat = torch.empty(g.codebook_size, g.dim, **bf)
@@ -141,6 +147,10 @@ class CTViTEngine:
         pb.bias(P["to_patch_emb.2.weight"], self.bp, K=g.patch_voxels, Np=D, beta=P["to_patch_emb.1.bias"],
                 bias_in=P["to_patch_emb.2.bias"])
         pb.run()
+        if self.tc_fwd:
+            for i, lw in enumerate(self.spatial_w):   # logit bound of the fixed-reference softmax (attention_tc.cu)
+                a = f"enc_spatial_transformer.layers.{i}.1."
+                ops.qk_bound(P[a + "q_scale"], P[a + "k_scale"], lw.qkb, g.dim_head)
         self.prepare_codebook(P)
 
     def prepare_codebook(self, P):
@@ -162,7 +172,9 @@ class CTViTEngine:
             return dict(n=g.S, heads=g.heads, num_seqs=b * T, seq_inner=1, seq_outer_stride=g.S, tok_stride=1)
         return dict(n=T, heads=g.heads, num_seqs=b * g.S, seq_inner=g.S, seq_outer_stride=T * g.S, tok_stride=g.S)
 
-    def _cpb_forward(self, P, save):
+    def _cpb_forward(self, P, save, want_dense=False):
+        """Continuous position bias: MLP on the (2H-1)(2W-1) distinct offsets -> table [R, heads]. The tcgen05 attention
+        kernels read the table itself; the mma.sync kernels need it expanded to [heads, S, S] (+ fragment-ordered copies)."""
         g, dev = self.g, self.device
         R = self.cpb_x.shape[0]
         pre = "spatial_rel_pos_bias.net."
@@ -172,21 +184,28 @@ class CTViTEngine:
         ops.sgemm(self.cpb_x, P[pre + "0.0.weight"], h1, M=R, N=g.dim, K=2, trans_b=True, bias=P[pre + "0.0.bias"], act=1)
         ops.sgemm(h1, P[pre + "1.0.weight"], h2, M=R, N=g.dim, K=g.dim, trans_b=True, bias=P[pre + "1.0.bias"], act=1)
         ops.sgemm(h2, P[pre + "2.weight"], tab, M=R, N=g.heads, K=g.dim, trans_b=True, bias=P[pre + "2.bias"])
-        bias = torch.empty(g.heads, g.S, g.S, dtype=torch.bfloat16, device=dev)     # natural layout: dbias kernel, taps
-        ops.cpb_expand(tab, g.heads, g.H, g.W, bias, None)
-        nfrag = ops.frag_elems(g.heads, g.S)
-        bias_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)             # MMA-fragment order (fwd / dQ)
-        bias_t_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)           # transposed, fragment order (dK/dV)
-        ops.cpb_expand_frag(tab, g.heads, g.H, g.W, bias_frag, bias_t_frag)
-        return bias, (bias_frag, bias_t_frag), (h1, h2)
+        bias = frags = None
+        need_dense = not (self.tc_fwd and (self.tc_bwd or not save))
+        if need_dense or want_dense:
+            bias = torch.empty(g.heads, g.S, g.S, dtype=torch.bfloat16, device=dev)     # natural layout: dbias kernel, taps
+            ops.cpb_expand(tab, g.heads, g.H, g.W, bias, None)
+        if need_dense:
+            nfrag = ops.frag_elems(g.heads, g.S)
+            bias_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)             # MMA-fragment order (fwd / dQ)
+            bias_t_frag = torch.empty(nfrag, dtype=torch.bfloat16, device=dev)           # transposed, fragment order (dK/dV)
+            ops.cpb_expand_frag(tab, g.heads, g.H, g.W, bias_frag, bias_t_frag)
+            frags = (bias_frag, bias_t_frag)
+        return tab, bias, frags, (h1, h2)
 
-    def _cpb_backward(self, P, G, dbias, hs):
+    def _cpb_backward(self, P, G, dbias, hs, dtab=None):
+        """dbias: fp32 [heads,S,S] (mma.sync path) or None with dtab [R, heads] already reduced (tcgen05 path)."""
         g, dev = self.g, self.device
         R = self.cpb_x.shape[0]
         pre = "spatial_rel_pos_bias.net."
         h1, h2 = hs
-        dtab = torch.empty(R, g.heads, device=dev)
-        ops.cpb_reduce(dbias, g.heads, g.H, g.W, dtab)
+        if dtab is None:
+            dtab = torch.empty(R, g.heads, device=dev)
+            ops.cpb_reduce(dbias, g.heads, g.H, g.W, dtab)
         # layer 2: tab = h2 W2^T + b2
         ops.sgemm(dtab, h2, G[pre + "2.weight"], M=g.heads, N=g.dim, K=R, trans_a=True, accumulate=True)
         ops.colsum(dtab, G[pre + "2.bias"], M=R, N=g.heads)
@@ -200,7 +219,7 @@ class CTViTEngine:
         ops.colsum(dh1, G[pre + "0.0.bias"], M=R, N=g.dim)
 
     # ------------------------------------------------------------------------------------------
-    def _layer_forward(self, x, P, pre, lw, b, T, temporal, bias, save, frags=None):
+    def _layer_forward(self, x, P, pre, lw, b, T, temporal, bias, save, frags=None, tab=None):
         """x: fp32 stream [M, D] (consumed). Returns (new stream, saved-or-None)."""
         g, dev = self.g, self.device
         M, D, I, Fp = x.shape[0], g.dim, g.inner, g.ff_pad
@@ -224,8 +243,12 @@ class CTViTEngine:
         o = torch.empty(M, I, **bf)
         lse = torch.empty(M, g.heads, device=dev) if save else None
         v = kv_raw[:, I:]
-        ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, bias_frag=frags[0] if frags else None,
-                     bias_t_frag=frags[1] if frags else None, **self._attn_geom(b, T, temporal))
+        if tab is not None and self.tc_fwd and not temporal and (self.tc_bwd or not save):     # tcgen05 / TMEM kernel, bias from the table
+            ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, cpb_table=tab, grid_hw=(g.H, g.W), qk_bound=lw.qkb,
+                         **self._attn_geom(b, T, temporal))
+        else:
+            ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, bias=bias, bias_frag=frags[0] if frags else None,
+                         bias_t_frag=frags[1] if frags else None, **self._attn_geom(b, T, temporal))
         ops.gemm(o, lw.wo, M=M, N=D, K=I, epilogue=ops.EPI_RESID_F32, C_out=x1, resid=x1)          # x2 (in place)
         xhat2 = torch.empty(M, D, **bf)
         rstd2 = torch.empty(M, device=dev) if save else None
@@ -263,13 +286,14 @@ class CTViTEngine:
             taps["patch_tokens"] = x.clone()
         ctx.update(xhat_p=xhat_p if save else None, xhat3=xhat3, rstd3=rstd3)
         # --- spatial stack (ctvit.py:291-297)
-        bias, bias_t, cpb_h = self._cpb_forward(P, save)
+        tab, bias, bias_t, cpb_h = self._cpb_forward(P, save, want_dense=taps is not None)
         if taps is not None:
             taps["cpb_bias"] = bias.float()
-        ctx.update(bias=bias, bias_t=bias_t, cpb_h=cpb_h if save else None)
+        ctx.update(bias=bias, bias_t=bias_t, cpb_tab=tab, cpb_h=cpb_h if save else None)
         saved_s, saved_t = [], []
         for i, lw in enumerate(self.spatial_w):
-            x, sv = self._layer_forward(x, P, f"enc_spatial_transformer.layers.{i}.", lw, b, T, False, bias, save, frags=bias_t)
+            x, sv = self._layer_forward(x, P, f"enc_spatial_transformer.layers.{i}.", lw, b, T, False, bias, save, frags=bias_t,
+                                        tab=tab)
             saved_s.append(sv)
             if taps is not None:
                 taps[f"spatial.{i}"] = x.clone()
@@ -320,7 +344,7 @@ class CTViTEngine:
         ops.gemm(dY, X, M=n_out, N=k_out, K=rows, a_major=1, b_major=1, epilogue=ops.EPI_ATOMIC_F32, C_out=out,
                  ldc=ld_out if ld_out is not None else out.stride(0), splits=ops.wgrad_splits(rows, tiles))
 
-    def _layer_backward(self, dres, dxb, sv, P, G, pre, lw, b, T, temporal, bias, bias_t, dbias):
+    def _layer_backward(self, dres, dxb, sv, P, G, pre, lw, b, T, temporal, bias, bias_t, dbias, tab=None, dtab=None):
         """dres: fp32 [M,D] gradient w.r.t. the layer output (consumed); dxb: its bf16 copy.
         Returns (gradient w.r.t. the layer input fp32, its bf16 copy)."""
         g, dev = self.g, self.device
@@ -356,11 +380,16 @@ class CTViTEngine:
         dqh = torch.empty(M, I, **bf)
         dkv = torch.empty(M, 2 * I, **bf)       # [dk_hat | dv]
         delta = torch.empty(M, g.heads, device=dev)
-        ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
-                     ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias,
-                     bias_frag=bias_t[0] if bias_t else None, bias_t_frag=bias_t[1] if bias_t else None,
-                     dbias=dbias, ds_scratch=self._ds_scratch(b, T) if dbias is not None else None,
-                     **self._attn_geom(b, T, temporal))
+        if dtab is not None:      # tcgen05 / TMEM kernel: one pass, table gradient accumulated into dtab
+            ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
+                         ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(g.H, g.W),
+                         dcpb_table=dtab, ds_scratch=self._ds_scratch(b, T), **self._attn_geom(b, T, temporal))
+        else:
+            ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
+                         ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, bias=bias,
+                         bias_frag=bias_t[0] if bias_t else None, bias_t_frag=bias_t[1] if bias_t else None,
+                         dbias=dbias, ds_scratch=self._ds_scratch(b, T) if dbias is not None else None,
+                         **self._attn_geom(b, T, temporal))
         # ---- l2norm * scale backward (attention.py:152-154); dq/dk overwritten with raw-projection gradients
         ops.l2norm_bwd(dqh, I, sv.q_raw, I, P[a + "q_scale"], dqh, I, G[a + "q_scale"], M, g.heads)
         ops.l2norm_bwd(dkv, 2 * I, sv.kv_raw, 2 * I, P[a + "k_scale"], dkv, 2 * I, G[a + "k_scale"], M, g.heads)
@@ -400,12 +429,17 @@ class CTViTEngine:
         ops.ln_bwd(M, D, g_f32=dres, gamma=P["enc_spatial_transformer.norm_out.gamma"], xhat=ctx["xhat_ns"],
                    rstd=ctx["rstd_ns"], dx_f32=d2, dx_bf16=dxb, dgamma=G["enc_spatial_transformer.norm_out.gamma"])
         dres = d2
-        dbias = torch.zeros(g.heads, g.S, g.S, device=dev)
+        dbias = dtab = None
+        if self.tc_bwd:
+            dtab = torch.zeros(self.cpb_x.shape[0], g.heads, device=dev)
+        else:
+            dbias = torch.zeros(g.heads, g.S, g.S, device=dev)
         for i in reversed(range(g.spatial_depth)):
             dres, dxb = self._layer_backward(dres, dxb, ctx["saved_s"][i], P, G, f"enc_spatial_transformer.layers.{i}.",
-                                             self.spatial_w[i], b, T, False, ctx["bias"], ctx["bias_t"], dbias)
+                                             self.spatial_w[i], b, T, False, ctx["bias"], ctx["bias_t"], dbias,
+                                             tab=ctx["cpb_tab"], dtab=dtab)
             ctx["saved_s"][i] = None
-        self._cpb_backward(P, G, dbias, ctx["cpb_h"])
+        self._cpb_backward(P, G, dbias, ctx["cpb_h"], dtab=dtab)
         # patch embedding: x = LN_D(xhat_p Wp'^T + bp')
         ops.ln_bwd(M, D, g_f32=dres, gamma=P["to_patch_emb.3.weight"], xhat=ctx["xhat3"], rstd=ctx["rstd3"], dx_bf16=dxb,
                    dgamma=G["to_patch_emb.3.weight"], dbeta=G["to_patch_emb.3.bias"])

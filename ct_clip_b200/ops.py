@@ -150,8 +150,13 @@ def peg_bwd_weight(x, dy, dweight, dbias, **kw):
 
 
 def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
-               bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None, bias_frag=None, bias_t_frag=None):
+               bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None, bias_frag=None, bias_t_frag=None,
+               cpb_table=None, grid_hw=None, qk_bound=None):
+    """cpb_table (fp32 [(2h-1)(2w-1), heads]) + grid_hw=(h, w) select the tcgen05 / TMEM kernels (csrc/attention_tc.cu)."""
     a = AttnArgs()
+    if cpb_table is not None:
+        a.cpb_table, a.qk_bound = cpb_table.data_ptr(), _ptr(qk_bound)
+        a.grid_h, a.grid_w = grid_hw
     a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv
     a.o, a.ldo, a.lse = o.data_ptr(), ldo, _ptr(lse)
     a.bias, a.bias_t = _ptr(bias), _ptr(bias_t)
@@ -168,26 +173,33 @@ def _attn_flops(kw):
 
 
 def attn_fwd(q, k, v, o, lse, **kw):
-    call("ctclip_attn_fwd", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream(), tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}",
-         work=("F", _attn_flops(kw)))
+    call("ctclip_attn_fwd", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream(),
+         tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}" + (" tc" if kw.get("cpb_table") is not None else ""), work=("F", _attn_flops(kw)))
 
 
-def attn_fwd_tc(q, k, v, o, lse, **kw):
-    """EXPERIMENTAL tcgen05 / TMEM forward (csrc/attention_tc.cu): not part of the default path."""
-    call("ctclip_attn_fwd_tc", C.byref(_attn_args(q, k, v, o, lse, **kw)), _stream(), tag=f"tc n{kw['n']}",
-         work=("F", _attn_flops(kw)))
+def attn_tc_supported(n, grid_h, grid_w, dim_head=32) -> int:
+    """bit 0: the tcgen05 forward kernel takes this geometry, bit 1: the tcgen05 backward kernel does."""
+    return int(_lib.lib().ctclip_attn_tc_supported(n, grid_h, grid_w, dim_head))
 
 
-def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, ds_scratch=None, **kw):
+def qk_bound(q_scale, k_scale, out, dim_head=32):
+    """out[0] = max_d |q_scale_d * k_scale_d| (the logit bound of the fixed-reference softmax of the tcgen05 kernels)."""
+    call("ctclip_qk_bound", q_scale.data_ptr(), k_scale.data_ptr(), dim_head, out.data_ptr(), _stream())
+
+
+def attn_bwd(q, k, v, o, lse, d_o, delta, dq, dk, dv, *, ld_dq, ld_dk, ld_dv, total_rows, dbias=None, ds_scratch=None,
+             dcpb_table=None, **kw):
     a = _attn_args(q, k, v, o, lse, **kw)
     a.ds_scratch = _ptr(ds_scratch)
+    a.dcpb_table = _ptr(dcpb_table)
     a.d_o, a.delta = d_o.data_ptr(), delta.data_ptr()
     a.dq, a.ld_dq, a.dk, a.ld_dk, a.dv, a.ld_dv = dq.data_ptr(), ld_dq, dk.data_ptr(), ld_dk, dv.data_ptr(), ld_dv
     a.dbias = _ptr(dbias)
     a.total_rows = total_rows
     # algorithmic backward = 5 contractions (S, dP, dV, dQ, dK) = 2.5x the forward (the three kernels recompute S/dP)
-    call("ctclip_attn_bwd", C.byref(a), _stream(), tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}" + (" +dbias" if dbias is not None else ""),
-         work=("F", 2.5 * _attn_flops(kw)))
+    call("ctclip_attn_bwd", C.byref(a), _stream(),
+         tag=f"n{kw['n']} dh{kw.get('dim_head', 32)}" + (" tc" if kw.get("cpb_table") is not None else "")
+         + (" +dbias" if (dbias is not None or dcpb_table is not None) else ""), work=("F", 2.5 * _attn_flops(kw)))
 
 
 def l2norm_bwd(dxh, ld_dxh, xraw, ld_x, scale, dx, ld_dx, dscale, rows, heads, dim_head=32):

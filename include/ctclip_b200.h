@@ -217,12 +217,28 @@ typedef struct {
   /* optional scratch, bf16 [num_seqs*heads, n, n] (n even): with dbias, the dQ kernel spills its d logits there and a
    * streaming reduction over the sequences replaces the third (recomputing) backward pass */
   uint16_t* ds_scratch;
+  /* tcgen05 / TMEM path (csrc/attention_tc.cu), selected by cpb_table != NULL; the spatial stack of CTViT, where the
+   * sequence is the grid_h x grid_w token grid of one frame (n == grid_h*grid_w, contiguous sequences, dim_head 32, no key
+   * mask) and the bias is the continuous position bias of attention.py:245-282:
+   *   cpb_table  fp32 [(2*grid_h-1)*(2*grid_w-1), heads]: bias[h,i,j] = cpb_table[rel(i,j), h] with
+   *              rel(i,j) = (yi-yj+grid_h-1)*(2*grid_w-1) + (xi-xj+grid_w-1)  (what ctclip_cpb_expand expands); bias,
+   *              bias_t, bias_frag, bias_t_frag are ignored on this path;
+   *   qk_bound   device scalar >= max_d |q_scale_d * k_scale_d| (NULL: 1): with unit-norm q_hat/q_scale, k_hat/k_scale it bounds
+   *              |q_hat . k_hat|, which lets the kernels use a fixed softmax reference instead of an online maximum;
+   *   dcpb_table backward: fp32 [(2*grid_h-1)*(2*grid_w-1), heads], ACCUMULATED gradient w.r.t. cpb_table (replaces dbias;
+   *              needs ds_scratch, bf16 [num_seqs*heads, n, n]).
+   * ctclip_attn_tc_supported() tells whether a geometry can take this path. */
+  const float* cpb_table;
+  int32_t grid_h, grid_w;
+  const float* qk_bound;
+  float* dcpb_table;
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
-/* EXPERIMENTAL (not used by the default path, not yet run on hardware -- see csrc/attention_tc.cu): the same forward
- * with tcgen05.mma / TMEM for both contractions; dim_head 32, n % 64 == 0, n <= 768, natural-layout bias, no key mask. */
-int ctclip_attn_fwd_tc(const ctclip_attn_args* args, void* stream);
+/* bit 0: the tcgen05 forward kernel takes this geometry; bit 1: the tcgen05 backward kernel does (NOT an error code) */
+int ctclip_attn_tc_supported(int32_t n, int32_t grid_h, int32_t grid_w, int32_t dim_head);
+/* out[0] = max_d |q_scale[d] * k_scale[d]|  (attention.py:131-132 parameters): the qk_bound of ctclip_attn_args */
+int ctclip_qk_bound(const float* q_scale, const float* k_scale, int32_t dim_head, float* out, void* stream);
 
 /* Backward of x_hat = x/max(||x||,1e-12)*scale per (row, head) (attention.py:152-154):
  * dxh, xraw, dx: bf16 [rows, heads*32]; dscale[32] accumulated. */
