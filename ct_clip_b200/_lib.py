@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("epilogue", I32), ("splits", I32),
         ("C", P), ("ldc", I64), ("bias", P), ("resid", P), ("ldr", I64),
         ("C2", P), ("ldc2", I64), ("arg_out", P), ("argval_out", P),
-        ("norm_cols", I32), ("norm_scale", P), ("colsum", P),
+        ("norm_cols", I32), ("norm_scale", P), ("colsum", P), ("arg2_out", P),
     ]
 
 
@@ -107,6 +107,7 @@ SIGNATURES = {
     "ctclip_cpb_expand_frag": [P, I32, I32, I32, P, P, P],
     "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
+    "ctclip_vq_rerank": [P, P, P, P, I64, I32, P],
     "ctclip_vq_gather": [P, P, P, I64, I32, P],
     "ctclip_vq_gather_pool": [P, P, I32, I32, I32, I32, P, P, P],
     "ctclip_pool_bwd": [P, I32, I32, I32, I32, P, P],
@@ -151,12 +152,15 @@ def lib() -> C.CDLL:
 # bench.py sets this to a list to collect (entry point, tag, work, start_event, end_event) per call (per-stage roofline
 # table); work = ("B", algorithmic bytes) | ("F", algorithmic flops) | None. Never enabled inside a timed region.
 STAGE_TIMER = None
+# optional predicate (name, tag) -> bool: record only matching calls (bench.py times the dominant stage + the GEMM family INSIDE
+# its timed region with it; None = record every call)
+STAGE_FILTER = None
 
 
 def call(name: str, *args, tag=None, work=None) -> None:
     """Invoke an entry point; raise CtclipError with the library's message on failure."""
     global launch_count
-    if STAGE_TIMER is not None:
+    if STAGE_TIMER is not None and (STAGE_FILTER is None or STAGE_FILTER(name, tag)):
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

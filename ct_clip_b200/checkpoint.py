@@ -102,6 +102,10 @@ class AsyncCheckpointWriter:
             with torch.cuda.stream(self._stream):
                 for n, t in tensors.items():
                     staged[n] = self._host_buffer(n, t).copy_(t.detach(), non_blocking=True) if torch.is_tensor(t) else t
+                    if torch.is_tensor(t) and t.is_cuda:
+                        # the caller may drop `t` (a clone made on the compute stream) as soon as save() returns: tell the caching
+                        # allocator that this side stream still reads it, or the block could be re-used under the queued copy
+                        t.record_stream(self._stream)
                 event = torch.cuda.Event()
                 event.record(self._stream)
             self.copy_event = event

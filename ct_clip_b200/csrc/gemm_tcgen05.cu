@@ -43,6 +43,7 @@ struct GemmKParams {
   long long ldc2;
   int* arg_out;
   float* argval_out;
+  int* arg2_out;   // ARGMAX: optional runner-up index per row (fp32 re-ranking of the bf16 top-2, ctclip_vq_rerank)
   int norm_cols;
   const float* norm_scale;
   int fast_store;  // all output / residual rows are 16-byte aligned: staged, fully coalesced epilogue stores
@@ -695,8 +696,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const long long row0 = (long long)m_blk * BM + q * 32;   // first row of this warp
       const int rows_valid = (int)max(0LL, min(32LL, (long long)p.M - row0));
       uint8_t* st = stage_all + (warp - 2) * 2048;
-      float best_v = -INFINITY;
-      int best_i = 0;
+      float best_v = -INFINITY, sec_v = -INFINITY;
+      int best_i = 0, sec_i = 0;
+      const bool top2 = p.arg2_out != nullptr;   // kernel-uniform
       for (int j = 0; j < p.n_per_unit; j++, it++) {
         const int n_blk = ng * p.n_per_unit + j;
         const uint32_t acc = it & 1;
@@ -746,9 +748,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
           if (p.epi == EPI_ARGMAX) {
+            if (!top2) {
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-              if (i < ncols && v[i] > best_v) { best_v = v[i]; best_i = col0 + i; }
+              for (int i = 0; i < 32; i++)
+                if (i < ncols && v[i] > best_v) { best_v = v[i]; best_i = col0 + i; }
+            } else {   // running top-2 (first maximum wins ties, like torch.argmax)
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                if (i < ncols) {
+                  const float x = v[i];
+                  if (x > best_v) { sec_v = best_v; sec_i = best_i; best_v = x; best_i = col0 + i; }
+                  else if (x > sec_v) { sec_v = x; sec_i = col0 + i; }
+                }
+              }
+            }
             continue;
           }
           if (fast) {   // warp-uniform: every lane takes part in the shared-memory bounce
@@ -904,15 +917,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (p.epi == EPI_ARGMAX) {
         // merge the two column-halves of every row (first maximum wins, like torch.argmax)
         const int rit = q * 32 + lane;
+        float* merge2 = reinterpret_cast<float*>(stage_all);   // [128][2] runner-up (value, index): the store staging buffers are idle here
         if (half == 1) {
           arg_merge[2 * rit] = best_v;
           arg_merge[2 * rit + 1] = __int_as_float(best_i);
+          if (top2) {
+            merge2[2 * rit] = sec_v;
+            merge2[2 * rit + 1] = __int_as_float(sec_i);
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
         if (half == 0 && row_ok) {
           const float ov = arg_merge[2 * rit];
           const int oi = __float_as_int(arg_merge[2 * rit + 1]);
-          if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+          if (top2) {
+            // merge two sorted pairs (a1 >= a2), (b1 >= b2); earlier index wins ties
+            const float o2v = merge2[2 * rit];
+            const int o2i = __float_as_int(merge2[2 * rit + 1]);
+            auto before = [](float xv, int xi, float yv, int yi) { return xv > yv || (xv == yv && xi < yi); };
+            if (before(ov, oi, best_v, best_i)) {   // other half holds the winner: runner-up = better of (its second, our best)
+              if (before(o2v, o2i, best_v, best_i)) { sec_v = o2v; sec_i = o2i; }
+              else { sec_v = best_v; sec_i = best_i; }
+              best_v = ov; best_i = oi;
+            } else if (before(ov, oi, sec_v, sec_i)) { sec_v = ov; sec_i = oi; }
+            p.arg2_out[row] = sec_i;
+          } else if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
           p.arg_out[row] = best_i;
           if (p.argval_out != nullptr) p.argval_out[row] = best_v;
         }
@@ -1057,7 +1086,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   p.bias = a->bias;
   p.resid = a->resid; p.ldr = a->ldr;
   p.C2 = a->C2; p.ldc2 = a->ldc2;
-  p.arg_out = a->arg_out; p.argval_out = a->argval_out;
+  p.arg_out = a->arg_out; p.argval_out = a->argval_out; p.arg2_out = a->arg2_out;
   p.norm_cols = a->norm_cols; p.norm_scale = a->norm_scale;
   p.colsum = a->colsum;
   {

@@ -497,6 +497,31 @@ __global__ void zero_shot_probs_kernel(const float* __restrict__ img, const floa
   }
 }
 
+// warp per token: fp32 scores of the two bf16-GEMM candidates, x . e / ||e|| (the token norm is a common positive factor)
+__global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict__ x, const float* __restrict__ embed,
+                                                        int* __restrict__ idx, const int* __restrict__ idx2, long long M, int D) {
+  const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int c1 = idx[m], c2 = idx2[m];
+  const float4* xr = reinterpret_cast<const float4*>(x + m * D);
+  const float4* e1 = reinterpret_cast<const float4*>(embed + (long long)c1 * D);
+  const float4* e2 = reinterpret_cast<const float4*>(embed + (long long)c2 * D);
+  float d1 = 0.f, d2 = 0.f, n1 = 0.f, n2 = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 a = xr[i], b = __ldg(e1 + i), c = __ldg(e2 + i);
+    d1 += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    d2 += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+    n1 += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    n2 += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+  }
+  d1 = warp_sum(d1); d2 = warp_sum(d2); n1 = warp_sum(n1); n2 = warp_sum(n2);
+  if (lane == 0) {
+    const float s1 = d1 / fmaxf(sqrtf(n1), 1e-12f), s2 = d2 / fmaxf(sqrtf(n2), 1e-12f);
+    if (s2 > s1 || (s2 == s1 && c2 < c1)) idx[m] = c2;
+  }
+}
+
 }  // namespace ctb
 
 using namespace ctb;
@@ -591,6 +616,14 @@ extern "C" int ctclip_l2norm_rows_bf16(const float* x, void* y, int32_t rows, in
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(x && y && rows > 0 && D > 0, "l2norm_rows: bad args");
   l2norm_rows_bf16_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), rows, D);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_vq_rerank(const float* x, const float* embed, int32_t* idx, const int32_t* idx2, int64_t M, int32_t D,
+                                void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && embed && idx && idx2 && M > 0 && D > 0 && D % 4 == 0, "vq_rerank: bad args");
+  vq_rerank_kernel<<<ceil_div(M * 32, 256), 256, 0, stream>>>(x, embed, idx, idx2, M, D);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

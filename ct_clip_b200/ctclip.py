@@ -278,7 +278,9 @@ class CTCLIP(nn.Module):
         d_t, d_i = st.d_t_raw, st.d_i_raw
         if gscale != 1.0:
             d_t, d_i = d_t * gscale, d_i * gscale      # scalar rescale of two [b, L] tensors (loss weighting)
-        G["temperature"].add_(st.dtemp.view(()), alpha=gscale)   # one scalar
+        # one scalar. Under data parallelism every rank evaluates d loss / d temperature over the WHOLE global similarity matrix
+        # (the tower gradients are row-partitioned, this one is not) and the arena is SUM-all-reduced: take 1/world of it here.
+        G["temperature"].add_(st.dtemp.view(()), alpha=gscale / max(1, self.dp_world))
         # text projection: t_raw = cls Wt^T
         ops.sgemm(d_t, st.cls32, G["to_text_latent.weight"], M=L, N=self.dim_text, K=b, trans_a=True, accumulate=True)
         dcls = torch.empty(b, self.dim_text, device=dev)

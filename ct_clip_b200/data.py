@@ -8,10 +8,15 @@ from __future__ import annotations
 import torch
 
 
-def cycle(dl):  # scripts/CTCLIPTrainer.py:55-58
+def cycle(dl, on_epoch=None):  # scripts/CTCLIPTrainer.py:55-58
+    """on_epoch(epoch) is called before each pass (DistributedSampler.set_epoch: a different shuffle per epoch)."""
+    epoch = 0
     while True:
+        if on_epoch is not None:
+            on_epoch(epoch)
         for data in dl:
             yield data
+        epoch += 1
 
 
 class SyntheticCTReportDataset(torch.utils.data.Dataset):

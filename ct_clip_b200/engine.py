@@ -319,8 +319,12 @@ class CTViTEngine:
                    y_f32=y, y_bf16=yb, xhat=xhat_nt, rstd=rstd_nt)
         del x
         # --- vector quantiser lookup (ctvit.py:403): argmax of cosine similarity fused in the GEMM epilogue
+        # (bf16 operands decide ~5 % of the near-ties differently from the fp32 quantiser: the epilogue also reports the runner-up
+        # and ctclip_vq_rerank re-ranks the pair in fp32 against the un-rounded token and code-book rows)
         idx = torch.empty(M, dtype=torch.int32, device=dev)
-        ops.gemm(yb, self.ehat, M=M, N=g.codebook_size, K=D, epilogue=ops.EPI_ARGMAX, arg_out=idx)
+        idx2 = torch.empty(M, dtype=torch.int32, device=dev)
+        ops.gemm(yb, self.ehat, M=M, N=g.codebook_size, K=D, epilogue=ops.EPI_ARGMAX, arg_out=idx, arg2_out=idx2)
+        ops.vq_rerank(y, P["vq._codebook.embed"], idx, idx2, M, D)
         ctx.update(saved_s=saved_s, saved_t=saved_t, xhat_ns=xhat_ns, rstd_ns=rstd_ns, xhat_nt=xhat_nt, rstd_nt=rstd_nt,
                    pre_vq=y, idx=idx)
         return ctx

@@ -15,10 +15,6 @@ from ._lib import (EPI_ARGMAX, EPI_ATOMIC_F32, EPI_BF16, EPI_BIAS_GELU, EPI_F32,
                    SgemmArgs, call)
 
 
-# bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per GEMM launch
-GEMM_TIMER = None
-
-
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -30,7 +26,7 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, bias=None, resid=None, C2=None,
          arg_out=None, argval_out=None, splits=1, lda=None, ldb=None, ldc=None, ldc2=None, norm_cols=0,
-         norm_scale=None, colsum=None):
+         norm_scale=None, colsum=None, arg2_out=None):
     """C[M,N] = sum_k A(m,k) B(n,k); see include/ctclip_b200.h for the epilogues."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
     a = GemmArgs()
@@ -48,18 +44,12 @@ def gemm(A, B, *, M, N, K, a_major=0, b_major=0, epilogue=EPI_BF16, C_out=None, 
     a.ldc2 = ldc2 if ldc2 is not None else (C2.stride(0) if C2 is not None else 0)
     a.arg_out = _ptr(arg_out)
     a.argval_out = _ptr(argval_out)
+    a.arg2_out = _ptr(arg2_out)
     a.norm_cols = norm_cols
     a.norm_scale = _ptr(norm_scale)
     a.colsum = _ptr(colsum)
-    if GEMM_TIMER is None:
-        call("ctclip_gemm_bf16", C.byref(a), _stream(), tag=f"{M}x{N}x{K} a{a_major}b{b_major} epi{epilogue} s{splits}",
-             work=("FB", 2.0 * M * N * K, _gemm_bytes(M, N, K, epilogue, norm_cols, C_out is not None)))
-    else:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        call("ctclip_gemm_bf16", C.byref(a), _stream())
-        e1.record()
-        GEMM_TIMER.append((e0, e1, 2.0 * M * N * K, (M, N, K, a_major, b_major, epilogue, splits)))
+    call("ctclip_gemm_bf16", C.byref(a), _stream(), tag=f"{M}x{N}x{K} a{a_major}b{b_major} epi{epilogue} s{splits}",
+         work=("FB", 2.0 * M * N * K, _gemm_bytes(M, N, K, epilogue, norm_cols, C_out is not None)))
 
 
 def _gemm_bytes(M, N, K, epilogue, norm_cols, has_c):
@@ -259,6 +249,12 @@ def geglu_bwd(dg, h, *, M, n_pairs, colsum_out=None, ld_dg=None, ld_h=None):
 
 def l2norm_rows_bf16(x, y, rows, D):
     call("ctclip_l2norm_rows_bf16", x.data_ptr(), y.data_ptr(), rows, D, _stream())
+
+
+def vq_rerank(x, embed, idx, idx2, M, D):
+    """fp32 re-ranking of the bf16 argmax GEMM's top-2 code candidates (in place on idx)."""
+    call("ctclip_vq_rerank", x.data_ptr(), embed.data_ptr(), idx.data_ptr(), idx2.data_ptr(), M, D, _stream(),
+         work=("B", float(M) * D * 4))
 
 
 def vq_gather(idx, embed, out, M, D):

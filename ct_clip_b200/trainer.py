@@ -126,9 +126,20 @@ class CTClipTrainer(nn.Module):
             train_dataset = load_reference_dataset(data_train, reports_file_train, train_meta_file)
         self.ds = train_dataset
         self.valid_ds = valid_dataset
-        self.dl = torch.utils.data.DataLoader(self.ds, num_workers=num_workers, batch_size=batch_size, shuffle=True,
-                                              pin_memory=True, collate_fn=getattr(self.ds, "collate", None))
-        self.dl_iter = cycle(self.dl)
+        if valid_dataset is not None or save_results_every not in (0, 1, None):
+            import warnings
+            warnings.warn("CTClipTrainer: the validation pass of CTCLIPTrainer.py:266-329 (AUROC on valid_dataset every "
+                          "save_results_every steps) is outside the hot-path build; valid_dataset / save_results_every are ignored")
+        # every rank draws a DISJOINT shard (accelerate.prepare(dl) does the same in the reference): identical batches on all
+        # ranks would put world-size copies of each (volume, report) pair into the all-gathered global batch = false negatives
+        self.sampler = None
+        if self.world > 1:
+            from torch.utils.data.distributed import DistributedSampler
+            self.sampler = DistributedSampler(self.ds, num_replicas=self.world, rank=self.rank, shuffle=True, drop_last=True)
+        self.dl = torch.utils.data.DataLoader(self.ds, num_workers=num_workers, batch_size=batch_size,
+                                              shuffle=self.sampler is None, sampler=self.sampler, pin_memory=True,
+                                              drop_last=self.world > 1, collate_fn=getattr(self.ds, "collate", None))
+        self.dl_iter = cycle(self.dl, on_epoch=self.sampler.set_epoch if self.sampler is not None else None)
         self._prefetcher = None
 
         # ---- flat arena over everything that can receive a gradient
@@ -177,14 +188,24 @@ class CTClipTrainer(nn.Module):
     def save(self, path):
         if not self.is_main:
             return
-        torch.save(dict(model=self.CTClip.state_dict(), optim=self.arena.state_dict()), path)
+        # parameters are views into ONE arena storage: clone them, or every entry would serialise the whole 1.1 GB storage
+        model = {k: v.detach().clone() for k, v in self.CTClip.state_dict().items()}
+        torch.save(dict(model=model, optim=self.arena.state_dict()), path)
 
     def load(self, path):
+        """Reads a package written by save(); a reference package (CTCLIPTrainer.py:210-217: 'optim' is a torch.optim.Adam
+        state dict keyed by parameter index) restores the model and leaves the Adam moments at zero, with a warning."""
         path = Path(path)
         assert path.exists()
         pkg = torch.load(path, map_location="cpu")
         self.CTClip.load_state_dict(pkg['model'])
-        self.arena.load_state_dict(pkg['optim'])
+        optim = pkg.get('optim')
+        if isinstance(optim, dict) and "names" in optim and "exp_avg" in optim:
+            self.arena.load_state_dict(optim)
+        elif optim is not None:
+            import warnings
+            warnings.warn("CTClipTrainer.load: optimizer state is not in the flat-arena format of this trainer (a "
+                          "torch.optim.Adam state dict from the reference?); model restored, Adam moments start from zero")
         self.CTClip.mark_weights_dirty()
 
     # ------------------------------------------------------------------------------------------
@@ -237,7 +258,7 @@ class CTClipTrainer(nn.Module):
             if self.async_checkpoints:
                 self._save_async(model_path)
             else:
-                torch.save(self.CTClip.state_dict(), model_path)
+                torch.save({k: v.detach().clone() for k, v in self.CTClip.state_dict().items()}, model_path)
             self.print(f'{steps}: saving model to {str(self.results_folder)}')
         self.steps += 1
         return logs

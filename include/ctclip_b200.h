@@ -50,7 +50,8 @@ const char* ctclip_last_error(void);
  *                                                           skipped if C == NULL)
  *                C2(bf16)[m,j] = gelu_erf(gate_j) * value_j
  *   4 ATOMIC_F32 C(f32)[m,n]  += acc      (red.global.add; with splits > 1 = split-K)
- *   5 ARGMAX     arg_out[m] = argmax_n acc (first max wins), argval_out[m] = max (optional)
+ *   5 ARGMAX     arg_out[m] = argmax_n acc (first max wins), argval_out[m] = max (optional), arg2_out[m] = index of the
+ *                runner-up (optional; ctclip_vq_rerank re-ranks the pair in fp32)
  *   6 L2NORM     per 32-column group (= one attention head, dim_head 32):
  *                C(bf16)[m,n]  = acc                      (raw q/k/v, optional)
  *                C2(bf16)[m,n] = acc / max(||acc_group||, 1e-12) * norm_scale[n % 32]   for n < norm_cols
@@ -82,6 +83,7 @@ typedef struct {
   int32_t norm_cols;
   const float* norm_scale;
   float* colsum;          /* GEGLU_BWD: [2N] column sums, accumulated */
+  int32_t* arg2_out;      /* ARGMAX: optional runner-up index */
 } ctclip_gemm_args;
 
 int ctclip_gemm_bf16(const ctclip_gemm_args* args, void* stream);
@@ -285,6 +287,10 @@ int ctclip_geglu_bwd(const void* dg, int64_t ld_dg, void* h, int64_t ld_h, int64
 /* Vector quantiser pieces (vector_quantize_pytorch==1.1.2 CosineSimCodebook, called at ctvit.py:403):
  * the argmax itself is GEMM epilogue 5 on (tokens, l2norm(embed)). */
 int ctclip_l2norm_rows_bf16(const float* x, void* y, int32_t rows, int32_t D, void* stream);
+/* fp32 re-ranking of the bf16 GEMM's top-2 candidates: idx[m] <- argmax over {idx[m], idx2[m]} of x[m,:] . embed[c,:] / ||embed[c,:]||
+ * (the cosine code-book's ranking, vector_quantize_pytorch 1.1.2 CosineSimCodebook.forward; first index wins ties).
+ * x fp32 [M, D] (the quantiser input), embed fp32 [C, D] (un-normalised master copy). */
+int ctclip_vq_rerank(const float* x, const float* embed, int32_t* idx, const int32_t* idx2, int64_t M, int32_t D, void* stream);
 int ctclip_vq_gather(const int32_t* idx, const float* embed, float* out, int64_t M, int32_t D, void* stream);
 int ctclip_vq_gather_pool(const int32_t* idx, const float* embed, int32_t B, int32_t T, int32_t S, int32_t D,
                           float* pooled_f32, void* pooled_bf16, void* stream);   /* + ct_clip.py:724 mean over t */

@@ -122,3 +122,34 @@ def test_gemm_argmax():
     assert agree > 0.995, agree
     picked = ref.gather(1, idx.long()[:, None])[:, 0]
     assert ((rv - picked).abs() <= 1e-3 * rv.abs().max()).all()
+
+
+def test_gemm_argmax_top2_and_fp32_rerank():
+    """ARGMAX epilogue with the runner-up index + ctclip_vq_rerank: the pair must be the true top-2 of the bf16 scores, and
+    after the fp32 re-ranking the index must equal the fp32 cosine code-book argmax (vector_quantize_pytorch 1.1.2 ranking)
+    except where even the fp32 top-3 is closer than summation noise."""
+    from ct_clip_b200 import ops
+    M, C, D = 3000, 8192, 512
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(M, D, generator=g).cuda()                       # quantiser input (fp32)
+    embed = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=-1).cuda() * (0.8 + 0.4 * torch.rand(C, 1, generator=g).cuda())
+    xb = x.to(torch.bfloat16)
+    ehat = torch.empty(C, D, dtype=torch.bfloat16, device="cuda")
+    ops.l2norm_rows_bf16(embed, ehat, C, D)
+    idx = torch.empty(M, dtype=torch.int32, device="cuda")
+    idx2 = torch.empty(M, dtype=torch.int32, device="cuda")
+    ops.gemm(xb, ehat, M=M, N=C, K=D, epilogue=ops.EPI_ARGMAX, arg_out=idx, arg2_out=idx2)
+    torch.cuda.synchronize()
+    sb = xb.float() @ ehat.float().t()                               # the scores the GEMM ranks
+    top = sb.topk(3, dim=1)
+    got1, got2 = sb.gather(1, idx.long()[:, None])[:, 0], sb.gather(1, idx2.long()[:, None])[:, 0]
+    tol = 1e-3 * sb.abs().max()
+    assert (idx != idx2).all()
+    assert ((top.values[:, 0] - got1).abs() <= tol).all() and ((top.values[:, 1] - got2).abs() <= tol).all()
+    before = (idx.long() == (torch.nn.functional.normalize(x, dim=-1) @ torch.nn.functional.normalize(embed, dim=-1).t()).argmax(1)).float().mean().item()
+    ops.vq_rerank(x, embed, idx, idx2, M, D)
+    torch.cuda.synchronize()
+    ref = (torch.nn.functional.normalize(x, dim=-1) @ torch.nn.functional.normalize(embed, dim=-1).t()).argmax(1)
+    after = (idx.long() == ref).float().mean().item()
+    print(f"index agreement with the fp32 quantiser: {before:.4f} (bf16 argmax) -> {after:.4f} (top-2 + fp32 re-rank)")
+    assert after >= 0.998 and after >= before, (before, after)

@@ -1,0 +1,113 @@
+"""Parity at the BENCHMARK geometry (BASELINE.json configs[1]: 480x480 frames, patch (20,20,10), P = 4000 voxels per patch,
+S = 24x24 = 576 spatial tokens -- scripts/run_train.py:17-27, ctvit.py:170-175), which every other parity test leaves out
+(they use the 64x64x32 / patch 16/8 geometry of configs[0]). A 20-frame slab (T = 2) keeps the CPU oracle at a few seconds.
+This is the geometry that exercises: the 40-byte patch rows of the patchify kernel, the K = 4000 patch GEMM with the folded
+LayerNorm(P), the tcgen05 spatial attention kernels (S = 576, grid 24x24) and the CPB table gradient.
+"""
+import pytest
+import torch
+
+from tests.helpers import oracle_vit_cfg, rel_err, rms_err, temporal_to_canonical
+from tests.test_ctclip_gpu import _Tok, build_clip
+
+pytestmark = pytest.mark.gpu
+
+HEAD_VIT = dict(dim=512, codebook_size=8192, image_size=480, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+                temporal_depth=1, dim_head=32, heads=8)
+
+
+@pytest.mark.parametrize("dtype", ["int16", "f32"])
+def test_patchify_layernorm_p4000(dtype):
+    """ops.patchify (Rearrange + LayerNorm(P) standardisation, int16 HU -> x/1000 fused) at patch (20,20,10)."""
+    from ct_clip_b200 import ops
+    from oracle import ctclip_oracle as O
+    hu, _, _ = O.synth_inputs(2, 20, 480, 8)
+    video = hu.float() / 1000.0
+    b, c, f, Hh, Ww = video.shape
+    pt, p = 10, 20
+    t, h, w = f // pt, Hh // p, Ww // p
+    P = c * pt * p * p
+    x = video.reshape(b, c, t, pt, h, p, w, p).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(b * t * h * w, P)
+    ref = (x - x.mean(-1, keepdim=True)) / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    out = torch.empty(b * t * h * w, P, dtype=torch.bfloat16, device="cuda")
+    vin = hu.cuda() if dtype == "int16" else video.cuda()
+    ops.patchify(vin, out, B=b, Cc=c, F=f, H=Hh, W=Ww, pt=pt, p1=p, p2=p)
+    torch.cuda.synchronize()
+    assert rms_err(out, ref) < 4e-3, rms_err(out, ref)          # bf16 rounding of a unit-variance row: 2^-9 relative
+    assert rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", ["int16", "f32"])
+def test_ctvit_taps_headline_geometry(dtype):
+    from ct_clip_b200 import CTViT
+    from oracle import ctclip_oracle as O
+    kw = HEAD_VIT
+    vit = CTViT(**kw)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in vit.state_dict().items()}, 0)
+    vit.load_state_dict(sd, strict=True)
+    vit = vit.cuda().eval()
+    assert vit.engine.tc_fwd and vit.engine.tc_bwd, "the 24x24 grid must take the tcgen05 attention kernels"
+    hu, _, _ = O.synth_inputs(2, 20, 480, 8)
+    video = hu.float() / 1000.0
+    cfg = oracle_vit_cfg(kw)
+    sdo = {"visual_transformer." + k: v for k, v in sd.items()}
+    taps_o = {}
+    with torch.no_grad():
+        tok_o, ind_o, _ = O.ctvit_forward(video, sdo, "visual_transformer.", cfg, False, taps_o)
+    names, tensors = vit.named_live_tensors()
+    taps = {}
+    vin = hu.cuda() if dtype == "int16" else video.cuda()
+    with torch.no_grad():
+        ectx = vit._run_forward(vin, dict(zip(names, tensors)), save=False, taps=taps)
+    torch.cuda.synchronize()
+    b, T, H, W, D = 2, 2, 24, 24, 512
+    report = {}
+    report["patch_tokens"] = rms_err(taps["patch_tokens"].view(b, T, H, W, D), taps_o["patch_tokens"])
+    report["cpb_bias"] = rel_err(taps["cpb_bias"], taps_o["cpb_bias"])
+    ref = taps_o["visual_transformer.enc_spatial_transformer.layers.0.ff"].reshape(b, T, H, W, D)
+    report["spatial.0"] = rms_err(taps["spatial.0"].view(b, T, H, W, D), ref)
+    report["spatial_out"] = rms_err(taps["spatial_out"].view(b, T, H, W, D), taps_o["spatial_out"])
+    ref = temporal_to_canonical(taps_o["visual_transformer.enc_temporal_transformer.layers.0.ff"], b, H, W)
+    report["temporal.0"] = rms_err(taps["temporal.0"].view(b, T, H, W, D), ref)
+    report["pre_vq"] = rms_err(ectx["pre_vq"].view(b, T, H, W, D), taps_o["pre_vq"])
+    report["vq_index_agreement"] = (ectx["idx"].view(b, T, H, W).cpu().long() == ind_o).float().mean().item()
+    for k, v in report.items():
+        print(f"  {k:24s} {v:.5f}")
+    for k, v in report.items():
+        if k == "vq_index_agreement":
+            assert v >= 0.9, report
+        else:
+            assert v < 1e-2, (k, report)          # north_star: 1e-2 on the bf16 path
+
+
+def test_contrastive_step_headline_geometry():
+    """loss + every gradient (incl. the CPB MLP through the table-gradient path of the tcgen05 backward) vs the oracle."""
+    from oracle import ctclip_oracle as O
+    clip, sd, cfg = build_clip(HEAD_VIT, bert_layers=1)
+    hu, ids, mask = O.synth_inputs(2, 20, 480, 32)
+    video = hu.float() / 1000.0
+    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
+    out["loss"].backward()
+    clip.train()
+    clip.visual_transformer._force_indices = out["indices"]
+    loss = clip(_Tok(ids.cuda(), mask.cuda()), hu.cuda(), device="cuda", return_loss=True)     # int16 HU input, as bench.py
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - out["loss"].item()) < 1e-2 * abs(out["loss"].item()), (loss.item(), out["loss"].item())
+    gmax = max(v.grad.abs().max().item() for v in sdp.values() if v.is_floating_point() and v.grad is not None)
+    report = {}
+    for name, p in clip.named_parameters():
+        ref = sdp[name].grad
+        if ref is None or ref.numel() == 0 or ref.abs().max().item() < 1e-6 * gmax:
+            continue
+        assert p.grad is not None, f"missing gradient for {name}"
+        report[name] = rms_err(p.grad, ref)
+    worst = sorted(report.items(), key=lambda kv: -kv[1])[:10]
+    print("worst gradient rms errors:", [(k, round(v, 4)) for k, v in worst])
+    errs = sorted(report.values())
+    print("median / p90 / max gradient rms error:", errs[len(errs) // 2], errs[int(0.9 * len(errs))], errs[-1])
+    cpb = {k: v for k, v in report.items() if "spatial_rel_pos_bias" in k}
+    print("CPB MLP gradients:", {k.split("net.")[1]: round(v, 4) for k, v in cpb.items()})
+    assert errs[-1] < 3e-2, worst                  # 1+1 layers: every tensor within 3e-2 relative RMS
+    assert errs[len(errs) // 2] < 1.5e-2, errs[len(errs) // 2]

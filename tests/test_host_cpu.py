@@ -120,11 +120,15 @@ def _dp_worker(rank, world, port, b, L, ret):
     tg = torch.cat([tg[:r0], t_loc, tg[r0 + nr:]])
     ig = torch.cat([ig[:r0], i_loc, ig[r0 + nr:]])
     norm = torch.nn.functional.normalize
-    loss = O.clip_loss(norm(tg, dim=-1), norm(ig, dim=-1), torch.tensor(1.0))
+    temp = torch.tensor(1.3, requires_grad=True)       # the learned temperature (ct_clip.py:553): NOT row-partitioned
+    loss = O.clip_loss(norm(tg, dim=-1), norm(ig, dim=-1), temp)
     loss.backward()
     gw = Wl.grad.clone()
     dist.all_reduce(gw, op=dist.ReduceOp.SUM)          # gradients are SUMMED across ranks (not averaged)
-    ret[rank] = (loss.item(), t_loc.grad.clone(), gw)
+    # every rank holds d loss / d temperature of the WHOLE global matrix: CTCLIP._backward_into adds 1/world of it to the arena
+    gt = temp.grad.clone() / world
+    dist.all_reduce(gt, op=dist.ReduceOp.SUM)
+    ret[rank] = (loss.item(), t_loc.grad.clone(), gw, gt.item())
     dist.destroy_process_group()
 
 
@@ -179,13 +183,15 @@ def test_data_parallel_global_loss_two_ranks_gloo():
     T.requires_grad_(True)
     W.requires_grad_(True)
     norm = torch.nn.functional.normalize
-    loss = O.clip_loss(norm(T, dim=-1), norm(I @ W, dim=-1), torch.tensor(1.0))
+    temp = torch.tensor(1.3, requires_grad=True)
+    loss = O.clip_loss(norm(T, dim=-1), norm(I @ W, dim=-1), temp)
     loss.backward()
     for r in range(world):
-        l_r, dt_r, gw_r = ret[r]
+        l_r, dt_r, gw_r, gt_r = ret[r]
         assert abs(l_r - loss.item()) < 1e-6
         assert torch.allclose(dt_r, T.grad[r * b:(r + 1) * b], atol=1e-6)
         assert torch.allclose(gw_r, W.grad, atol=1e-5)
+        assert abs(gt_r - temp.grad.item()) < 1e-6      # the un-partitioned scalar must not be counted world times
 
 
 # ---------------------------------------------------------------------------------------------------------------
