@@ -16,6 +16,7 @@ P = C.c_void_p
 I32 = C.c_int32
 I64 = C.c_int64
 F32 = C.c_float
+U64 = C.c_uint64
 
 
 class CtclipError(RuntimeError):
@@ -62,7 +63,8 @@ class AttnArgs(C.Structure):
                 ("d_o", P), ("delta", P), ("dq", P), ("ld_dq", I64), ("dk", P), ("ld_dk", I64),
                 ("dv", P), ("ld_dv", I64), ("dbias", P), ("total_rows", I64), ("key_mask", P),
                 ("bias_frag", P), ("bias_t_frag", P), ("ds_scratch", P),
-                ("cpb_table", P), ("grid_h", I32), ("grid_w", I32), ("qk_bound", P), ("dcpb_table", P)]
+                ("cpb_table", P), ("grid_h", I32), ("grid_w", I32), ("qk_bound", P), ("dcpb_table", P),
+                ("dropout_p", F32), ("dropout_seed", U64), ("dropout_offset", U64)]
 
 
 class SgemmArgs(C.Structure):
@@ -107,6 +109,7 @@ SIGNATURES = {
     "ctclip_cpb_expand_frag": [P, I32, I32, I32, P, P, P],
     "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
+    "ctclip_dropout": [P, P, P, P, I64, F32, U64, U64, P],
     "ctclip_vq_rerank": [P, P, P, P, I64, I32, P],
     "ctclip_vq_gather": [P, P, P, I64, I32, P],
     "ctclip_vq_gather_pool": [P, P, I32, I32, I32, I32, P, P, P],

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rng.cuh"
 #include "../../include/ctclip_b200.h"
 
 namespace ctb {
@@ -261,6 +262,40 @@ __device__ __forceinline__ void logits_tile_full_regs(float (&s)[NT][4], float s
   }
 }
 
+
+// Attention-probability dropout (BERT): keep flags of the element pair (row, col), (row, col + 1) of item `item` (col even:
+// both elements sit in the same Philox group of 4). Returns the multipliers (0 or 1/(1-p)).
+struct AttnDrop {
+  unsigned long long seed, offset;
+  uint32_t thresh;
+  float inv_keep;
+  int n;
+  __device__ __forceinline__ float2 pair(long long item, int row, int col) const {
+    const unsigned long long idx = ((unsigned long long)item * n + row) * n + col;
+    uint32_t w[4];
+    philox4(seed, offset + (idx >> 2), w);
+    const int e = (int)(idx & 3);
+    float2 r;
+    r.x = (w[e] >= thresh) ? inv_keep : 0.f;
+    r.y = (w[(e + 1) & 3] >= thresh && e < 3) ? inv_keep : 0.f;   // e is 0 or 2 when n is even and col is even
+    return r;
+  }
+  __device__ __forceinline__ float one(long long item, int row, int col) const {
+    const unsigned long long idx = ((unsigned long long)item * n + row) * n + col;
+    uint32_t w[4];
+    philox4(seed, offset + (idx >> 2), w);
+    return (w[idx & 3] >= thresh) ? inv_keep : 0.f;
+  }
+};
+__device__ __forceinline__ AttnDrop make_attn_drop(const ctclip_attn_args& a) {
+  AttnDrop d;
+  d.seed = a.dropout_seed; d.offset = a.dropout_offset;
+  d.thresh = dropout_threshold(a.dropout_p);
+  d.inv_keep = 1.f / (1.f - a.dropout_p);
+  d.n = a.n;
+  return d;
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -273,7 +308,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int DH, int WPG, int GROUPS, bool MASK>
+template <int DH, int WPG, int GROUPS, bool MASK, bool DROP = false>
 __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -378,6 +413,18 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
         oacc[dt][0] *= corr_a; oacc[dt][1] *= corr_a;
         oacc[dt][2] *= corr_b; oacc[dt][3] *= corr_b;
       }
+      if (DROP) {   // the row sums above use the un-dropped probabilities (softmax first, dropout second)
+        const AttnDrop dr = make_attn_drop(a);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int c = key0 + nt * 8 + 2 * t;
+          if (c < a.n) {
+            const float2 ka = dr.pair(item, ra < a.n ? ra : 0, c), kb = dr.pair(item, rb < a.n ? rb : 0, c);
+            s[nt][0] *= ka.x; s[nt][1] *= ka.y;
+            s[nt][2] *= kb.x; s[nt][3] *= kb.y;
+          }
+        }
+      }
       // masked / beyond-n_pad keys carry p == 0 and V^T rows are zero-filled there
       if (full) pv_block<8, DH, true>(oacc, s, sV, key0, lane);
       else pv_block<8, DH>(oacc, s, sV, key0, lane, ntv);
@@ -405,7 +452,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, 2) attn_fwd_kernel(ctclip_at
 // ------------------------------------------------------------------------------------------------
 // backward, part 1 (query-row parallel): dq_hat.   dlogits = P * (dP - delta), dq = scale * dlogits K
 // ------------------------------------------------------------------------------------------------
-template <int DH, int WPG, int GROUPS, bool MASK>
+template <int DH, int WPG, int GROUPS, bool MASK, bool DROP = false>
 __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1) attn_bwd_dq_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -490,6 +537,18 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
         qk_block<4, DH>(dp, da, sV, key0, lane, ntv);
         logits_tile<4, MASK>(s, sc2, brow_a, brow_b, key0, t, a.n, key0 + 32 <= a.n, pair_ok, sMask, ntv, bfr);
       }
+      if (DROP) {   // dP is the gradient w.r.t. the DROPPED probabilities: d softmax-output = keep/(1-p) * dP
+        const AttnDrop dr = make_attn_drop(a);
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const int c = key0 + nt * 8 + 2 * t;
+          if (c < a.n) {
+            const float2 ka = dr.pair(item, ra < a.n ? ra : 0, c), kb = dr.pair(item, rb < a.n ? rb : 0, c);
+            dp[nt][0] *= ka.x; dp[nt][1] *= ka.y;
+            dp[nt][2] *= kb.x; dp[nt][3] *= kb.y;
+          }
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
@@ -532,7 +591,7 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32, (WPG * GROUPS <= 8) ? 2 : 1)
 // backward, part 2 (key-row parallel): dk_hat, dv.  Works on S^T = K Q^T so that P^T / dS^T come out
 // of the MMA in the register layout the next MMA needs as its A operand.
 // ------------------------------------------------------------------------------------------------
-template <int DH, int WPG, int GROUPS, bool MASK>
+template <int DH, int WPG, int GROUPS, bool MASK, bool DROP = false>
 __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_attn_args a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const AttnGeom g{a.n, a.heads, a.seq_inner, a.seq_outer_stride, a.tok_stride};
@@ -640,8 +699,13 @@ __global__ void __launch_bounds__(WPG* GROUPS * 32) attn_bwd_dkv_kernel(ctclip_a
         for (int e = 0; e < 4; e++) {
           const bool keep = (e < 2) ? keep_a : keep_b;
           const float p = keep ? fast_exp2(s[nt][e] - ((e & 1) ? l2.y : l2.x)) : 0.f;
-          s[nt][e] = p;                                                            // P^T
-          ds[nt][e] = p * (dp[nt][e] - ((e & 1) ? d2.y : d2.x));                   // dS^T w.r.t. the logits (scale applied to dk below)
+          float dmul = 1.f;
+          if (DROP) {   // element (query qr + (e&1), key ka_ / kb_) of the probability tensor
+            const int qq = qr + (e & 1), kk = (e < 2) ? ka_ : kb_;
+            dmul = (qq < a.n && kk < a.n) ? make_attn_drop(a).one(item, qq, kk) : 0.f;
+          }
+          s[nt][e] = p * dmul;                                                     // (dropped) P^T: dV = (P o M)^T dO
+          ds[nt][e] = p * (dp[nt][e] * dmul - ((e & 1) ? d2.y : d2.x));            // dS^T w.r.t. the logits (scale applied to dk below)
         }
       }
       if (full) {
@@ -1198,6 +1262,7 @@ static int attn_check(const ctclip_attn_args* a, const char* who) {
   CTB_CHECK_ARG(a->q && a->k && a->v, "%s: null q/k/v", who);
   CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0, "%s: q/k/v rows must be 16B aligned", who);
   CTB_CHECK_ARG(a->key_mask == nullptr || a->bias == nullptr, "%s: key_mask and bias are not combined on this path", who);
+  CTB_CHECK_ARG(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0, 1)", who);
   return CTCLIP_OK;
 }
 
@@ -1219,6 +1284,17 @@ static int launch_grouped(Kern kern, const ctclip_attn_args* a, size_t group_byt
 template <int DH, bool MASK>
 static int attn_dispatch(int which, const ctclip_attn_args* a, cudaStream_t stream) {
   const int n_pad = (a->n + 15) & ~15;
+  if (a->dropout_p > 0.f) {   // attention-probability dropout: the BERT shape only (64 < n <= 256, even n)
+    if (DH == 64 && a->n > 64 && a->n <= 256 && a->n % 2 == 0) {
+      const size_t mk2 = MASK ? (size_t)n_pad * 4 : 0;
+      const size_t g_f = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk2, g_kv = (size_t)(2 * n_pad * (DH + 8)) * 2 + (size_t)n_pad * 8;
+      if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
+      if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
+      return launch_grouped(attn_bwd_dkv_kernel<DH, 4, 2, MASK, true>, a, g_kv, 4, 2, stream);
+    }
+    set_error("attention: dropout_p > 0 is implemented for dim_head 64, 64 < n <= 256, even n (got dh %d, n %d)", DH, a->n);
+    return CTCLIP_ERR_UNSUPPORTED;
+  }
   const size_t mk = MASK ? (size_t)n_pad * 4 : 0;
   const size_t gb_fwd = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk;
   const size_t gb_dq = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk;

@@ -690,7 +690,8 @@ static int tc_grid_w(const ctclip_attn_args* a) { return a->grid_w; }
 extern "C" int ctclip_attn_tc_supported(int32_t n, int32_t grid_h, int32_t grid_w, int32_t dim_head) {
   if (dim_head != 32 || grid_h <= 0 || grid_w <= 0 || n != grid_h * grid_w) return 0;
   // bit 0: forward kernel, bit 1: backward kernel (its dQ accumulators need ceil(n/128)*32 <= 192 TMEM columns)
-  if (grid_w == 24 && n % 96 == 0 && n <= 1152) return 1 | ((n % 64 == 0 && (n + 127) / 128 * 32 <= 192) ? 2 : 0);
+  // (n % 64: K / V / Q-chunk TMA boxes are 64 rows; n % 96 resp. 64: whole key chunks)
+  if (grid_w == 24 && n % 192 == 0 && n <= 1152) return 1 | (((n + 127) / 128 * 32 <= 192) ? 2 : 0);
   if (grid_w == 32 && n % 64 == 0 && n <= 1024) return 1;
   return 0;
 }

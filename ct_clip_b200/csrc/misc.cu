@@ -8,6 +8,7 @@
 //     matching un-folding of weight gradients
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rng.cuh"
 #include "../../include/ctclip_b200.h"
 
 namespace ctb {
@@ -522,6 +523,44 @@ __global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dropout (HF BertModel: embeddings, BertSelfOutput, BertOutput -- modeling_bert.py `self.dropout(hidden_states)`): masks are
+// regenerated from (seed, offset, element index) with Philox (rng.cuh); 4 elements per thread = one Philox call.
+//   forward : y = resid + keep * x / (1 - p)          (resid optional; y_f32 / y_bf16 optional outputs)
+//   backward: dx = keep * dy / (1 - p)                (dx_f32 / dx_bf16 optional outputs)   -- the same kernel with resid = NULL
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, const float* __restrict__ resid,
+                                                      float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_bf16, long long n,
+                                                      float inv_keep, uint32_t thresh, unsigned long long seed,
+                                                      unsigned long long offset) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 elements
+  const long long i0 = g * 4;
+  if (i0 >= n) return;
+  uint32_t w[4];
+  philox4(seed, offset + (unsigned long long)g, w);
+  float v[4];
+  if (i0 + 3 < n) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i0);
+    v[0] = xv.x; v[1] = xv.y; v[2] = xv.z; v[3] = xv.w;
+  } else {
+    for (int e = 0; e < 4; e++) v[e] = (i0 + e < n) ? x[i0 + e] : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    v[e] = (w[e] >= thresh) ? v[e] * inv_keep : 0.f;
+    if (resid != nullptr && i0 + e < n) v[e] += resid[i0 + e];
+  }
+  if (i0 + 3 < n) {
+    if (y_f32 != nullptr) *reinterpret_cast<float4*>(y_f32 + i0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (y_bf16 != nullptr) *reinterpret_cast<uint2*>(y_bf16 + i0) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  } else {
+    for (int e = 0; e < 4 && i0 + e < n; e++) {
+      if (y_f32 != nullptr) y_f32[i0 + e] = v[e];
+      if (y_bf16 != nullptr) y_bf16[i0 + e] = __float2bfloat16(v[e]);
+    }
+  }
+}
+
 }  // namespace ctb
 
 using namespace ctb;
@@ -616,6 +655,18 @@ extern "C" int ctclip_l2norm_rows_bf16(const float* x, void* y, int32_t rows, in
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(x && y && rows > 0 && D > 0, "l2norm_rows: bad args");
   l2norm_rows_bf16_kernel<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), rows, D);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_dropout(const float* x, const float* resid, float* y_f32, void* y_bf16, int64_t n, float p, uint64_t seed,
+                              uint64_t offset, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(x && (y_f32 || y_bf16) && n > 0 && p >= 0.f && p < 1.f, "dropout: bad args");
+  CTB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(y_f32)) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(y_bf16) % 8 == 0, "dropout: pointers must be 16-byte aligned");
+  const long long groups = (n + 3) / 4;
+  dropout_kernel<<<ceil_div(groups, 256), 256, 0, stream>>>(x, resid, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), n, 1.f / (1.f - p),
+                                                          dropout_threshold(p), seed, offset);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

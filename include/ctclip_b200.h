@@ -234,6 +234,10 @@ typedef struct {
   int32_t grid_h, grid_w;
   const float* qk_bound;
   float* dcpb_table;
+  /* attention-probability dropout (HF BertSelfAttention: `attention_probs = self.dropout(attention_probs)`), dim_head 64 path
+   * only: element ((seq*heads + head)*n + i)*n + j of the probability tensor is kept per the rule of ctclip_dropout. */
+  float dropout_p;
+  uint64_t dropout_seed, dropout_offset;
 } ctclip_attn_args;
 int ctclip_attn_fwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
@@ -283,6 +287,15 @@ int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t
  * h[:,2j] <- dg[:,j]*gelu(gate_j), h[:,2j+1] <- dg[:,j]*value_j*gelu'(gate_j); colsum[2*n_pairs] += column sums. */
 int ctclip_geglu_bwd(const void* dg, int64_t ld_dg, void* h, int64_t ld_h, int64_t M, int32_t n_pairs, float* colsum,
                      void* stream);
+
+/* Dropout with counter-based masks (csrc/rng.cuh: Philox4x32-10; element idx of a site is kept iff
+ * philox(seed, offset + idx/4).word[idx%4] >= floor(p*2^32)), so backward regenerates the mask from the same (seed, offset):
+ *   y = resid + keep * x / (1-p)   (resid optional; y_f32, y_bf16 optional outputs; n elements, 16-byte aligned pointers).
+ * The backward of the same site is the same call on the upstream gradient with resid = NULL.
+ * HF BertModel sites (modeling_bert.py): embeddings, BertSelfOutput, BertOutput; attention-probability dropout lives inside
+ * ctclip_attn_fwd / ctclip_attn_bwd (dropout_p / dropout_seed / dropout_offset of ctclip_attn_args). */
+int ctclip_dropout(const float* x, const float* resid, float* y_f32, void* y_bf16, int64_t n, float p, uint64_t seed,
+                   uint64_t offset, void* stream);
 
 /* Vector quantiser pieces (vector_quantize_pytorch==1.1.2 CosineSimCodebook, called at ctvit.py:403):
  * the argmax itself is GEMM epilogue 5 on (tokens, l2norm(embed)). */

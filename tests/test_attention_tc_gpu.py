@@ -31,7 +31,7 @@ def _inputs(nseq, H, W, heads=8, dh=32, seed=0):
     return q, k, kv, tab, d_o, qs, ks
 
 
-@pytest.mark.parametrize("nseq,H,W", [(2, 24, 24), (3, 8, 24), (1, 4, 24), (2, 16, 24), (1, 32, 32)])
+@pytest.mark.parametrize("nseq,H,W", [(2, 24, 24), (3, 8, 24), (2, 16, 24), (1, 32, 24), (1, 32, 32)])
 def test_attention_tc_fwd_bwd(nseq, H, W):
     from ct_clip_b200 import ops
     heads, dh = 8, 32
@@ -39,6 +39,7 @@ def test_attention_tc_fwd_bwd(nseq, H, W):
     M = nseq * n
     sup = ops.attn_tc_supported(n, H, W, dh)
     assert sup & 1
+    assert ops.attn_tc_supported(96, 4, 24, dh) == 0        # 96 keys: not a whole number of 64-row TMA boxes -> mma.sync path
     q, k, kv, tab, d_o, qs, ks = _inputs(nseq, H, W)
     v = kv[:, I:]
     qkb = torch.empty(1, device=DEV)
