@@ -7,8 +7,10 @@ eps from config): embeddings = word + position + token_type(0) -> LayerNorm; per
   m = gelu(x Wi^T + bi) Wo2^T + bo2                                              ;  x = LN(x + m)
 Only the CLS row of the last layer feeds CT-CLIP (ct_clip.py:762); the pooler is never evaluated.
 
-Dropout: supported only as p == 0 / eval mode (parity tests and bench use p = 0). With p > 0 in training mode the
-caller keeps the module on its PyTorch path (CTCLIP._text_cls decides).
+Dropout (CXR-BERT trains with hidden_dropout_prob = attention_probs_dropout_prob = 0.1, run_train.py:7-9 +
+CTCLIPTrainer.py:254): the four HF sites -- embeddings, attention probabilities, BertSelfOutput, BertOutput -- run on the
+native kernels with counter-based Philox masks (csrc/rng.cuh) that the backward pass regenerates from (seed, site offset).
+`forward(..., dropout=dict(p_hidden=, p_attn=, seed=))`; None = eval mode / p = 0.
 """
 from __future__ import annotations
 
@@ -36,6 +38,19 @@ def supports(bert) -> bool:
 def dropout_active(bert) -> bool:
     cfg = bert.config
     return bert.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
+
+
+def dropout_config(bert, seed: int):
+    """The dropout argument of BertEngine.forward for this module's current mode (None when nothing is dropped)."""
+    if not dropout_active(bert):
+        return None
+    return dict(p_hidden=float(bert.config.hidden_dropout_prob), p_attn=float(bert.config.attention_probs_dropout_prob), seed=int(seed))
+
+
+def site_offset(layer: int, kind: int) -> int:
+    """Philox counter base of a dropout site: embeddings = (layer -1, kind 3) -> 0; layer i: kind 0 attention probabilities,
+    1 BertSelfOutput, 2 BertOutput. Sites are 2^40 counters apart (a site has < 2^38 groups of 4 elements)."""
+    return (4 * (layer + 1) + kind - 3) << 40
 
 
 class BertEngine:
@@ -77,8 +92,11 @@ class BertEngine:
         self._version = None
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, input_ids, attention_mask, P, *, save):
-        """-> (last_hidden_state fp32 [b, n, H], ctx)"""
+    def forward(self, input_ids, attention_mask, P, *, save, dropout=None):
+        """-> (last_hidden_state fp32 [b, n, H], ctx). dropout: None or dict(p_hidden, p_attn, seed) (training mode)."""
+        ph = float(dropout["p_hidden"]) if dropout else 0.0
+        pa = float(dropout["p_attn"]) if dropout else 0.0
+        seed = int(dropout["seed"]) if dropout else 0
         dev, H, I, heads = self.device, self.H, self.inter, self.heads
         b, n = input_ids.shape
         M = b * n
@@ -96,6 +114,8 @@ class BertEngine:
         sv0 = dict(xhat=torch.empty(M, H, **bf), rstd=torch.empty(M, device=dev)) if save else dict(xhat=None, rstd=None)
         ops.ln_fwd(e, M, H, eps=self.eps, gamma=P["embeddings.LayerNorm.weight"], beta=P["embeddings.LayerNorm.bias"],
                    y_f32=x, y_bf16=xb, xhat=sv0["xhat"], rstd=sv0["rstd"])
+        if ph > 0:    # BertEmbeddings: dropout after the LayerNorm
+            ops.dropout(x, n=M * H, p=ph, seed=seed, offset=site_offset(-1, 3), y_f32=x, y_bf16=xb)
         saved = []
         for i, w in enumerate(self.w):
             lp = f"encoder.layer.{i}."
@@ -103,10 +123,15 @@ class BertEngine:
             ops.gemm(xb, w["qkv"], M=M, N=3 * H, K=H, epilogue=ops.EPI_BF16, C_out=qkv, bias=w["bqkv"])
             ao = torch.empty(M, H, **bf)
             lse = torch.empty(M, heads, device=dev) if save else None
-            ops.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], ao, lse, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, **geom)
+            ops.attn_fwd(qkv, qkv[:, H:], qkv[:, 2 * H:], ao, lse, ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, dropout_p=pa,
+                         dropout_seed=seed, dropout_offset=site_offset(i, 0), **geom)
             y = torch.empty(M, H, device=dev)
-            ops.gemm(ao, w["wo"], M=M, N=H, K=H, epilogue=ops.EPI_RESID_F32, C_out=y, resid=x,
-                     bias=P[lp + "attention.output.dense.bias"])
+            if ph > 0:   # BertSelfOutput: LayerNorm(x + dropout(dense(ao)))
+                ops.gemm(ao, w["wo"], M=M, N=H, K=H, epilogue=ops.EPI_F32, C_out=y, bias=P[lp + "attention.output.dense.bias"])
+                ops.dropout(y, n=M * H, p=ph, seed=seed, offset=site_offset(i, 1), resid=x, y_f32=y)
+            else:
+                ops.gemm(ao, w["wo"], M=M, N=H, K=H, epilogue=ops.EPI_RESID_F32, C_out=y, resid=x,
+                         bias=P[lp + "attention.output.dense.bias"])
             x1 = torch.empty(M, H, device=dev)
             x1b = torch.empty(M, H, **bf)
             s1 = dict(xhat=torch.empty(M, H, **bf), rstd=torch.empty(M, device=dev)) if save else dict(xhat=None, rstd=None)
@@ -116,8 +141,12 @@ class BertEngine:
             pre = torch.empty(M, I, **bf) if save else None
             ops.gemm(x1b, w["wi"], M=M, N=I, K=H, epilogue=ops.EPI_BIAS_GELU, C_out=act, C2=pre,
                      bias=P[lp + "intermediate.dense.bias"])
-            ops.gemm(act, w["wo2"], M=M, N=H, K=I, epilogue=ops.EPI_RESID_F32, C_out=y, resid=x1,
-                     bias=P[lp + "output.dense.bias"])
+            if ph > 0:   # BertOutput: LayerNorm(x1 + dropout(dense(act)))
+                ops.gemm(act, w["wo2"], M=M, N=H, K=I, epilogue=ops.EPI_F32, C_out=y, bias=P[lp + "output.dense.bias"])
+                ops.dropout(y, n=M * H, p=ph, seed=seed, offset=site_offset(i, 2), resid=x1, y_f32=y)
+            else:
+                ops.gemm(act, w["wo2"], M=M, N=H, K=I, epilogue=ops.EPI_RESID_F32, C_out=y, resid=x1,
+                         bias=P[lp + "output.dense.bias"])
             x2 = torch.empty(M, H, device=dev)
             x2b = torch.empty(M, H, **bf)
             s2 = dict(xhat=torch.empty(M, H, **bf), rstd=torch.empty(M, device=dev)) if save else dict(xhat=None, rstd=None)
@@ -126,13 +155,14 @@ class BertEngine:
             if save:
                 saved.append(dict(xb=xb, qkv=qkv, ao=ao, lse=lse, ln1=s1, x1b=x1b, act=act, pre=pre, ln2=s2))
             x, xb = x2, x2b
-        ctx = dict(b=b, n=n, M=M, ids=ids, geom=geom, emb=sv0, saved=saved) if save else None
+        ctx = dict(b=b, n=n, M=M, ids=ids, geom=geom, emb=sv0, saved=saved, drop=(ph, pa, seed)) if save else None
         return x.view(b, n, H), ctx
 
     def backward(self, ctx, d_last, P, G):
         """d_last: fp32 [b*n, H] gradient w.r.t. last_hidden_state. Accumulates into G (keys like P)."""
         dev, H, I, heads = self.device, self.H, self.inter, self.heads
         M, n = ctx["M"], ctx["n"]
+        ph, pa, seed = ctx.get("drop", (0.0, 0.0, 0))
         bf = dict(dtype=torch.bfloat16, device=dev)
         dx = d_last
         for i in reversed(range(self.layers)):
@@ -143,7 +173,11 @@ class BertEngine:
             dyb = torch.empty(M, H, **bf)
             ops.ln_bwd(M, H, g_f32=dx, gamma=P[lp + "output.LayerNorm.weight"], xhat=sv["ln2"]["xhat"], rstd=sv["ln2"]["rstd"],
                        dx_f32=dy, dx_bf16=dyb, dgamma=G[lp + "output.LayerNorm.weight"], dbeta=G[lp + "output.LayerNorm.bias"])
-            ops.colsum(dyb, G[lp + "output.dense.bias"], M=M, N=H)
+            dsrc = dy
+            if ph > 0:   # gradient w.r.t. the dense output = keep/(1-p) * dy (the residual branch keeps the full dy)
+                dsrc = torch.empty(M, H, device=dev)
+                ops.dropout(dy, n=M * H, p=ph, seed=seed, offset=site_offset(i, 2), y_f32=dsrc, y_bf16=dyb)
+            ops.colsum(dsrc, G[lp + "output.dense.bias"], M=M, N=H)       # bias gradients from the fp32 gradient, not its bf16 copy
             self._wgrad(dyb, sv["act"], G[lp + "output.dense.weight"], n_out=H, k_out=I, rows=M)
             dact = torch.empty(M, I, **bf)
             ops.gemm(dyb, w["wo2"], M=M, N=I, K=H, b_major=1, epilogue=ops.EPI_BF16, C_out=dact)
@@ -156,7 +190,11 @@ class BertEngine:
             ops.ln_bwd(M, H, g_f32=dy, gamma=P[lp + "attention.output.LayerNorm.weight"], xhat=sv["ln1"]["xhat"],
                        rstd=sv["ln1"]["rstd"], dx_f32=d1, dx_bf16=d1b, dgamma=G[lp + "attention.output.LayerNorm.weight"],
                        dbeta=G[lp + "attention.output.LayerNorm.bias"])
-            ops.colsum(d1b, G[lp + "attention.output.dense.bias"], M=M, N=H)
+            dsrc = d1
+            if ph > 0:
+                dsrc = torch.empty(M, H, device=dev)
+                ops.dropout(d1, n=M * H, p=ph, seed=seed, offset=site_offset(i, 1), y_f32=dsrc, y_bf16=d1b)
+            ops.colsum(dsrc, G[lp + "attention.output.dense.bias"], M=M, N=H)
             self._wgrad(d1b, sv["ao"], G[lp + "attention.output.dense.weight"], n_out=H, k_out=H, rows=M)
             dao = torch.empty(M, H, **bf)
             ops.gemm(d1b, w["wo"], M=M, N=H, K=H, b_major=1, epilogue=ops.EPI_BF16, C_out=dao)
@@ -165,7 +203,7 @@ class BertEngine:
             qkv = sv["qkv"]
             ops.attn_bwd(qkv, qkv[:, H:], qkv[:, 2 * H:], sv["ao"], sv["lse"], dao, delta, dqkv, dqkv[:, H:], dqkv[:, 2 * H:],
                          ldq=3 * H, ldk=3 * H, ldv=3 * H, ldo=H, ld_dq=3 * H, ld_dk=3 * H, ld_dv=3 * H, total_rows=M,
-                         **ctx["geom"])
+                         dropout_p=pa, dropout_seed=seed, dropout_offset=site_offset(i, 0), **ctx["geom"])
             for j, nm in enumerate(("query", "key", "value")):
                 dj = dqkv[:, j * H:(j + 1) * H]
                 ops.colsum(dj, G[lp + f"attention.self.{nm}.bias"], M=M, N=H, ld=3 * H)
@@ -173,7 +211,9 @@ class BertEngine:
             ops.gemm(dqkv, w["qkv"], M=M, N=H, K=3 * H, b_major=1, epilogue=ops.EPI_RESID_F32, C_out=d1, resid=d1)  # dx
             dx = d1
             ctx["saved"][i] = None
-        # embeddings: x0 = LN(e)
+        # embeddings: x0 = dropout(LN(e))
+        if ph > 0:
+            ops.dropout(dx, n=M * H, p=ph, seed=seed, offset=site_offset(-1, 3), y_f32=dx)
         de = torch.empty(M, H, device=dev)
         ops.ln_bwd(M, H, g_f32=dx, gamma=P["embeddings.LayerNorm.weight"], xhat=ctx["emb"]["xhat"], rstd=ctx["emb"]["rstd"],
                    dx_f32=de, dgamma=G["embeddings.LayerNorm.weight"], dbeta=G["embeddings.LayerNorm.bias"])

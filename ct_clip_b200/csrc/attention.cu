@@ -1284,15 +1284,25 @@ static int launch_grouped(Kern kern, const ctclip_attn_args* a, size_t group_byt
 template <int DH, bool MASK>
 static int attn_dispatch(int which, const ctclip_attn_args* a, cudaStream_t stream) {
   const int n_pad = (a->n + 15) & ~15;
-  if (a->dropout_p > 0.f) {   // attention-probability dropout: the BERT shape only (64 < n <= 256, even n)
-    if (DH == 64 && a->n > 64 && a->n <= 256 && a->n % 2 == 0) {
+  if (a->dropout_p > 0.f) {   // attention-probability dropout (BERT text tower: dim_head 64, even sequence lengths)
+    if (DH == 64 && a->n % 2 == 0) {
       const size_t mk2 = MASK ? (size_t)n_pad * 4 : 0;
       const size_t g_f = (size_t)(2 * n_pad * (DH + 8)) * 2 + mk2, g_kv = (size_t)(2 * n_pad * (DH + 8)) * 2 + (size_t)n_pad * 8;
-      if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
-      if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
-      return launch_grouped(attn_bwd_dkv_kernel<DH, 4, 2, MASK, true>, a, g_kv, 4, 2, stream);
+      if (a->n <= 64) {
+        if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 1, 8, MASK, true>, a, g_f, 1, 8, stream);
+        if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 1, 8, MASK, true>, a, g_f, 1, 8, stream);
+        return launch_grouped(attn_bwd_dkv_kernel<DH, 1, 8, MASK, true>, a, g_kv, 1, 8, stream);
+      }
+      if (a->n <= 256) {
+        if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
+        if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 4, 2, MASK, true>, a, g_f, 4, 2, stream);
+        return launch_grouped(attn_bwd_dkv_kernel<DH, 4, 2, MASK, true>, a, g_kv, 4, 2, stream);
+      }
+      if (which == 0) return launch_grouped(attn_fwd_kernel<DH, 8, 1, MASK, true>, a, g_f, 8, 1, stream);
+      if (which == 1) return launch_grouped(attn_bwd_dq_kernel<DH, 8, 1, MASK, true>, a, g_f, 8, 1, stream);
+      return launch_grouped(attn_bwd_dkv_kernel<DH, 12, 1, MASK, true>, a, g_kv, 12, 1, stream);
     }
-    set_error("attention: dropout_p > 0 is implemented for dim_head 64, 64 < n <= 256, even n (got dh %d, n %d)", DH, a->n);
+    set_error("attention: dropout_p > 0 is implemented for dim_head 64 and even n (got dh %d, n %d)", DH, a->n);
     return CTCLIP_ERR_UNSUPPORTED;
   }
   const size_t mk = MASK ? (size_t)n_pad * 4 : 0;

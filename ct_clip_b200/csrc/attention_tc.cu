@@ -241,36 +241,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, NCH);
       constexpr uint32_t idesc_pv = umma_idesc(1, 0, 1, 128, 32);     // A = P from TMEM (K-major), B = V MN-major
-      const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-      auto issue_s = [&](int b) {
-        const int t = b / NC, c = b % NC, st = b & 1;
-        if (c == 0) mbar_wait_tag(&q_full[t & 1], (t >> 1) & 1, 30 + (t & 1));
+      constexpr uint32_t hi64 = umma_desc_hi(512, SW64);              // every operand tile here: 64-byte rows, 8-row groups 512 B apart
+      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16), k_lo = umma_desc_lo(smem_u32(sK), 16), v_lo = umma_desc_lo(smem_u32(sV), 512);
+      // (t, c) of the NEXT S block to issue / of the block whose P is consumed: advanced incrementally, no divisions in this thread
+      int ts = 0, cs = 0;
+      auto issue_s = [&]() {
+        const int st = (ts * NC + cs) & 1;
+        if (cs == 0) mbar_wait_tag(&q_full[ts & 1], (ts >> 1) & 1, 30 + (ts & 1));
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-          const uint64_t ad = umma_smem_desc_sw(sQ_u + (t & 1) * 8192 + ks * 32, 16, 512, SW64);
-          const uint64_t bd = umma_smem_desc_sw(sK_u + (uint32_t)c * NCH * 64 + ks * 32, 16, 512, SW64);
-          umma_bf16(tmem_base + st * NCH, ad, bd, idesc_s, ks > 0 ? 1u : 0u);
-        }
+        const uint32_t ql = q_lo + (ts & 1) * (8192 >> 4), kl = k_lo + (uint32_t)cs * (NCH * 64 >> 4);
+        umma_bf16(tmem_base + st * NCH, umma_desc_join(ql, hi64), umma_desc_join(kl, hi64), idesc_s, 0u);
+        umma_bf16(tmem_base + st * NCH, umma_desc_join(ql + 2, hi64), umma_desc_join(kl + 2, hi64), idesc_s, 1u);
         umma_commit(&s_full[st]);
-        if (c == NC - 1) umma_commit(&q_empty[t & 1]);   // every S MMA of this Q tile has been issued
+        if (cs == NC - 1) umma_commit(&q_empty[ts & 1]);   // every S MMA of this Q tile has been issued
+        if (++cs == NC) { cs = 0; ts++; }
       };
       mbar_wait_tag(k_full, 0, 32);
-      issue_s(0);
+      issue_s();
+      int c = 0;
       for (int b = 0; b < NB; b++) {
-        if (b + 1 < NB) issue_s(b + 1);
-        const int c = b % NC, st = b & 1;
+        if (b + 1 < NB) issue_s();
+        const int st = b & 1;
         if (b == 0) mbar_wait_tag(v_full, 0, 33);
         mbar_wait_tag(&p_full[st], (b >> 1) & 1, 34 + st);
         tc_fence_after();
+        const uint32_t vl = v_lo + (uint32_t)c * (NCH * 64 >> 4);
 #pragma unroll
         for (int ks = 0; ks < NCH / 16; ks++) {
           const int k0 = ks * 16;
           const uint32_t acol = st * NCH + (k0 / HALF) * HALF + (k0 % HALF) / 2;
-          const uint64_t bd = umma_smem_desc_sw(sV_u + (uint32_t)(c * NCH + k0) * 64, 512, 512, SW64);
-          umma_bf16_ts(tmem_base + OCOL, tmem_base + acol, bd, idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + OCOL, tmem_base + acol, umma_desc_join(vl + ks * (1024 >> 4), hi64), idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
         }
         if (c == NC - 1) umma_commit(o_full);
+        if (++c == NC) c = 0;
       }
     }
   }
@@ -475,13 +478,22 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
               dk_[e / 2] = pack_bf16x2(d0, d1);
             }
             tmem_st_32x16(scol, pk);                                 // P^T over this warp's own S^T columns
-            __nv_bfloat16* sp = (p.ds_spill != nullptr)
-                                    ? p.ds_spill + ((long long)item * n + key) * n + qc * 64 + hf * 32 : nullptr;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) {
-              const uint4 val = make_uint4(dk_[4 * c4], dk_[4 * c4 + 1], dk_[4 * c4 + 2], dk_[4 * c4 + 3]);
-              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) = val;
-              if (sp != nullptr) __stcs(reinterpret_cast<uint4*>(sp) + c4, val);
+            for (int c4 = 0; c4 < 4; c4++)
+              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) =
+                  make_uint4(dk_[4 * c4], dk_[4 * c4 + 1], dk_[4 * c4 + 2], dk_[4 * c4 + 3]);
+            if (p.ds_spill != nullptr) {
+              // spill this warp's 32 keys x 32 queries through the tile it has just written: 8 rows x 64 contiguous bytes per
+              // store instruction (full 32-byte sectors) instead of 32 rows x 16 bytes straight from the registers
+              __syncwarp();
+              const uint8_t* tile_w = sDS + buf * 32768 + grp * 16384 + (q * 32) * 128;
+              __nv_bfloat16* sp = p.ds_spill + ((long long)item * n + kb * 128 + q * 32) * n + qc * 64;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int rr = j * 8 + (lane >> 2), ch = hf * 4 + (lane & 3);
+                const uint4 val = *reinterpret_cast<const uint4*>(tile_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                __stcs(reinterpret_cast<uint4*>(sp + (long long)rr * n + ch * 8), val);
+              }
             }
             tmem_st_wait();
           } else {
@@ -552,54 +564,62 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, 64);     // S^T, dP^T : A, B K-major
       constexpr uint32_t idesc_dv = umma_idesc(1, 0, 1, 128, 32);    // dV (A TMEM), dK (A smem K-major): B MN-major
       constexpr uint32_t idesc_dq = umma_idesc(1, 1, 1, 128, 32);    // dQ: A, B MN-major
-      const uint32_t sKV_u = smem_u32(sKV), sDS_u = smem_u32(sDS), sQD_u = smem_u32(sQD);
-      // look-ahead issue of S^T / dP^T for flat block f (0 .. total_blocks): needs its K/V block and its Q/dO chunk
-      auto issue_s = [&](long long f) {
-        const int qc = (int)(f % NQC);
-        const long long ub = f / NQC;                               // running key-block index of this CTA
-        const int ks = (int)(ub & 1), slot = (int)(f % TCB_QD_SLOTS), st = (int)(f & 1);
-        if (qc == 0) mbar_wait_tag(&kv_full[ks], (uint32_t)((ub >> 1) & 1), 60);
-        mbar_wait_tag(&qd_full[slot], (uint32_t)((f / TCB_QD_SLOTS) & 1), 61);
+      constexpr uint32_t hi64 = umma_desc_hi(512, SW64), hi128 = umma_desc_hi(1024, SW128);
+      const uint32_t kv_lo_k = umma_desc_lo(smem_u32(sKV), 16), kv_lo_mn = umma_desc_lo(smem_u32(sKV), 512);
+      const uint32_t qd_lo_k = umma_desc_lo(smem_u32(sQD), 16), qd_lo_mn = umma_desc_lo(smem_u32(sQD), 512);
+      const uint32_t ds_lo_k = umma_desc_lo(smem_u32(sDS), 16), ds_lo_mn = umma_desc_lo(smem_u32(sDS), 16384);
+      // incrementally advanced state of the look-ahead S issue (s*) and of the consumer side (no divisions in this thread)
+      int s_qc = 0, s_slot = 0, s_st = 0;
+      uint32_t s_ub = 0, s_qpar = 0, s_round = 0;     // key-block counter, qd ring parity, (f >> 1) of the look-ahead block
+      auto issue_s = [&]() {
+        const int ks = (int)(s_ub & 1);
+        if (s_qc == 0) mbar_wait_tag(&kv_full[ks], (s_ub >> 1) & 1, 60);
+        mbar_wait_tag(&qd_full[s_slot], s_qpar, 61);
         tc_fence_after();
-        const uint32_t kA = sKV_u + ks * 16384, vA = kA + 8192, qB = sQD_u + slot * TCB_QD_BYTES, dB = qB + 4096;
-        const uint32_t d0 = tmem_base + st * 128;
-#pragma unroll
-        for (int k2 = 0; k2 < 2; k2++)
-          umma_bf16(d0, umma_smem_desc_sw(kA + k2 * 32, 16, 512, SW64), umma_smem_desc_sw(qB + k2 * 32, 16, 512, SW64), idesc_s, k2);
-#pragma unroll
-        for (int k2 = 0; k2 < 2; k2++)
-          umma_bf16(d0 + 64, umma_smem_desc_sw(vA + k2 * 32, 16, 512, SW64), umma_smem_desc_sw(dB + k2 * 32, 16, 512, SW64), idesc_s, k2);
-        umma_commit(&s_full[st]);
+        const uint32_t kA = kv_lo_k + ks * (16384 >> 4), vA = kA + (8192 >> 4);
+        const uint32_t qB = qd_lo_k + s_slot * (TCB_QD_BYTES >> 4), dB = qB + (4096 >> 4);
+        const uint32_t d0 = tmem_base + s_st * 128;
+        umma_bf16(d0, umma_desc_join(kA, hi64), umma_desc_join(qB, hi64), idesc_s, 0u);
+        umma_bf16(d0, umma_desc_join(kA + 2, hi64), umma_desc_join(qB + 2, hi64), idesc_s, 1u);
+        umma_bf16(d0 + 64, umma_desc_join(vA, hi64), umma_desc_join(dB, hi64), idesc_s, 0u);
+        umma_bf16(d0 + 64, umma_desc_join(vA + 2, hi64), umma_desc_join(dB + 2, hi64), idesc_s, 1u);
+        umma_commit(&s_full[s_st]);
+        s_st ^= 1;
+        if (++s_slot == TCB_QD_SLOTS) { s_slot = 0; s_qpar ^= 1; }
+        if (++s_qc == NQC) { s_qc = 0; s_ub++; }
+        (void)s_round;
       };
-      issue_s(0);
-      int v = 0;
+      issue_s();
+      int v = 0, qc = 0, kb = 0, slot = 0, st = 0;
+      uint32_t ub = 0, ppar = 0;       // p_full parity of this stage use = (f >> 1) & 1
       for (long long f = 0; f < total_blocks; f++) {
-        if (f + 1 < total_blocks) issue_s(f + 1);
-        const int qc = (int)(f % NQC);
-        const long long ub = f / NQC;
-        const int kb = (int)(ub % NKB);
-        const int ks = (int)(ub & 1), slot = (int)(f % TCB_QD_SLOTS), st = (int)(f & 1);
+        if (f + 1 < total_blocks) issue_s();
+        const int ks = (int)(ub & 1);
         const int buf = v & 1, grp = qc & 1;
-        mbar_wait_tag(&p_full[st], (uint32_t)((f >> 1) & 1), 62);
+        mbar_wait_tag(&p_full[st], ppar, 62);
         tc_fence_after();
-        const uint32_t kA = sKV_u + ks * 16384, qB = sQD_u + slot * TCB_QD_BYTES, dB = qB + 4096;
-        const uint32_t tile = sDS_u + buf * 32768;
+        const uint32_t qmn = qd_lo_mn + slot * (TCB_QD_BYTES >> 4), dmn = qmn + (4096 >> 4);
+        const uint32_t tile_k = ds_lo_k + buf * (32768 >> 4) + grp * (16384 >> 4);
+        const uint32_t acol = tmem_base + st * 128;
+        const uint32_t acc0 = qc > 0 ? 1u : 0u;
+        // dV += P^T dO_c : K = 64 queries, A = P^T in TMEM (16 queries = 8 columns; the two column halves sit 32 columns apart)
+        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 0, umma_desc_join(dmn, hi64), idesc_dv, acc0);
+        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 8, umma_desc_join(dmn + (1024 >> 4), hi64), idesc_dv, 1u);
+        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 32, umma_desc_join(dmn + (2048 >> 4), hi64), idesc_dv, 1u);
+        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 40, umma_desc_join(dmn + (3072 >> 4), hi64), idesc_dv, 1u);
+        // dK += dS^T Q_c : A = dS tile group grp read K-major (128-byte rows), B = Q chunk MN-major
 #pragma unroll
-        for (int k4 = 0; k4 < 4; k4++) {     // dV += P^T dO_c : K = 64 queries
-          const uint32_t acol = st * 128 + (k4 >> 1) * 32 + (k4 & 1) * 8;
-          umma_bf16_ts(tmem_base + TCB_COL_DV, tmem_base + acol, umma_smem_desc_sw(dB + k4 * 1024, 512, 512, SW64), idesc_dv,
-                       (qc > 0 || k4 > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < 4; k4++)       // dK += dS^T Q_c : A = dS tile group grp, K-major
-          umma_bf16(tmem_base + TCB_COL_DK, umma_smem_desc_sw(tile + grp * 16384 + k4 * 32, 16, 1024, SW128),
-                    umma_smem_desc_sw(qB + k4 * 1024, 512, 512, SW64), idesc_dv, (qc > 0 || k4 > 0) ? 1u : 0u);
+        for (int k4 = 0; k4 < 4; k4++)
+          umma_bf16(tmem_base + TCB_COL_DK, umma_desc_join(tile_k + k4 * 2, hi128), umma_desc_join(qmn + k4 * (1024 >> 4), hi64), idesc_dv,
+                    (k4 > 0) ? 1u : acc0);
         umma_commit(&qd_empty[slot]);
         if (grp == 1 || qc == NQC - 1) {     // dQ tile (qc/2) += dS K_blk : A = both groups of the tile, MN-major, K = 128 keys
+          const uint32_t tile_mn = ds_lo_mn + buf * (32768 >> 4), kmn = kv_lo_mn + ks * (16384 >> 4);
+          const uint32_t dqc = tmem_base + TCB_COL_DQ + (qc >> 1) * 32;
 #pragma unroll
           for (int k8 = 0; k8 < 8; k8++)
-            umma_bf16(tmem_base + TCB_COL_DQ + (qc >> 1) * 32, umma_smem_desc_sw(tile + k8 * 2048, 16384, 1024, SW128),
-                      umma_smem_desc_sw(kA + k8 * 1024, 512, 512, SW64), idesc_dq, (kb > 0 || k8 > 0) ? 1u : 0u);
+            umma_bf16(dqc, umma_desc_join(tile_mn + k8 * (2048 >> 4), hi128), umma_desc_join(kmn + k8 * (1024 >> 4), hi64), idesc_dq,
+                      (kb > 0 || k8 > 0) ? 1u : 0u);
           umma_commit(&ds_free[buf]);
           v++;
         }
@@ -607,6 +627,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           umma_commit(&kv_empty[ks]);
           umma_commit(acc_full);
           if (kb == NKB - 1) umma_commit(dq_full);
+        }
+        // advance
+        if (st == 1) ppar ^= 1;
+        st ^= 1;
+        if (++slot == TCB_QD_SLOTS) slot = 0;
+        if (++qc == NQC) {
+          qc = 0;
+          ub++;
+          if (++kb == NKB) kb = 0;
         }
       }
     }

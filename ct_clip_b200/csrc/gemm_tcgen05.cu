@@ -752,13 +752,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; i++)
                 if (i < ncols && v[i] > best_v) { best_v = v[i]; best_i = col0 + i; }
-            } else {   // running top-2 (first maximum wins ties, like torch.argmax)
+            } else {
+              // running top-2 on PACKED keys: the low 13 mantissa bits of the score carry (8191 - column), so the pair is
+              // tracked with three FMNMX per element and no index registers (the (value, index) select chains made this
+              // epilogue the bottleneck of the code-book GEMM: 1.30 ms vs 0.65 ms). The scores lose 2^-10 of relative
+              // resolution, which only matters for candidates the fp32 re-ranking (ctclip_vq_rerank) orders anyway; equal
+              // truncated scores prefer the lower column, like torch.argmax. N <= 8192 (checked by the launcher).
 #pragma unroll
               for (int i = 0; i < 32; i++) {
                 if (i < ncols) {
-                  const float x = v[i];
-                  if (x > best_v) { sec_v = best_v; sec_i = best_i; best_v = x; best_i = col0 + i; }
-                  else if (x > sec_v) { sec_v = x; sec_i = col0 + i; }
+                  const float x = __uint_as_float((__float_as_uint(v[i]) & 0xFFFFE000u) | (uint32_t)(8191 - (col0 + i)));
+                  const float lo = fminf(x, best_v);
+                  best_v = fmaxf(x, best_v);
+                  sec_v = fmaxf(sec_v, lo);
                 }
               }
             }
@@ -917,6 +923,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (p.epi == EPI_ARGMAX) {
         // merge the two column-halves of every row (first maximum wins, like torch.argmax)
         const int rit = q * 32 + lane;
+        if (top2) {   // unpack the column indices of the packed keys
+          best_i = 8191 - (int)(__float_as_uint(best_v) & 0x1FFFu);
+          sec_i = 8191 - (int)(__float_as_uint(sec_v) & 0x1FFFu);
+        }
         float* merge2 = reinterpret_cast<float*>(stage_all);   // [128][2] runner-up (value, index): the store staging buffers are idle here
         if (half == 1) {
           arg_merge[2 * rit] = best_v;
@@ -940,6 +950,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               else { sec_v = best_v; sec_i = best_i; }
               best_v = ov; best_i = oi;
             } else if (before(ov, oi, sec_v, sec_i)) { sec_v = ov; sec_i = oi; }
+            if (sec_v == -INFINITY) sec_i = best_i;   // fewer than two columns seen: no runner-up
             p.arg2_out[row] = sec_i;
           } else if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
           p.arg_out[row] = best_i;
@@ -1041,6 +1052,8 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   CTB_CHECK_ARG(a->splits >= 0, "gemm: splits must be >= 0 (0 = choose automatically, ATOMIC_F32 only)");
   CTB_CHECK_ARG(a->splits == 1 || a->epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the ATOMIC_F32 epilogue");
   if (a->epilogue == EPI_ARGMAX) CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
+  if (a->epilogue == EPI_ARGMAX && a->arg2_out != nullptr)
+    CTB_CHECK_ARG(a->N >= 2 && a->N <= 8192, "gemm: ARGMAX with arg2_out packs the column into 13 mantissa bits: N must be in [2, 8192] (got %d)", a->N);
   else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU || a->epilogue == EPI_L2NORM, "gemm: null C");
   if (a->epilogue == EPI_GEGLU) CTB_CHECK_ARG(a->C2 != nullptr && (a->N % 2) == 0, "gemm: GEGLU needs C2 and even N");
   if (a->epilogue == EPI_RESID_F32) CTB_CHECK_ARG(a->resid != nullptr, "gemm: RESID_F32 needs resid");

@@ -200,6 +200,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw(uint32_t saddr, uint32_t l
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
+// The same descriptor split into its two 32-bit words: the high word (SBO, version, swizzle mode) is a compile-time constant of
+// a tile shape, the low word = start address | LBO; stepping through a tile only ADDS (bytes >> 4) to the low word -- the
+// single MMA-issuing thread should not rebuild 64-bit descriptors with shifts for every instruction.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // 32 lanes x 16 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -43,7 +43,8 @@ class _ClipStepFn(torch.autograd.Function):
         tctx = None
         if cls is None:   # native BERT
             PT = {n[len("text_transformer."):]: P[n] for n in names if n.startswith("text_transformer.")}
-            last, tctx = module._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=need_grad)
+            last, tctx = module._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=need_grad,
+                                                       dropout=module._text_dropout())
             cls_in = last[:, 0, :]
             ctx.PT = PT
         else:
@@ -199,7 +200,16 @@ class CTCLIP(nn.Module):
     def _text_native(self):
         """True when the injected text encoder is a HF BertModel this build runs on its own kernels."""
         tt = self.text_transformer
-        return (not self.force_torch_text) and bert_native.supports(tt) and not bert_native.dropout_active(tt)
+        return (not self.force_torch_text) and bert_native.supports(tt)
+
+    def _text_dropout(self):
+        """dropout argument of the native text tower for this call: a fresh Philox seed per training-mode forward, drawn from
+        torch's CPU generator (reproducible under torch.manual_seed, no device synchronisation); None in eval mode / p = 0."""
+        tt = self.text_transformer
+        if not bert_native.dropout_active(tt):
+            return None
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        return bert_native.dropout_config(tt, seed)
 
     def _bert_engine(self):
         dev = self.to_text_latent.weight.device
@@ -221,7 +231,8 @@ class CTCLIP(nn.Module):
         if self._text_native():
             with torch.no_grad():
                 PT = dict(self.text_transformer.named_parameters())
-                enc_text, _ = self._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=False)
+                enc_text, _ = self._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=False,
+                                                          dropout=self._text_dropout())
             return enc_text, enc_text[:, 0, :]
         out = self.text_transformer(text.input_ids, attention_mask=text.attention_mask)
         enc_text = out[0]

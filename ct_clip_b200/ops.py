@@ -141,9 +141,10 @@ def peg_bwd_weight(x, dy, dweight, dbias, **kw):
 
 def _attn_args(q, k, v, o, lse, *, ldq, ldk, ldv, ldo, n, heads, num_seqs, seq_inner, seq_outer_stride, tok_stride,
                bias=None, bias_t=None, scale=8.0, dim_head=32, key_mask=None, bias_frag=None, bias_t_frag=None,
-               cpb_table=None, grid_hw=None, qk_bound=None):
+               cpb_table=None, grid_hw=None, qk_bound=None, dropout_p=0.0, dropout_seed=0, dropout_offset=0):
     """cpb_table (fp32 [(2h-1)(2w-1), heads]) + grid_hw=(h, w) select the tcgen05 / TMEM kernels (csrc/attention_tc.cu)."""
     a = AttnArgs()
+    a.dropout_p, a.dropout_seed, a.dropout_offset = dropout_p, dropout_seed, dropout_offset
     if cpb_table is not None:
         a.cpb_table, a.qk_bound = cpb_table.data_ptr(), _ptr(qk_bound)
         a.grid_h, a.grid_w = grid_hw
@@ -249,6 +250,12 @@ def geglu_bwd(dg, h, *, M, n_pairs, colsum_out=None, ld_dg=None, ld_h=None):
 
 def l2norm_rows_bf16(x, y, rows, D):
     call("ctclip_l2norm_rows_bf16", x.data_ptr(), y.data_ptr(), rows, D, _stream())
+
+
+def dropout(x, *, n, p, seed, offset, resid=None, y_f32=None, y_bf16=None):
+    """y = resid + keep * x / (1 - p) with the Philox mask of (seed, offset) (csrc/rng.cuh); the backward of a site is the same
+    call on the upstream gradient with resid=None. In-place (y_f32 is x) is fine."""
+    call("ctclip_dropout", x.data_ptr(), _ptr(resid), _ptr(y_f32), _ptr(y_bf16), n, p, seed, offset, _stream())
 
 
 def vq_rerank(x, embed, idx, idx2, M, D):

@@ -208,13 +208,25 @@ def ctvit_forward(video, sd, pre, cfg: CTViTConfig, training: bool, taps=None, f
 # ------------------------------------------------------------------------------------------------
 # text tower (HF BertModel restated: transformers/models/bert/modeling_bert.py, eager attention)
 # ------------------------------------------------------------------------------------------------
-def bert_forward(input_ids, attention_mask, sd, pre, cfg: BertConfigLite):
-    """Returns last_hidden_state (b, n, hidden). Called at ct_clip.py:685-686."""
+def bert_forward(input_ids, attention_mask, sd, pre, cfg: BertConfigLite, dropout=None):
+    """Returns last_hidden_state (b, n, hidden). Called at ct_clip.py:685-686.
+    dropout (training mode, CTCLIPTrainer.py:254 with CXR-BERT's p = 0.1): None, or dict(p_hidden, p_attn, masks) where
+    masks[(layer, kind)] is the boolean KEEP mask of a site -- HF applies `nn.Dropout` at: the embeddings after their LayerNorm
+    ((-1, 3), BertEmbeddings.forward), the attention probabilities ((i, 0), BertSelfAttention: softmax -> dropout -> @ V),
+    BertSelfOutput ((i, 1): dense -> dropout -> + residual -> LayerNorm) and BertOutput ((i, 2), same shape). A dropped
+    element is zero, a kept one is scaled by 1/(1-p) (torch.nn.functional.dropout)."""
+    def drop(t, site, p):
+        if dropout is None or p <= 0:
+            return t
+        return t * dropout["masks"][site].to(t.dtype).reshape(t.shape) / (1.0 - p)
+    ph = dropout["p_hidden"] if dropout else 0.0
+    pa = dropout["p_attn"] if dropout else 0.0
     b, n = input_ids.shape
     x = (sd[pre + "embeddings.word_embeddings.weight"][input_ids]
          + sd[pre + "embeddings.position_embeddings.weight"][:n][None]
          + sd[pre + "embeddings.token_type_embeddings.weight"][0][None, None])
     x = _ln(x, sd[pre + "embeddings.LayerNorm.weight"], sd[pre + "embeddings.LayerNorm.bias"], cfg.eps)
+    x = drop(x, (-1, 3), ph)
     dh = cfg.hidden // cfg.heads
     neg = torch.finfo(x.dtype).min
     add_mask = (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * neg
@@ -225,12 +237,12 @@ def bert_forward(input_ids, attention_mask, sd, pre, cfg: BertConfigLite):
         v = F.linear(x, sd[lp + "attention.self.value.weight"], sd[lp + "attention.self.value.bias"])
         q, k, v = (t.reshape(b, n, cfg.heads, dh).transpose(1, 2) for t in (q, k, v))
         s = q @ k.transpose(-1, -2) / math.sqrt(dh) + add_mask
-        a = (s.softmax(dim=-1) @ v).transpose(1, 2).reshape(b, n, cfg.hidden)
+        a = (drop(s.softmax(dim=-1), (i, 0), pa) @ v).transpose(1, 2).reshape(b, n, cfg.hidden)
         a = F.linear(a, sd[lp + "attention.output.dense.weight"], sd[lp + "attention.output.dense.bias"])
-        x = _ln(a + x, sd[lp + "attention.output.LayerNorm.weight"], sd[lp + "attention.output.LayerNorm.bias"], cfg.eps)
+        x = _ln(drop(a, (i, 1), ph) + x, sd[lp + "attention.output.LayerNorm.weight"], sd[lp + "attention.output.LayerNorm.bias"], cfg.eps)
         m = F.gelu(F.linear(x, sd[lp + "intermediate.dense.weight"], sd[lp + "intermediate.dense.bias"]))
         m = F.linear(m, sd[lp + "output.dense.weight"], sd[lp + "output.dense.bias"])
-        x = _ln(m + x, sd[lp + "output.LayerNorm.weight"], sd[lp + "output.LayerNorm.bias"], cfg.eps)
+        x = _ln(drop(m, (i, 2), ph) + x, sd[lp + "output.LayerNorm.weight"], sd[lp + "output.LayerNorm.bias"], cfg.eps)
     return x
 
 

@@ -131,3 +131,49 @@ def test_vq_restated_semantics():
     qq.sum().backward()
     assert torch.allclose(xx.grad, torch.ones_like(xx))  # straight-through estimator
     assert ii.shape == (2, 5) and loss.shape == (1,)
+
+
+def test_oracle_bert_dropout_sites_match_transformers_train_mode():
+    """Pins the oracle's dropout placement (embeddings / attention probabilities / BertSelfOutput / BertOutput) against
+    transformers.BertModel in TRAINING mode: torch.nn.functional.dropout is replaced by a function that applies the oracle's
+    keep masks in call order, so both sides drop exactly the same elements."""
+    import torch.nn.functional as F
+    from transformers import BertConfig, BertModel
+
+    from oracle import ctclip_oracle as O
+    layers, b, n, p = 2, 2, 12, 0.1
+    torch.manual_seed(0)
+    bert = BertModel(BertConfig(num_hidden_layers=layers, attn_implementation="eager", hidden_dropout_prob=p,
+                                attention_probs_dropout_prob=p)).train()
+    sd = {"t." + k: v for k, v in bert.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(5, 1000, (b, n), generator=g)
+    mask = torch.ones(b, n, dtype=torch.long)
+    mask[1, 8:] = 0
+    masks = {(-1, 3): torch.rand(b, n, 768, generator=g) > p}
+    order = [(-1, 3)]
+    for i in range(layers):
+        masks[(i, 0)] = torch.rand(b, 12, n, n, generator=g) > p
+        masks[(i, 1)] = torch.rand(b, n, 768, generator=g) > p
+        masks[(i, 2)] = torch.rand(b, n, 768, generator=g) > p
+        order += [(i, 0), (i, 1), (i, 2)]
+    ref = O.bert_forward(ids, mask, sd, "t.", O.BertConfigLite(layers=layers), dropout=dict(p_hidden=p, p_attn=p, masks=masks))
+    calls = []
+    real = F.dropout
+
+    def fake(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0:
+            return x
+        site = order[len(calls)]
+        calls.append(site)
+        return x * masks[site].to(x.dtype).reshape(x.shape) / (1.0 - p)
+    F.dropout = fake
+    torch.nn.functional.dropout = fake
+    try:
+        hf = bert(ids, attention_mask=mask)[0]
+    finally:
+        F.dropout = real
+        torch.nn.functional.dropout = real
+    assert calls == order, calls
+    valid = mask.bool()
+    assert (hf[valid] - ref[valid]).abs().max().item() < 1e-4
