@@ -67,6 +67,12 @@ class AttnArgs(C.Structure):
                 ("dropout_p", F32), ("dropout_seed", U64), ("dropout_offset", U64)]
 
 
+class PreprocessArgs(C.Structure):
+    _fields_ = [("raw", P), ("raw_dtype", I32), ("X", I32), ("Y", I32), ("Z", I32), ("slope", F32), ("intercept", F32),
+                ("xy_spacing", F32), ("z_spacing", F32), ("target_xy", F32), ("target_z", F32),
+                ("out_d", I32), ("out_h", I32), ("out_w", I32), ("out", P), ("out_dtype", I32), ("pad_value", F32)]
+
+
 class SgemmArgs(C.Structure):
     _fields_ = [("M", I32), ("N", I32), ("K", I32), ("A", P), ("lda", I64), ("trans_a", I32),
                 ("B", P), ("ldb", I64), ("trans_b", I32), ("C", P), ("ldc", I64), ("bias", P), ("act", I32),
@@ -110,6 +116,7 @@ SIGNATURES = {
     "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
     "ctclip_dropout": [P, P, P, P, I64, F32, U64, U64, P],
+    "ctclip_ct_preprocess": [C.POINTER(PreprocessArgs), P],
     "ctclip_vq_rerank": [P, P, P, P, I64, I32, P],
     "ctclip_vq_gather": [P, P, P, I64, I32, P],
     "ctclip_vq_gather_pool": [P, P, I32, I32, I32, I32, P, P, P],

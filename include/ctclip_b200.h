@@ -288,6 +288,27 @@ int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t
 int ctclip_geglu_bwd(const void* dg, int64_t ld_dg, void* h, int64_t ld_h, int64_t M, int32_t n_pairs, float* colsum,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GPU input pipeline (scripts/data.py:92-162 nii_img_to_tensor, scripts/data_inference_nii.py:96-176): raw NIfTI voxels
+ * (x, y, z)-contiguous as nibabel returns them -> slope/intercept -> trilinear resample to (target_xy, target_xy, target_z)
+ * spacing (F.interpolate, align_corners=False, size = int(dim * current / target)) -> clip [-1000, 1000] -> /1000 ->
+ * centre crop / pad (pad_value, reference: -1) -> out [out_d, out_h, out_w] = (z, x, y) order, the (1, 240, 480, 480) volume
+ * of the dataset contract. out_dtype 0: fp32 in [-1, 1]; 1: int16 HU (rounded), read as x/1000 by ctclip_patchify.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* raw;
+  int32_t raw_dtype;        /* 0 = float32, 1 = int16 */
+  int32_t X, Y, Z;
+  float slope, intercept;   /* RescaleSlope / RescaleIntercept of the metadata table */
+  float xy_spacing, z_spacing;
+  float target_xy, target_z;   /* reference: 0.75, 1.5 */
+  int32_t out_d, out_h, out_w; /* reference: 240, 480, 480 */
+  void* out;
+  int32_t out_dtype;
+  float pad_value;          /* reference: -1 */
+} ctclip_preprocess_args;
+int ctclip_ct_preprocess(const ctclip_preprocess_args* args, void* stream);
+
 /* Dropout with counter-based masks (csrc/rng.cuh: Philox4x32-10; element idx of a site is kept iff
  * philox(seed, offset + idx/4).word[idx%4] >= floor(p*2^32)), so backward regenerates the mask from the same (seed, offset):
  *   y = resid + keep * x / (1-p)   (resid optional; y_f32, y_bf16 optional outputs; n elements, 16-byte aligned pointers).

@@ -354,3 +354,40 @@ def synth_inputs(b, frames, image, n_text, seed=1234, vocab=30522):
     ids[torch.arange(b), lens - 1] = 3
     ids = ids * mask
     return hu, ids, mask
+
+
+# ------------------------------------------------------------------------------------------------
+# dataset pre-processing: restatement of scripts/data.py:12-34 (resize_array) + :92-162 (nii_img_to_tensor)
+# from the point where nibabel has produced the voxel array (`img_data = nii_img.get_fdata()`, float64, (x, y, z))
+# ------------------------------------------------------------------------------------------------
+def ct_preprocess(img_data, slope, intercept, xy_spacing, z_spacing, target_shape=(480, 480, 240)):
+    """Returns the (1, D, H, W) float32 tensor in [-1, 1] the reference dataset yields."""
+    import numpy as np
+    current = (z_spacing, xy_spacing, xy_spacing)
+    target = (1.5, 0.75, 0.75)
+    img_data = slope * np.asarray(img_data, dtype=np.float64) + intercept            # data.py:109
+    img_data = img_data.transpose(2, 0, 1)                                           # data.py:111
+    tensor = torch.tensor(img_data).unsqueeze(0).unsqueeze(0)
+    original_shape = tensor.shape[2:]
+    new_shape = [int(original_shape[i] * (current[i] / target[i])) for i in range(3)]        # data.py:26-31
+    resized = F.interpolate(tensor, size=new_shape, mode="trilinear", align_corners=False).cpu().numpy()
+    img_data = np.transpose(resized[0][0], (1, 2, 0))                                # data.py:117
+    img_data = (np.clip(img_data, -1000, 1000) / 1000).astype(np.float32)            # data.py:119-123
+    tensor = torch.tensor(img_data)
+    h, w, d = tensor.shape
+    dh, dw, dd = target_shape
+    h_start = max((h - dh) // 2, 0)
+    h_end = min(h_start + dh, h)
+    w_start = max((w - dw) // 2, 0)
+    w_end = min(w_start + dw, w)
+    d_start = max((d - dd) // 2, 0)
+    d_end = min(d_start + dd, d)
+    tensor = tensor[h_start:h_end, w_start:w_end, d_start:d_end]
+    pad_h_before = (dh - tensor.size(0)) // 2
+    pad_h_after = dh - tensor.size(0) - pad_h_before
+    pad_w_before = (dw - tensor.size(1)) // 2
+    pad_w_after = dw - tensor.size(1) - pad_w_before
+    pad_d_before = (dd - tensor.size(2)) // 2
+    pad_d_after = dd - tensor.size(2) - pad_d_before
+    tensor = F.pad(tensor, (pad_d_before, pad_d_after, pad_w_before, pad_w_after, pad_h_before, pad_h_after), value=-1)
+    return tensor.permute(2, 0, 1).unsqueeze(0)                                      # data.py:160-162
