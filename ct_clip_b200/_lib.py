@@ -69,7 +69,7 @@ class AttnArgs(C.Structure):
 
 class PreprocessArgs(C.Structure):
     _fields_ = [("raw", P), ("raw_dtype", I32), ("X", I32), ("Y", I32), ("Z", I32), ("slope", F32), ("intercept", F32),
-                ("xy_spacing", F32), ("z_spacing", F32), ("target_xy", F32), ("target_z", F32),
+                ("xy_spacing", C.c_double), ("z_spacing", C.c_double), ("target_xy", C.c_double), ("target_z", C.c_double),
                 ("out_d", I32), ("out_h", I32), ("out_w", I32), ("out", P), ("out_dtype", I32), ("pad_value", F32)]
 
 
@@ -117,6 +117,8 @@ SIGNATURES = {
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],
     "ctclip_dropout": [P, P, P, P, I64, F32, U64, U64, P],
     "ctclip_ct_preprocess": [C.POINTER(PreprocessArgs), P],
+    "ctclip_topk_rows": [P, I64, I32, I32, I32, P, P, P],
+    "ctclip_l2norm_rows_f32": [P, P, I32, I32, P],
     "ctclip_vq_rerank": [P, P, P, P, I64, I32, P],
     "ctclip_vq_gather": [P, P, P, I64, I32, P],
     "ctclip_vq_gather_pool": [P, P, I32, I32, I32, I32, P, P, P],
@@ -130,7 +132,7 @@ SIGNATURES = {
     "ctclip_clip_loss": [C.POINTER(LossArgs), P],
     "ctclip_clip_sims": [P, I32, P, I32, I32, P, P, P],
     "ctclip_grad_sumsq": [P, I64, P, P],
-    "ctclip_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, I32, F32, P, F32, P],
+    "ctclip_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, I32, F32, P, F32, F32, I64, P],
     "ctclip_bert_embed": [P, P, P, P, P, I64, I32, I32, P],
     "ctclip_bert_embed_bwd": [P, P, P, P, I64, I32, I32, P],
     "ctclip_gelu_bwd": [P, I64, P, I64, I64, I32, P, P],

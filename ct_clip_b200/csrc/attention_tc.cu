@@ -169,20 +169,21 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         if (warp_valid) {
           tc_fence_after();
           const uint32_t scol = lane_base + st * NCH + hf * HALF;
-          uint32_t sv[HALF];
-#pragma unroll
-          for (int g = 0; g < HALF / 16; g++) tmem_ld_32x16(scol + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&sv[g * 16]));
-          tmem_ld_wait();
+          // groups of 16 keys: the TMEM load of group g+1 is in flight while group g goes through the exponentials
+          uint32_t sv[HALF / 16][16];
+          tmem_ld_32x16(scol, sv[0]);
           const int j0 = c * NCH + hf * HALF;              // multiple of W
           const float* tp = sTab + (qi - (j0 / W) * STR);
 #pragma unroll
           for (int g = 0; g < HALF / 16; g++) {
+            tmem_ld_wait_dep1(sv[g]);
+            if (g + 1 < HALF / 16) tmem_ld_32x16(scol + (g + 1) * 16, sv[g + 1]);
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
               const int cc = g * 16 + e;
-              const float x0 = fmaf(__uint_as_float(sv[cc]), sc2, tp[-TcGeom<W>::off(cc)]);
-              const float x1 = fmaf(__uint_as_float(sv[cc + 1]), sc2, tp[-TcGeom<W>::off(cc + 1)]);
+              const float x0 = fmaf(__uint_as_float(sv[g][e]), sc2, tp[-TcGeom<W>::off(cc)]);
+              const float x1 = fmaf(__uint_as_float(sv[g][e + 1]), sc2, tp[-TcGeom<W>::off(cc + 1)]);
               const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
               l0 += p0;
               l1 += p1;
@@ -237,8 +238,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       }
     }
   } else {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (all 32 lanes run the loop; tcgen05 instructions on the elected lane) =====================
+    {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, NCH);
       constexpr uint32_t idesc_pv = umma_idesc(1, 0, 1, 128, 32);     // A = P from TMEM (K-major), B = V MN-major
       constexpr uint32_t hi64 = umma_desc_hi(512, SW64);              // every operand tile here: 64-byte rows, 8-row groups 512 B apart
@@ -250,10 +252,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         if (cs == 0) mbar_wait_tag(&q_full[ts & 1], (ts >> 1) & 1, 30 + (ts & 1));
         tc_fence_after();
         const uint32_t ql = q_lo + (ts & 1) * (8192 >> 4), kl = k_lo + (uint32_t)cs * (NCH * 64 >> 4);
-        umma_bf16(tmem_base + st * NCH, umma_desc_join(ql, hi64), umma_desc_join(kl, hi64), idesc_s, 0u);
-        umma_bf16(tmem_base + st * NCH, umma_desc_join(ql + 2, hi64), umma_desc_join(kl + 2, hi64), idesc_s, 1u);
-        umma_commit(&s_full[st]);
-        if (cs == NC - 1) umma_commit(&q_empty[ts & 1]);   // every S MMA of this Q tile has been issued
+        if (leader) {
+          umma_bf16(tmem_base + st * NCH, umma_desc_join(ql, hi64), umma_desc_join(kl, hi64), idesc_s, 0u);
+          umma_bf16(tmem_base + st * NCH, umma_desc_join(ql + 2, hi64), umma_desc_join(kl + 2, hi64), idesc_s, 1u);
+          umma_commit(&s_full[st]);
+          if (cs == NC - 1) umma_commit(&q_empty[ts & 1]);   // every S MMA of this Q tile has been issued
+        }
+        __syncwarp();
         if (++cs == NC) { cs = 0; ts++; }
       };
       mbar_wait_tag(k_full, 0, 32);
@@ -266,13 +271,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         mbar_wait_tag(&p_full[st], (b >> 1) & 1, 34 + st);
         tc_fence_after();
         const uint32_t vl = v_lo + (uint32_t)c * (NCH * 64 >> 4);
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < NCH / 16; ks++) {
-          const int k0 = ks * 16;
-          const uint32_t acol = st * NCH + (k0 / HALF) * HALF + (k0 % HALF) / 2;
-          umma_bf16_ts(tmem_base + OCOL, tmem_base + acol, umma_desc_join(vl + ks * (1024 >> 4), hi64), idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < NCH / 16; ks++) {
+            const int k0 = ks * 16;
+            const uint32_t acol = st * NCH + (k0 / HALF) * HALF + (k0 % HALF) / 2;
+            umma_bf16_ts(tmem_base + OCOL, tmem_base + acol, umma_desc_join(vl + ks * (1024 >> 4), hi64), idesc_pv, (c > 0 || ks > 0) ? 1u : 0u);
+          }
+          if (c == NC - 1) umma_commit(o_full);
         }
-        if (c == NC - 1) umma_commit(o_full);
+        __syncwarp();
         if (++c == NC) c = 0;
       }
     }
@@ -460,23 +468,31 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           if (warp_valid) {
             tc_fence_after();
             const uint32_t scol = lane_base + st * 128 + hf * 32;
-            uint32_t sv[32], dp[32];
-            tmem_ld_32x32(scol, sv);
-            tmem_ld_32x32(scol + 64, dp);
-            tmem_ld_wait();
+            // two groups of 16 queries: the TMEM loads of the second group are in flight while the first one is computed
+            uint32_t sv0[16], dp0[16], sv1[16], dp1[16];
+            tmem_ld_32x16(scol, sv0);
+            tmem_ld_32x16(scol + 64, dp0);
+            tmem_ld_wait_dep(sv0, dp0);
+            tmem_ld_32x16(scol + 16, sv1);
+            tmem_ld_32x16(scol + 64 + 16, dp1);
             const float4* rec = reinterpret_cast<const float4*>(sQD + slot * TCB_QD_BYTES + 8192) + hf * 32;
             const float* tp = sTab + tj;
             uint32_t pk[16], dk_[16];
+            auto half16 = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int base) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const float4 r0 = rec[e], r1 = rec[e + 1];            // {lse_i, delta_i, ci}: broadcast LDS.128
-              const float x0 = fmaf(__uint_as_float(sv[e]), sc2, tp[__float_as_int(r0.z)]) - r0.x;
-              const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, tp[__float_as_int(r1.z)]) - r1.x;
-              const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-              const float d0 = p0 * (__uint_as_float(dp[e]) - r0.y), d1 = p1 * (__uint_as_float(dp[e + 1]) - r1.y);
-              pk[e / 2] = pack_bf16x2(p0, p1);
-              dk_[e / 2] = pack_bf16x2(d0, d1);
-            }
+              for (int e = 0; e < 16; e += 2) {
+                const float4 r0 = rec[base + e], r1 = rec[base + e + 1];   // {lse_i, delta_i, ci}: broadcast LDS.128
+                const float x0 = fmaf(__uint_as_float(sv[e]), sc2, tp[__float_as_int(r0.z)]) - r0.x;
+                const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, tp[__float_as_int(r1.z)]) - r1.x;
+                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                const float d0 = p0 * (__uint_as_float(dp[e]) - r0.y), d1 = p1 * (__uint_as_float(dp[e + 1]) - r1.y);
+                pk[(base + e) / 2] = pack_bf16x2(p0, p1);
+                dk_[(base + e) / 2] = pack_bf16x2(d0, d1);
+              }
+            };
+            half16(sv0, dp0, 0);
+            tmem_ld_wait_dep(sv1, dp1);
+            half16(sv1, dp1, 16);
             tmem_st_32x16(scol, pk);                                 // P^T over this warp's own S^T columns
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++)
@@ -559,8 +575,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       }
     }
   } else {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && total_blocks > 0) {
+    // ===================== MMA issuer (all 32 lanes run the loop; tcgen05 instructions on the elected lane) =====================
+    if (total_blocks > 0) {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc_s = umma_idesc(1, 0, 0, 128, 64);     // S^T, dP^T : A, B K-major
       constexpr uint32_t idesc_dv = umma_idesc(1, 0, 1, 128, 32);    // dV (A TMEM), dK (A smem K-major): B MN-major
       constexpr uint32_t idesc_dq = umma_idesc(1, 1, 1, 128, 32);    // dQ: A, B MN-major
@@ -579,11 +596,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t kA = kv_lo_k + ks * (16384 >> 4), vA = kA + (8192 >> 4);
         const uint32_t qB = qd_lo_k + s_slot * (TCB_QD_BYTES >> 4), dB = qB + (4096 >> 4);
         const uint32_t d0 = tmem_base + s_st * 128;
-        umma_bf16(d0, umma_desc_join(kA, hi64), umma_desc_join(qB, hi64), idesc_s, 0u);
-        umma_bf16(d0, umma_desc_join(kA + 2, hi64), umma_desc_join(qB + 2, hi64), idesc_s, 1u);
-        umma_bf16(d0 + 64, umma_desc_join(vA, hi64), umma_desc_join(dB, hi64), idesc_s, 0u);
-        umma_bf16(d0 + 64, umma_desc_join(vA + 2, hi64), umma_desc_join(dB + 2, hi64), idesc_s, 1u);
-        umma_commit(&s_full[s_st]);
+        if (leader) {
+          umma_bf16(d0, umma_desc_join(kA, hi64), umma_desc_join(qB, hi64), idesc_s, 0u);
+          umma_bf16(d0, umma_desc_join(kA + 2, hi64), umma_desc_join(qB + 2, hi64), idesc_s, 1u);
+          umma_bf16(d0 + 64, umma_desc_join(vA, hi64), umma_desc_join(dB, hi64), idesc_s, 0u);
+          umma_bf16(d0 + 64, umma_desc_join(vA + 2, hi64), umma_desc_join(dB + 2, hi64), idesc_s, 1u);
+          umma_commit(&s_full[s_st]);
+        }
+        __syncwarp();
         s_st ^= 1;
         if (++s_slot == TCB_QD_SLOTS) { s_slot = 0; s_qpar ^= 1; }
         if (++s_qc == NQC) { s_qc = 0; s_ub++; }
@@ -602,6 +622,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t tile_k = ds_lo_k + buf * (32768 >> 4) + grp * (16384 >> 4);
         const uint32_t acol = tmem_base + st * 128;
         const uint32_t acc0 = qc > 0 ? 1u : 0u;
+        if (leader) {
         // dV += P^T dO_c : K = 64 queries, A = P^T in TMEM (16 queries = 8 columns; the two column halves sit 32 columns apart)
         umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 0, umma_desc_join(dmn, hi64), idesc_dv, acc0);
         umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 8, umma_desc_join(dmn + (1024 >> 4), hi64), idesc_dv, 1u);
@@ -621,13 +642,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             umma_bf16(dqc, umma_desc_join(tile_mn + k8 * (2048 >> 4), hi128), umma_desc_join(kmn + k8 * (1024 >> 4), hi64), idesc_dq,
                       (kb > 0 || k8 > 0) ? 1u : 0u);
           umma_commit(&ds_free[buf]);
-          v++;
         }
         if (qc == NQC - 1) {
           umma_commit(&kv_empty[ks]);
           umma_commit(acc_full);
           if (kb == NKB - 1) umma_commit(dq_full);
         }
+        }   // leader
+        __syncwarp();
+        if (grp == 1 || qc == NQC - 1) v++;
         // advance
         if (st == 1) ppar ^= 1;
         st ^= 1;

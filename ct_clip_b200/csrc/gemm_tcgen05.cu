@@ -1051,10 +1051,11 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_args* a, void* stream_) {
   if (a->epilogue == EPI_BIAS_GELU) CTB_CHECK_ARG(a->ldc % 8 == 0 && (a->C2 == nullptr || a->ldc2 % 8 == 0), "gemm: BIAS_GELU needs 16B-aligned rows");
   CTB_CHECK_ARG(a->splits >= 0, "gemm: splits must be >= 0 (0 = choose automatically, ATOMIC_F32 only)");
   CTB_CHECK_ARG(a->splits == 1 || a->epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the ATOMIC_F32 epilogue");
-  if (a->epilogue == EPI_ARGMAX) CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
-  if (a->epilogue == EPI_ARGMAX && a->arg2_out != nullptr)
-    CTB_CHECK_ARG(a->N >= 2 && a->N <= 8192, "gemm: ARGMAX with arg2_out packs the column into 13 mantissa bits: N must be in [2, 8192] (got %d)", a->N);
-  else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU || a->epilogue == EPI_L2NORM, "gemm: null C");
+  if (a->epilogue == EPI_ARGMAX) {
+    CTB_CHECK_ARG(a->arg_out != nullptr, "gemm: ARGMAX needs arg_out");
+    if (a->arg2_out != nullptr)
+      CTB_CHECK_ARG(a->N >= 2 && a->N <= 8192, "gemm: ARGMAX with arg2_out packs the column into 13 mantissa bits: N must be in [2, 8192] (got %d)", a->N);
+  } else CTB_CHECK_ARG(a->C != nullptr || a->epilogue == EPI_GEGLU || a->epilogue == EPI_L2NORM, "gemm: null C");
   if (a->epilogue == EPI_GEGLU) CTB_CHECK_ARG(a->C2 != nullptr && (a->N % 2) == 0, "gemm: GEGLU needs C2 and even N");
   if (a->epilogue == EPI_RESID_F32) CTB_CHECK_ARG(a->resid != nullptr, "gemm: RESID_F32 needs resid");
 

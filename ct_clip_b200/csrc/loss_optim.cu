@@ -156,11 +156,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
-// torch.nn.utils.clip_grad_norm_ (coef = min(1, max_norm/(norm+1e-6))) followed by torch.optim.Adam (no amsgrad, wd=0)
+// torch.nn.utils.clip_grad_norm_ (coef = min(1, max_norm/(norm+1e-6))) followed by torch.optim.Adam (no amsgrad), or -- with
+// decay_mul < 1 -- torch.optim.AdamW: the first n_decay elements of the arena (the tensors with ndim >= 2, optimizer.py:3-8,
+// 26-34) are multiplied by decay_mul = 1 - lr * weight_decay before the Adam update (decoupled weight decay).
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                   float* __restrict__ v, long long n, float lr, float beta1, float beta2,
                                                   float eps, float bc1, float bc2_sqrt, float max_norm,
-                                                  const float* __restrict__ sumsq, float grad_scale) {
+                                                  const float* __restrict__ sumsq, float grad_scale, float decay_mul,
+                                                  long long n_decay) {
   float coef = grad_scale;
   if (max_norm > 0.f && sumsq != nullptr) {
     const float norm = sqrtf(sumsq[0]) * grad_scale;
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 g4 = reinterpret_cast<const float4*>(g)[i];
     float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    if (4 * i < n_decay) { p4.x *= decay_mul; p4.y *= decay_mul; p4.z *= decay_mul; p4.w *= decay_mul; }   // n_decay % 4 == 0
     upd(g4.x, m4.x, v4.x, p4.x);
     upd(g4.y, m4.y, v4.y, p4.y);
     upd(g4.z, m4.z, v4.z, p4.z);
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float mi = m[i], vi = v[i], pi = p[i];
+    if (i < n_decay) pi *= decay_mul;
     upd(g[i], mi, vi, pi);
     m[i] = mi;
     v[i] = vi;
@@ -249,16 +254,17 @@ extern "C" int ctclip_grad_sumsq(const float* g, int64_t n, float* out, void* st
 
 extern "C" int ctclip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                                 float eps, int32_t step, float max_norm, const float* sumsq, float grad_scale,
-                                void* stream_) {
+                                float weight_decay, int64_t n_decay, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adam_step: bad args");
+  CTB_CHECK_ARG(weight_decay >= 0.f && n_decay >= 0 && n_decay <= n && n_decay % 4 == 0, "adam_step: bad weight-decay range");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   long long ctas = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (ctas > cap) ctas = cap;
   adam_kernel<<<(int)ctas, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, sumsq,
-                                            grad_scale);
+                                            grad_scale, 1.f - lr * weight_decay, weight_decay > 0.f ? (long long)n_decay : 0LL);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

@@ -84,14 +84,14 @@ extern "C" int ctclip_ct_preprocess(const ctclip_preprocess_args* p, void* strea
   CTB_CHECK_ARG(p->raw_dtype == 0 || p->raw_dtype == 1, "ct_preprocess: raw_dtype must be 0 (float32) or 1 (int16)");
   CTB_CHECK_ARG(p->out_dtype == 0 || p->out_dtype == 1, "ct_preprocess: out_dtype must be 0 (float32) or 1 (int16 HU)");
   CTB_CHECK_ARG(p->X > 0 && p->Y > 0 && p->Z > 0 && p->out_d > 0 && p->out_h > 0 && p->out_w > 0, "ct_preprocess: bad dims");
-  CTB_CHECK_ARG(p->xy_spacing > 0.f && p->z_spacing > 0.f && p->target_xy > 0.f && p->target_z > 0.f, "ct_preprocess: bad spacing");
+  CTB_CHECK_ARG(p->xy_spacing > 0. && p->z_spacing > 0. && p->target_xy > 0. && p->target_z > 0., "ct_preprocess: bad spacing");
   PreArgs a;
   a.raw = p->raw; a.raw_dtype = p->raw_dtype; a.X = p->X; a.Y = p->Y; a.Z = p->Z;
   a.slope = p->slope; a.intercept = p->intercept;
   // data.py:26-31: new_shape = int(original * current / target), evaluated in double like Python floats
-  a.Zr = (int)((double)p->Z * ((double)p->z_spacing / (double)p->target_z));
-  a.Xr = (int)((double)p->X * ((double)p->xy_spacing / (double)p->target_xy));
-  a.Yr = (int)((double)p->Y * ((double)p->xy_spacing / (double)p->target_xy));
+  a.Zr = (int)((double)p->Z * (p->z_spacing / p->target_z));
+  a.Xr = (int)((double)p->X * (p->xy_spacing / p->target_xy));
+  a.Yr = (int)((double)p->Y * (p->xy_spacing / p->target_xy));
   CTB_CHECK_ARG(a.Zr > 0 && a.Xr > 0 && a.Yr > 0, "ct_preprocess: resized volume is empty");
   a.sz = (float)((double)p->Z / (double)a.Zr); a.sx = (float)((double)p->X / (double)a.Xr); a.sy = (float)((double)p->Y / (double)a.Yr);
   a.D = p->out_d; a.H = p->out_h; a.W = p->out_w;

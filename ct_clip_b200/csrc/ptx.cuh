@@ -214,6 +214,18 @@ __device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+// One elected lane of a CONVERGED warp (elect.sync): the MMA-issuing warp runs its loop with all 32 lanes and predicates only the
+// tcgen05 instructions on this, so that ptxas keeps descriptors / addresses in uniform registers (an `if (lane == 0)` region is
+// divergent code: every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY serialisation loop, ~10 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // 32 lanes x 16 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -239,6 +251,24 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
       : "memory");
+}
+// tcgen05.wait::ld that also NAMES the registers of the loads it completes ("+r"): arithmetic on them cannot be scheduled above
+// the wait by the compiler (needed once loads of a later group are deliberately left in flight across other work).
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]),
+                 "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]),
+                 "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep1(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

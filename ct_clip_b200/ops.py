@@ -357,9 +357,11 @@ def grad_sumsq(g, n, out):
     call("ctclip_grad_sumsq", g.data_ptr(), n, out.data_ptr(), _stream(), work=("B", 4.0 * n))
 
 
-def adam_step(p, g, m, v, n, *, lr, beta1=0.9, beta2=0.99, eps=1e-8, step, max_norm=0.0, sumsq=None, grad_scale=1.0):
+def adam_step(p, g, m, v, n, *, lr, beta1=0.9, beta2=0.99, eps=1e-8, step, max_norm=0.0, sumsq=None, grad_scale=1.0,
+              weight_decay=0.0, n_decay=0):
+    """weight_decay > 0: AdamW with decoupled decay on the first n_decay elements (the ndim >= 2 tensors, laid out first)."""
     call("ctclip_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps, step,
-         max_norm, _ptr(sumsq), grad_scale, _stream(), work=("B", 28.0 * n))
+         max_norm, _ptr(sumsq), grad_scale, weight_decay, n_decay, _stream(), work=("B", 28.0 * n))
 
 
 def bert_embed(ids, word, pos, type0, out, rows, n, H):

@@ -50,11 +50,18 @@ class ParamArena:
     def __init__(self, named_params, device):
         self.names, self.params, self.offsets = [], [], []
         off = 0
-        for n, p in named_params:
+        # tensors with ndim >= 2 first: they are the weight-decayed group of the reference's AdamW (optimizer.py:3-8, 26-34), so
+        # decoupled weight decay is "scale the first n_decay elements" inside the Adam kernel -- no mask, no extra pass
+        named_params = list(named_params)
+        ordered = [(n, p) for n, p in named_params if p.ndim >= 2] + [(n, p) for n, p in named_params if p.ndim < 2]
+        self.n_decay = 0
+        for n, p in ordered:
             self.names.append(n)
             self.params.append(p)
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            if p.ndim >= 2:
+                self.n_decay = off
         self.numel = max(off, 4)
         self.p = torch.zeros(self.numel, device=device)
         self.g = torch.zeros(self.numel, device=device)
@@ -77,12 +84,14 @@ class ParamArena:
             if p.grad is None or p.grad.data_ptr() != self.grad_views[n].data_ptr():
                 p.grad = self.grad_views[n]
 
-    def adam_step(self, *, lr, max_norm, grad_scale=1.0, betas=(0.9, 0.99), eps=1e-8):
+    def adam_step(self, *, lr, max_norm, grad_scale=1.0, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0):
+        """weight_decay == 0: Adam (optimizer.py:23-24); > 0: AdamW on the ndim >= 2 tensors (optimizer.py:26-34)."""
         self.step += 1
         self.sumsq.zero_()
         ops.grad_sumsq(self.g, self.numel, self.sumsq)
         ops.adam_step(self.p, self.g, self.m, self.v, self.numel, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
-                      step=self.step, max_norm=(max_norm or 0.0), sumsq=self.sumsq, grad_scale=grad_scale)
+                      step=self.step, max_norm=(max_norm or 0.0), sumsq=self.sumsq, grad_scale=grad_scale,
+                      weight_decay=weight_decay, n_decay=self.n_decay)
 
     def state_dict(self):
         return dict(step=self.step, names=list(self.names), offsets=list(self.offsets), exp_avg=self.m.cpu(),
@@ -103,7 +112,7 @@ class CTClipTrainer(nn.Module):
                  results_folder='./ctclip/', num_workers=8, accelerate_kwargs: dict = dict(),
                  train_dataset=None, valid_dataset=None, text_max_length=512, async_checkpoints=False):
         super().__init__()
-        assert wd == 0., "the reference trains with wd=0 (Adam, optimizer.py:23-24); AdamW is not part of this build"
+        self.wd = float(wd)      # 0 (reference default): Adam; > 0: AdamW on the ndim >= 2 tensors (optimizer.py:10-34)
         if not torch.cuda.is_available():
             raise RuntimeError("CTClipTrainer needs a CUDA (sm_100a) device: there is no CPU training path")
         self.world, self.rank, local = _dist_env()
@@ -238,7 +247,7 @@ class CTClipTrainer(nn.Module):
         if ev is not None:       # an asynchronous checkpoint copy may still be reading the parameters
             torch.cuda.current_stream().wait_event(ev)
             self._ckpt_event = None
-        self.arena.adam_step(lr=self.lr, max_norm=self.max_grad_norm)
+        self.arena.adam_step(lr=self.lr, max_norm=self.max_grad_norm, weight_decay=self.wd)
         self.CTClip.mark_weights_dirty()
         return loss
 

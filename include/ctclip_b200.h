@@ -300,14 +300,20 @@ typedef struct {
   int32_t raw_dtype;        /* 0 = float32, 1 = int16 */
   int32_t X, Y, Z;
   float slope, intercept;   /* RescaleSlope / RescaleIntercept of the metadata table */
-  float xy_spacing, z_spacing;
-  float target_xy, target_z;   /* reference: 0.75, 1.5 */
+  double xy_spacing, z_spacing;   /* doubles: the resized shape int(dim * (current / target)) must round like the reference's */
+  double target_xy, target_z;     /* Python floats (0.6 / 0.75 * 40 = 31.999999999999996 -> 31); reference targets: 0.75, 1.5 */
   int32_t out_d, out_h, out_w; /* reference: 240, 480, 480 */
   void* out;
   int32_t out_dtype;
   float pad_value;          /* reference: -1 */
 } ctclip_preprocess_args;
 int ctclip_ct_preprocess(const ctclip_preprocess_args* args, void* stream);
+
+/* Retrieval over saved latents (scripts/report_to_volume_new.py:47-63, scripts/volume_to_volume_new.py:80-96): the k best
+ * columns of every row of scores fp32 [Q, ld >= G], descending, lower index first among equal scores (Python's stable
+ * sorted(..., reverse=True)); G <= 49152. ctclip_l2norm_rows_f32: y = x / max(||x||, 1e-12) per row (cosine similarity). */
+int ctclip_topk_rows(const float* scores, int64_t ld, int32_t Q, int32_t G, int32_t k, int32_t* idx_out, float* val_out, void* stream);
+int ctclip_l2norm_rows_f32(const float* x, float* y, int32_t rows, int32_t D, void* stream);
 
 /* Dropout with counter-based masks (csrc/rng.cuh: Philox4x32-10; element idx of a site is kept iff
  * philox(seed, offset + idx/4).word[idx%4] >= floor(p*2^32)), so backward regenerates the mask from the same (seed, offset):
@@ -386,10 +392,13 @@ int ctclip_clip_sims(const float* t_hat, int32_t Bt, const float* i_hat, int32_t
                      float* out, void* stream);
 
 /* Optimiser over a flat fp32 arena: out[0] += sum g^2; then clip_grad_norm_(max_norm) + Adam
- * (CTCLIPTrainer.py:259-263, optimizer.py:23-24). grad_scale multiplies g before everything else. */
+ * (CTCLIPTrainer.py:259-263, optimizer.py:23-24). grad_scale multiplies g before everything else.
+ * weight_decay > 0 = torch.optim.AdamW (optimizer.py:26-34): the first n_decay elements (a multiple of 4; the caller lays
+ * the ndim >= 2 tensors out first, optimizer.py:3-8) are scaled by 1 - lr*weight_decay before the Adam update. */
 int ctclip_grad_sumsq(const float* g, int64_t n, float* out, void* stream);
 int ctclip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                     int32_t step, float max_norm, const float* sumsq, float grad_scale, void* stream);
+                     int32_t step, float max_norm, const float* sumsq, float grad_scale, float weight_decay, int64_t n_decay,
+                     void* stream);
 
 /* BERT text tower helpers (transformers.BertModel, called at ct_clip.py:685): embeddings gather
  * (word[ids] + position + token_type 0) and its scatter-add backward; GELU backward of BertIntermediate

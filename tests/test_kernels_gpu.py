@@ -311,3 +311,23 @@ def test_adam_and_clip():
         ops.grad_sumsq(gi, n, ss)
         ops.adam_step(pw, gi, m, v, n, lr=1e-3, step=step, max_norm=0.5, sumsq=ss)
     assert rel_err(pw, pr.data) < 1e-5
+
+
+def test_adamw_decoupled_decay_on_leading_range():
+    """AdamW of the reference's get_optimizer (optimizer.py:26-34): weight decay on the ndim >= 2 tensors only, which the arena
+    lays out first; against torch.optim.AdamW with the same two parameter groups."""
+    from ct_clip_b200 import ops
+    n_w, n_b = 4096 * 8, 1000                       # a [4096, 8] weight (decayed) followed by a bias vector (not decayed)
+    w0, b0 = _randn(n_w, seed=40), _randn(n_b, seed=41)
+    gw, gb = _randn(n_w, seed=42) * 0.01, _randn(n_b, seed=43) * 0.01
+    wr, br = torch.nn.Parameter(w0.clone().view(4096, 8)), torch.nn.Parameter(b0.clone())
+    opt = torch.optim.AdamW([{"params": [wr]}, {"params": [br], "weight_decay": 0}], lr=1e-2, weight_decay=0.1, betas=(0.9, 0.99), eps=1e-8)
+    n = n_w + n_b
+    p = torch.cat([w0, b0]).clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        wr.grad, br.grad = (gw * step).view(4096, 8).clone(), (gb * step).clone()
+        opt.step()
+        g = torch.cat([gw, gb]) * step
+        ops.adam_step(p, g, m, v, n, lr=1e-2, step=step, weight_decay=0.1, n_decay=n_w)
+    assert rel_err(p[:n_w], wr.data.view(-1)) < 1e-5 and rel_err(p[n_w:], br.data) < 1e-5
