@@ -105,6 +105,7 @@ SIGNATURES = {
     "ctclip_attn_bwd": [C.POINTER(AttnArgs), P],
     "ctclip_attn_tc_supported": [I32, I32, I32, I32],
     "ctclip_qk_bound": [P, P, I32, P, P],
+    "ctclip_debug_set_attn_bwd_warps": [I32],
     "ctclip_l2norm_bwd": [P, I64, P, I64, P, P, I64, P, I64, I32, I32, P],
     "ctclip_sgemm_f32": [C.POINTER(SgemmArgs), P],
     "ctclip_colsum": [P, I32, I64, I64, I32, P, P],

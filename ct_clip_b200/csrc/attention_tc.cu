@@ -332,8 +332,11 @@ constexpr int TCB_QD_BYTES = 4096 + 4096 + 64 * 16;   // Q chunk, dO chunk, per-
 constexpr int TCB_COL_DV = 256, TCB_COL_DK = 288, TCB_COL_DQ = 320;
 constexpr uint32_t SW128 = 2;
 
-template <int W>
-__global__ void __launch_bounds__(320, 1)
+// EW = number of softmax-backward warps (8 or 16): warp w owns TMEM lanes 32*(w & 3).. and the (w >> 2)-th slice of CW = 256 / EW
+// query columns of every half-block. 16 warps (4 per scheduler) hide the LDS -> LDS -> MUFU latency chain of the element loop
+// that 8 warps (2 per scheduler, 38 % issue utilisation in profiles/r2c) leave exposed.
+template <int W, int EW>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv, const TcBwdParams p) {
   constexpr int STR = TcGeom<W>::STR;
@@ -356,7 +359,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint64_t* acc_full = bars + 18;
   uint64_t* dq_full = bars + 19;
   uint32_t* holder = reinterpret_cast<uint32_t*>(bars + 20);
-  float* sRed = reinterpret_cast<float*>(holder + 2);    // [10]
+  float* sRed = reinterpret_cast<float*>(holder + 2);    // [EW + 2]
+  constexpr int NTHREADS = (EW + 2) * 32;
+  constexpr int CW = 256 / EW;                           // query columns per warp and half-block (32 or 16)
+  constexpr int NG = CW / 16;                            // groups of 16 columns
+  constexpr int CPR = CW / 8;                            // 16-byte chunks of a dS row per warp
+  constexpr int DC = 128 / EW;                           // accumulator columns a warp drains (16 or 8)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NKB = (n + 127) / 128, NQC = n / 64;
@@ -365,7 +373,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const long long total_blocks = (long long)my_items * BPI;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == EW && lane == 0) {
     tma_prefetch_desc(&tq);
     tma_prefetch_desc(&tdo);
     tma_prefetch_desc(&tk);
@@ -374,7 +382,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[i], EW);
       mbar_init(&ds_free[i], 1);
     }
     for (int i = 0; i < TCB_QD_SLOTS; i++) {
@@ -385,7 +393,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     mbar_init(dq_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == EW + 1) {
     tmem_alloc(holder, 512);
     tmem_relinquish();
   }
@@ -393,42 +401,44 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   // gridDim.x % heads == 0 (enforced by the launcher) every item of this CTA has the same head.
   const int head = (int)blockIdx.x % p.heads;
   tc_fence_before();
-  (void)tc_load_table<W>(sTab, sRed, p.table, nullptr, 0.f, p.H, p.heads, head, tid, 320);   // table * log2e (no reference shift: lse is subtracted)
+  (void)tc_load_table<W>(sTab, sRed, p.table, nullptr, 0.f, p.H, p.heads, head, tid, NTHREADS);   // table * log2e (no reference shift: lse is subtracted)
   tc_fence_after();
   const uint32_t tmem_base = *holder;
   const float sc2 = p.scale * kTcLog2e;
 
-  if (warp < 8) {
+  if (warp < EW) {
     // ===================== softmax-backward warps =====================
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;
     const int r = q * 32 + lane;                          // key row inside the block = TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     int u = 0, v = 0, m = 0;                              // key blocks, query pairs, items completed so far (ring parities)
     int prev_item = 0, prev_kb = 0;
     long long g = 0;
+    auto ld_acc = [&](uint32_t col, uint32_t (&a)[DC]) {
+      if constexpr (DC == 16) tmem_ld_32x16(col, a);
+      else tmem_ld_32x8(col, a);
+    };
+    auto st_acc = [&](__nv_bfloat16* dst, const uint32_t (&a)[DC], float mul) {   // DC fp32 -> bf16, DC * 2 bytes
+      uint32_t x[DC / 2];
+#pragma unroll
+      for (int e = 0; e < DC / 2; e++) x[e] = pack_bf16x2(__uint_as_float(a[2 * e]) * mul, __uint_as_float(a[2 * e + 1]) * mul);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int e = 0; e < DC / 8; e++) d4[e] = make_uint4(x[4 * e], x[4 * e + 1], x[4 * e + 2], x[4 * e + 3]);
+    };
     auto drain_dvdk = [&](int item_, int kb_, uint32_t parity) {   // dV / dK of key block (item_, kb_): TMEM -> bf16 -> global
       mbar_wait_tag(acc_full, parity, 40);
       tc_fence_after();
       const int key = kb_ * 128 + r;
-      uint32_t a[16], b[16];
-      tmem_ld_32x16(lane_base + TCB_COL_DV + hf * 16, a);
-      tmem_ld_32x16(lane_base + TCB_COL_DK + hf * 16, b);
+      uint32_t a[DC], b[DC];
+      ld_acc(lane_base + TCB_COL_DV + cq * DC, a);
+      ld_acc(lane_base + TCB_COL_DK + cq * DC, b);
       tmem_ld_wait();
       if (key < n) {
         const int hd = item_ % p.heads;
         const long long row = (long long)(item_ / p.heads) * n + key;
-        uint32_t x[8], y[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          x[e] = pack_bf16x2(__uint_as_float(a[2 * e]), __uint_as_float(a[2 * e + 1]));
-          y[e] = pack_bf16x2(__uint_as_float(b[2 * e]) * p.scale, __uint_as_float(b[2 * e + 1]) * p.scale);
-        }
-        uint4* pv = reinterpret_cast<uint4*>(p.dv + row * p.ld_dv + hd * 32 + hf * 16);
-        uint4* pk = reinterpret_cast<uint4*>(p.dk + row * p.ld_dk + hd * 32 + hf * 16);
-        pv[0] = make_uint4(x[0], x[1], x[2], x[3]);
-        pv[1] = make_uint4(x[4], x[5], x[6], x[7]);
-        pk[0] = make_uint4(y[0], y[1], y[2], y[3]);
-        pk[1] = make_uint4(y[4], y[5], y[6], y[7]);
+        st_acc(p.dv + row * p.ld_dv + hd * 32 + cq * DC, a, 1.0f);
+        st_acc(p.dk + row * p.ld_dk + hd * 32 + cq * DC, b, p.scale);
       }
     };
     auto drain_dq = [&](int item_, uint32_t parity) {     // dQ of a finished item: NKB tiles of 128 queries
@@ -437,17 +447,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const int hd = item_ % p.heads;
       for (int t = 0; t < NKB; t++) {
         const int qi = t * 128 + r;
-        uint32_t a[16];
-        tmem_ld_32x16(lane_base + TCB_COL_DQ + t * 32 + hf * 16, a);
+        uint32_t a[DC];
+        ld_acc(lane_base + TCB_COL_DQ + t * 32 + cq * DC, a);
         tmem_ld_wait();
         if (qi < n) {
           const long long row = (long long)(item_ / p.heads) * n + qi;
-          uint32_t x[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) x[e] = pack_bf16x2(__uint_as_float(a[2 * e]) * p.scale, __uint_as_float(a[2 * e + 1]) * p.scale);
-          uint4* pq = reinterpret_cast<uint4*>(p.dq + row * p.ld_dq + hd * 32 + hf * 16);
-          pq[0] = make_uint4(x[0], x[1], x[2], x[3]);
-          pq[1] = make_uint4(x[4], x[5], x[6], x[7]);
+          st_acc(p.dq + row * p.ld_dq + hd * 32 + cq * DC, a, p.scale);
         }
       }
     };
@@ -458,6 +463,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const bool warp_valid = (kb * 128 + q * 32) < n;
         const int kc = key < n ? key : n - 1;
         const int tj = (p.H - 1 - kc / W) * STR + (W - 1 - kc % W);     // table index = tj + ci(query)
+        const char* tpb = reinterpret_cast<const char*>(sTab + tj);      // + ci * 4 (the records hold the byte offset)
         for (int qc = 0; qc < NQC; qc++, g++) {
           const int st = (int)(g & 1), slot = (int)(g % TCB_QD_SLOTS);
           const int buf = v & 1, grp = qc & 1;
@@ -467,46 +473,47 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           if (grp == 0) mbar_wait_tag(&ds_free[buf], (uint32_t)(((v >> 1) & 1) ^ 1), 44);
           if (warp_valid) {
             tc_fence_after();
-            const uint32_t scol = lane_base + st * 128 + hf * 32;
-            // two groups of 16 queries: the TMEM loads of the second group are in flight while the first one is computed
-            uint32_t sv0[16], dp0[16], sv1[16], dp1[16];
-            tmem_ld_32x16(scol, sv0);
-            tmem_ld_32x16(scol + 64, dp0);
-            tmem_ld_wait_dep(sv0, dp0);
-            tmem_ld_32x16(scol + 16, sv1);
-            tmem_ld_32x16(scol + 64 + 16, dp1);
-            const float4* rec = reinterpret_cast<const float4*>(sQD + slot * TCB_QD_BYTES + 8192) + hf * 32;
-            const float* tp = sTab + tj;
-            uint32_t pk[16], dk_[16];
-            auto half16 = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int base) {
+            const uint32_t scol = lane_base + st * 128 + cq * CW;       // this warp's S^T columns; dP^T sits 64 columns further
+            const float4* rec = reinterpret_cast<const float4*>(sQD + slot * TCB_QD_BYTES + 8192) + cq * CW;
+            // groups of 16 queries: the TMEM loads of group g+1 are in flight while group g is computed
+            uint32_t sv[NG][16], dp[NG][16];
+            tmem_ld_32x16(scol, sv[0]);
+            tmem_ld_32x16(scol + 64, dp[0]);
+#pragma unroll
+            for (int gi = 0; gi < NG; gi++) {
+              tmem_ld_wait_dep(sv[gi], dp[gi]);
+              if (gi + 1 < NG) {
+                tmem_ld_32x16(scol + (gi + 1) * 16, sv[gi + 1]);
+                tmem_ld_32x16(scol + 64 + (gi + 1) * 16, dp[gi + 1]);
+              }
+              uint32_t pk[8], dk_[8];
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
-                const float4 r0 = rec[base + e], r1 = rec[base + e + 1];   // {lse_i, delta_i, ci}: broadcast LDS.128
-                const float x0 = fmaf(__uint_as_float(sv[e]), sc2, tp[__float_as_int(r0.z)]) - r0.x;
-                const float x1 = fmaf(__uint_as_float(sv[e + 1]), sc2, tp[__float_as_int(r1.z)]) - r1.x;
+                const float4 r0 = rec[gi * 16 + e], r1 = rec[gi * 16 + e + 1];   // {lse_i, delta_i, 4*ci}: broadcast LDS.128
+                const float t0 = *reinterpret_cast<const float*>(tpb + __float_as_int(r0.z));
+                const float t1 = *reinterpret_cast<const float*>(tpb + __float_as_int(r1.z));
+                const float x0 = fmaf(__uint_as_float(sv[gi][e]), sc2, t0) - r0.x;
+                const float x1 = fmaf(__uint_as_float(sv[gi][e + 1]), sc2, t1) - r1.x;
                 const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                const float d0 = p0 * (__uint_as_float(dp[e]) - r0.y), d1 = p1 * (__uint_as_float(dp[e + 1]) - r1.y);
-                pk[(base + e) / 2] = pack_bf16x2(p0, p1);
-                dk_[(base + e) / 2] = pack_bf16x2(d0, d1);
+                const float d0 = p0 * (__uint_as_float(dp[gi][e]) - r0.y), d1 = p1 * (__uint_as_float(dp[gi][e + 1]) - r1.y);
+                pk[e / 2] = pack_bf16x2(p0, p1);
+                dk_[e / 2] = pack_bf16x2(d0, d1);
               }
-            };
-            half16(sv0, dp0, 0);
-            tmem_ld_wait_dep(sv1, dp1);
-            half16(sv1, dp1, 16);
-            tmem_st_32x16(scol, pk);                                 // P^T over this warp's own S^T columns
+              tmem_st_32x8(scol + gi * 8, pk);                          // P^T over this warp's own (already consumed) S^T columns
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++)
-              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) =
-                  make_uint4(dk_[4 * c4], dk_[4 * c4 + 1], dk_[4 * c4 + 2], dk_[4 * c4 + 3]);
+              for (int c2 = 0; c2 < 2; c2++)
+                *reinterpret_cast<uint4*>(tile_row + (((cq * CPR + gi * 2 + c2) ^ (r & 7)) << 4)) =
+                    make_uint4(dk_[4 * c2], dk_[4 * c2 + 1], dk_[4 * c2 + 2], dk_[4 * c2 + 3]);
+            }
             if (p.ds_spill != nullptr) {
-              // spill this warp's 32 keys x 32 queries through the tile it has just written: 8 rows x 64 contiguous bytes per
-              // store instruction (full 32-byte sectors) instead of 32 rows x 16 bytes straight from the registers
+              // spill this warp's 32 keys x CW queries through the tile it has just written: (32 / CPR) rows x CW*2 contiguous bytes
+              // per store instruction (full 32-byte sectors) instead of 32 rows x 16 bytes straight from the registers
               __syncwarp();
               const uint8_t* tile_w = sDS + buf * 32768 + grp * 16384 + (q * 32) * 128;
               __nv_bfloat16* sp = p.ds_spill + ((long long)item * n + kb * 128 + q * 32) * n + qc * 64;
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const int rr = j * 8 + (lane >> 2), ch = hf * 4 + (lane & 3);
+              for (int j = 0; j < CPR; j++) {
+                const int rr = j * (32 / CPR) + lane / CPR, ch = cq * CPR + lane % CPR;
                 const uint4 val = *reinterpret_cast<const uint4*>(tile_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
                 __stcs(reinterpret_cast<uint4*>(sp + (long long)rr * n + ch * 8), val);
               }
@@ -515,8 +522,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           } else {
             // key rows beyond the sequence: their dS must be ZERO in the shared tile (dQ contracts over all 128 keys)
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++)
-              *reinterpret_cast<uint4*>(tile_row + (((hf * 4 + c4) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            for (int c4 = 0; c4 < CPR; c4++)
+              *reinterpret_cast<uint4*>(tile_row + (((cq * CPR + c4) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
           }
           // drain the accumulators of the previous key block / item before this block's MMAs may overwrite them
           if (qc == 0 && u > 0) drain_dvdk(prev_item, prev_kb, (uint32_t)((u - 1) & 1));
@@ -537,7 +544,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       drain_dvdk(prev_item, prev_kb, (uint32_t)((u - 1) & 1));
       drain_dq(prev_item, (uint32_t)((m - 1) & 1));
     }
-  } else if (warp == 8) {
+  } else if (warp == EW) {
     // ===================== producer (whole warp: lane 0 drives TMA, all lanes write the per-query records) =====================
     long long g = 0;
     int u = 0;
@@ -568,7 +575,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           for (int h2 = 0; h2 < 2; h2++) {
             const int i = qc * 64 + h2 * 32 + lane;          // < n (n % 64 == 0)
             const long long idx = (row0 + i) * p.heads + hd;
-            rec[h2 * 32 + lane] = make_float4(__ldg(p.lse + idx), __ldg(p.delta + idx), __int_as_float((i / W) * STR + (i % W)), 0.f);
+            rec[h2 * 32 + lane] = make_float4(__ldg(p.lse + idx), __ldg(p.delta + idx), __int_as_float(4 * ((i / W) * STR + (i % W))), 0.f);
           }
           mbar_arrive(&qd_full[slot]);
         }
@@ -624,10 +631,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t acc0 = qc > 0 ? 1u : 0u;
         if (leader) {
         // dV += P^T dO_c : K = 64 queries, A = P^T in TMEM (16 queries = 8 columns; the two column halves sit 32 columns apart)
-        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 0, umma_desc_join(dmn, hi64), idesc_dv, acc0);
-        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 8, umma_desc_join(dmn + (1024 >> 4), hi64), idesc_dv, 1u);
-        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 32, umma_desc_join(dmn + (2048 >> 4), hi64), idesc_dv, 1u);
-        umma_bf16_ts(tmem_base + TCB_COL_DV, acol + 40, umma_desc_join(dmn + (3072 >> 4), hi64), idesc_dv, 1u);
+        // (queries 16*k4 .. +15 were written by warp slice (16*k4)/CW as its group ((16*k4) % CW)/16: 8 columns each)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++)
+          umma_bf16_ts(tmem_base + TCB_COL_DV, acol + ((16 * k4) / CW) * CW + (((16 * k4) % CW) / 16) * 8,
+                       umma_desc_join(dmn + k4 * (1024 >> 4), hi64), idesc_dv, k4 > 0 ? 1u : acc0);
         // dK += dS^T Q_c : A = dS tile group grp read K-major (128-byte rows), B = Q chunk MN-major
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++)
@@ -665,7 +673,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == EW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -790,6 +798,9 @@ int ctb_attn_fwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
   return launch_tc_fwd<64, 32>(a, stream);
 }
 
+static int g_tc_bwd_warps = 16;
+
+template <int EW>
 static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {
   const long long rows = (long long)a->num_seqs * a->n;
   CUtensorMap tq, tdo, tk, tv;
@@ -814,16 +825,16 @@ static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.ld_dv = a->ld_dv;
   p.ds_spill = (a->dcpb_table != nullptr) ? reinterpret_cast<__nv_bfloat16*>(a->ds_scratch) : nullptr;
   const int tab_elems = ((2 * a->grid_h - 1) * TcGeom<24>::STR + 31) & ~31;
-  const size_t smem = 1024 + 2 * 16384 + 2 * 32768 + (size_t)TCB_QD_SLOTS * TCB_QD_BYTES + (size_t)tab_elems * 4 + 20 * 8 + 8 + 16 * 4 + 64;
+  const size_t smem = 1024 + 2 * 16384 + 2 * 32768 + (size_t)TCB_QD_SLOTS * TCB_QD_BYTES + (size_t)tab_elems * 4 + 20 * 8 + 8 + 24 * 4 + 64;
   CTB_CHECK_ARG(smem <= 227 * 1024, "attn_bwd(tc): %zu B of shared memory needed", smem);
-  auto kern = attn_tc_bwd_kernel<24>;
+  auto kern = attn_tc_bwd_kernel<24, EW>;
   CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent grid: a multiple of `heads` CTAs so that every item a CTA walks (blockIdx.x + k*gridDim.x) has the same head
   const int items = a->num_seqs * a->heads;
   int grid = (num_sms() / a->heads) * a->heads;
   if (grid < a->heads) grid = a->heads;
   if (grid > items) grid = items;
-  kern<<<grid, 320, smem, stream>>>(tq, tdo, tk, tv, p);
+  kern<<<grid, (EW + 2) * 32, smem, stream>>>(tq, tdo, tk, tv, p);
   CTB_LAUNCH_CHECK();
   if (a->dcpb_table != nullptr) {
     const int n = a->n, R = (2 * a->grid_h - 1) * (2 * a->grid_w - 1);
@@ -846,5 +857,12 @@ int ctb_attn_bwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
                     a->ld_dv % 8 == 0, "attn_bwd(tc): rows must be 16B aligned");
   CTB_CHECK_ARG(a->dcpb_table == nullptr || a->ds_scratch != nullptr, "attn_bwd(tc): dcpb_table needs ds_scratch");
   CTB_CHECK_ARG(a->dbias == nullptr, "attn_bwd(tc): the table path produces dcpb_table, not dbias");
-  return launch_tc_bwd(a, stream);
+  return (g_tc_bwd_warps == 8) ? launch_tc_bwd<8>(a, stream) : launch_tc_bwd<16>(a, stream);
+}
+
+// Measurement knob (tools/attn_tc_probe.py): number of softmax-backward warps of the tcgen05 backward kernel, 8 or 16.
+extern "C" int ctclip_debug_set_attn_bwd_warps(int32_t warps) {
+  CTB_CHECK_ARG(warps == 8 || warps == 16, "attn bwd warps must be 8 or 16");
+  g_tc_bwd_warps = warps;
+  return CTCLIP_OK;
 }

@@ -67,18 +67,71 @@ class _ClipStepFn(torch.autograd.Function):
         else:
             G = {n: torch.zeros_like(p) for n, p in P.items() if p.requires_grad and p.numel() > 0}
             Gd = _GradDict(G)
-        dcls = module._backward_into(st, ectx, P, Gd, cls, float(gout))
+        text_bwd = None
         if ctx.native_text:
-            tctx = ctx.tctx
-            d_last = torch.zeros(tctx["M"], dcls.shape[1], device=dcls.device)
-            d_last.view(tctx["b"], tctx["n"], -1)[:, 0, :] = dcls            # only the CLS rows carry gradient (ct_clip.py:762)
-            module._bert_engine().backward(tctx, d_last, ctx.PT, _PrefixView(Gd, "text_transformer."))
+            tctx, PT = ctx.tctx, ctx.PT
+
+            def text_bwd(dcls_):
+                d_last = torch.zeros(tctx["M"], dcls_.shape[1], device=dcls_.device)
+                d_last.view(tctx["b"], tctx["n"], -1)[:, 0, :] = dcls_          # only the CLS rows carry gradient (ct_clip.py:762)
+                module._bert_engine().backward(tctx, d_last, PT, _PrefixView(Gd, "text_transformer."))
+                if module.dp_grad_ready is not None:
+                    module.dp_grad_ready("text_transformer.")
+        dcls = module._backward_into(st, ectx, P, Gd, cls, float(gout), text_backward=text_bwd)
+        if ctx.native_text:
             dcls = None
         ctx.ectx = ctx.st = ctx.tctx = None
         if sink is not None:
             return (None, None, dcls, None, None, None) + (None,) * len(names)
         grads = tuple(G[n] if (n in G and n in Gd.touched) else None for n in names)
         return (None, None, dcls, None, None, None) + grads
+
+
+class _ClipLatentsFn(torch.autograd.Function):
+    """(text, volume, parameters) -> (raw text latents [n_text, L], raw image latents [b, L]) with the hand-written backward of
+    both towers: the differentiable building block of everything that is NOT the contrastive step -- fine-tuning on the
+    similarity logits (scripts/ct_vocabfine_train.py:108-122) or on the latents. l2-normalisation, temperature and the tiny
+    task loss on top are ordinary autograd ops on [n, L] tensors."""
+
+    @staticmethod
+    def forward(ctx, module, need_grad, text, video, names, *params):
+        P = dict(zip(names, params))
+        vit: CTViT = module.visual_transformer
+        PV = {n[len("visual_transformer."):]: P[n] for n in names if n.startswith("visual_transformer.")}
+        PT = {n[len("text_transformer."):]: P[n] for n in names if n.startswith("text_transformer.")}
+        last, tctx = module._bert_engine().forward(text.input_ids, text.attention_mask, PT, save=need_grad,
+                                                   dropout=module._text_dropout())
+        cls_in = last[:, 0, :]
+        ectx = vit._run_forward(video, PV, save=need_grad)
+        st = module._heads_forward(cls_in, ectx, P, want_loss=False, want_grads=False, want_raw=True)
+        ctx.module, ctx.names, ctx.ectx, ctx.st, ctx.tctx, ctx.PT = module, names, ectx, st, tctx, PT
+        ctx.save_for_backward(cls_in, *params)
+        return st.t_raw, st.i_raw
+
+    @staticmethod
+    def backward(ctx, d_t_raw, d_i_raw):
+        module, names, st, ectx, tctx = ctx.module, ctx.names, ctx.st, ctx.ectx, ctx.tctx
+        cls, *params = ctx.saved_tensors
+        P = dict(zip(names, params))
+        sink = getattr(module, "_grad_sink", None)
+        if sink is not None:
+            Gd, G = _GradDict(sink), None
+        else:
+            G = {n: torch.zeros_like(p) for n, p in P.items() if p.requires_grad and p.numel() > 0}
+            Gd = _GradDict(G)
+        dev = cls.device
+        st.d_t_raw = (d_t_raw if d_t_raw is not None else torch.zeros_like(st.t_raw)).float().contiguous()
+        st.d_i_raw = (d_i_raw if d_i_raw is not None else torch.zeros_like(st.i_raw)).float().contiguous()
+        st.dtemp = torch.zeros(1, device=dev)          # the temperature enters downstream of the latents (plain autograd)
+        dcls = module._backward_into(st, ectx, P, Gd, cls, 1.0)
+        d_last = torch.zeros(tctx["M"], dcls.shape[1], device=dev)
+        d_last.view(tctx["b"], tctx["n"], -1)[:, 0, :] = dcls
+        module._bert_engine().backward(tctx, d_last, ctx.PT, _PrefixView(Gd, "text_transformer."))
+        ctx.ectx = ctx.st = ctx.tctx = None
+        if sink is not None:
+            return (None, None, None, None, None) + (None,) * len(names)
+        grads = tuple(G[n] if (n in G and n in Gd.touched) else None for n in names)
+        return (None, None, None, None, None) + grads
 
 
 class CTCLIP(nn.Module):
@@ -137,6 +190,7 @@ class CTCLIP(nn.Module):
         self.dp_rank, self.dp_world = 0, 1
         self.dp_all_gather = None
         self.dp_early_reduce = None      # callable(param name): start the gradient all-reduce of that tensor right away
+        self.dp_grad_ready = None        # callable(name prefix): every gradient under the prefix is final (bucketed all-reduce)
         self._wv_bf16 = None
         self._wv_version = None
         self._grad_sink = None
@@ -238,7 +292,7 @@ class CTCLIP(nn.Module):
         enc_text = out[0]
         return enc_text, enc_text[:, 0, :]
 
-    def _heads_forward(self, cls, ectx, P, *, want_loss, want_grads):
+    def _heads_forward(self, cls, ectx, P, *, want_loss, want_grads, want_raw=False):
         """pool + projections (+ loss fwd/bwd). cls: fp32 [b, dim_text]."""
         vit: CTViT = self.visual_transformer
         g = vit.engine.g
@@ -260,6 +314,9 @@ class CTCLIP(nn.Module):
         t_raw = torch.empty(bt, L, device=dev)
         ops.sgemm(cls32, P["to_text_latent.weight"], t_raw, M=bt, N=L, K=self.dim_text, trans_b=True)
         st.cls32, st.b, st.L, st.K = cls32, b, L, K
+        if want_raw:      # differentiable-latents path: the caller normalises (autograd) and owns the loss
+            st.t_raw, st.i_raw = t_raw, i_raw
+            return st
         if not want_loss:
             st.t_hat, st.i_hat = self._l2(t_raw), self._l2(i_raw)
             return st
@@ -280,12 +337,14 @@ class CTCLIP(nn.Module):
                           row0=self.dp_rank * b, nrows=b if want_grads else 0)
         return st
 
-    def _backward_into(self, st, ectx, P, G, cls, gscale):
-        """Accumulate parameter gradients into G; returns d(cls)."""
+    def _backward_into(self, st, ectx, P, G, cls, gscale, text_backward=None):
+        """Accumulate parameter gradients into G; returns d(cls). text_backward(dcls): optional callable that runs the text tower's
+        backward as soon as d(cls) exists, i.e. BEFORE the image tower's backward."""
         vit: CTViT = self.visual_transformer
         g = vit.engine.g
         dev = cls.device
         b, L, K = st.b, st.L, st.K
+        bt = st.cls32.shape[0]                          # reports in the text batch (== b for the contrastive step)
         d_t, d_i = st.d_t_raw, st.d_i_raw
         if gscale != 1.0:
             d_t, d_i = d_t * gscale, d_i * gscale      # scalar rescale of two [b, L] tensors (loss weighting)
@@ -293,9 +352,9 @@ class CTCLIP(nn.Module):
         # (the tower gradients are row-partitioned, this one is not) and the arena is SUM-all-reduced: take 1/world of it here.
         G["temperature"].add_(st.dtemp.view(()), alpha=gscale / max(1, self.dp_world))
         # text projection: t_raw = cls Wt^T
-        ops.sgemm(d_t, st.cls32, G["to_text_latent.weight"], M=L, N=self.dim_text, K=b, trans_a=True, accumulate=True)
-        dcls = torch.empty(b, self.dim_text, device=dev)
-        ops.sgemm(d_t, P["to_text_latent.weight"], dcls, M=b, N=self.dim_text, K=L)
+        ops.sgemm(d_t, st.cls32, G["to_text_latent.weight"], M=L, N=self.dim_text, K=bt, trans_a=True, accumulate=True)
+        dcls = torch.empty(bt, self.dim_text, device=dev)
+        ops.sgemm(d_t, P["to_text_latent.weight"], dcls, M=bt, N=self.dim_text, K=L)
         # visual projection: i_raw = pooled Wv^T  (294912 -> 512: HBM-bound, weight streamed once per GEMM)
         d_i_bf = torch.empty(b, L, dtype=torch.bfloat16, device=dev)
         ops.cast_bf16(d_i, d_i_bf, b * L)
@@ -303,6 +362,8 @@ class CTCLIP(nn.Module):
                  C_out=G["to_visual_latent.weight"], ldc=K)
         if self.dp_early_reduce is not None:   # 604 MB of the 1.14 GB gradient are final here: all-reduce them behind the towers' backward
             self.dp_early_reduce("to_visual_latent.weight")
+        if text_backward is not None:          # the text tower first: its 0.44 GB of gradients then travel behind the long image-tower backward
+            text_backward(dcls)
         dpooled = torch.empty(b, K, device=dev)
         ops.gemm(d_i_bf, self._visual_weight_bf16(P["to_visual_latent.weight"]), M=b, N=K, K=L, b_major=1,
                  epilogue=ops.EPI_F32, C_out=dpooled)
@@ -329,6 +390,14 @@ class CTCLIP(nn.Module):
             if freeze_text_encoder:
                 cls = cls.detach()
             return _ClipStepFn.apply(self, torch.is_grad_enabled(), cls, None, image, tuple(names), *tensors)
+        if torch.is_grad_enabled() and self._text_native() and not return_encodings and \
+                any(t.requires_grad for t in tensors):
+            # fine-tuning on the similarity logits / latents (scripts/ct_vocabfine_train.py:108, ct_lipro_train.py:26-27): same
+            # outputs as below, differentiable w.r.t. both towers through _ClipLatentsFn
+            tl, il = self.latents_with_grad(text, image)
+            if return_latents:
+                return tl, il, None
+            return (tl * il).sum(-1) * self.temperature.exp()                         # ct_clip.py:805-807
         enc_text, cls = self._text_cls(text)
         # inference / export paths: no gradient
         with torch.no_grad():
@@ -350,6 +419,12 @@ class CTCLIP(nn.Module):
             out = torch.empty(max(Bt, Bi), device=cls.device)
             ops.clip_sims(st.t_hat, Bt, st.i_hat, Bi, self.dim_latent, P["temperature"], out)   # ct_clip.py:805-807
             return out
+
+    def latents_with_grad(self, text, image):
+        """l2-normalised (text latents [n_text, L], image latents [b, L]), differentiable w.r.t. every live parameter."""
+        names, tensors = self._live()
+        t_raw, i_raw = _ClipLatentsFn.apply(self, torch.is_grad_enabled(), text, image, tuple(names), *tensors)
+        return torch.nn.functional.normalize(t_raw, dim=-1), torch.nn.functional.normalize(i_raw, dim=-1)
 
     def _forward_foreign(self, text, image, return_loss, return_encodings, return_latents):
         raise NotImplementedError("CTCLIP here drives ct_clip_b200.CTViT as its image encoder (the encoder every reference "

@@ -100,6 +100,9 @@ class CTViTEngine:
         import os
         tc = ops.attn_tc_supported(g.S, g.H, g.W, g.dim_head) if os.environ.get("CTCLIP_ATTN_TC", "1") != "0" else 0
         self.tc_fwd, self.tc_bwd = bool(tc & 1), bool(tc & 2)
+        # data parallelism: callable(prefix) invoked when every gradient of the parameters under `prefix` is final (the trainer
+        # starts their all-reduce while the rest of the backward is still running)
+        self.on_grads_ready = None
 
     def _canon_table(self, T):
         """canon(f) of the temporal stack's PEG (SURVEY trap T1) as an int32 lookup table (index prep, built once per T)."""
@@ -333,12 +336,12 @@ class CTViTEngine:
         """Training-mode code-book EMA (vector_quantize_pytorch 1.1.2 CosineSimCodebook.forward, training branch).
         all_reduce: optional callable(tensor) summing statistics across data-parallel ranks."""
         g, dev = self.g, self.device
-        bins = torch.zeros(g.codebook_size, device=dev)
-        esum = torch.zeros(g.codebook_size, g.dim, device=dev)
+        stats = torch.zeros(g.codebook_size * (g.dim + 1), device=dev)       # [bins | embed_sum]: ONE all-reduce under data parallelism
+        bins = stats[:g.codebook_size]
+        esum = stats[g.codebook_size:].view(g.codebook_size, g.dim)
         ops.vq_ema_accum(ctx["pre_vq"], ctx["idx"], bins, esum, ctx["M"], g.dim)
         if all_reduce is not None:
-            all_reduce(bins)
-            all_reduce(esum)
+            all_reduce(stats)
         ops.vq_ema_update(P["vq._codebook.embed"], P["vq._codebook.cluster_size"], bins, esum, g.codebook_size, g.dim, decay)
 
     # ------------------------------------------------------------------------------------------
@@ -429,6 +432,8 @@ class CTViTEngine:
             dres, dxb = self._layer_backward(dres, dxb, ctx["saved_t"][i], P, G, f"enc_temporal_transformer.layers.{i}.",
                                              self.temporal_w[i], b, T, True, None, None, None)
             ctx["saved_t"][i] = None
+            if self.on_grads_ready is not None:
+                self.on_grads_ready(f"enc_temporal_transformer.layers.{i}.")
         d2 = torch.empty_like(dres)
         ops.ln_bwd(M, D, g_f32=dres, gamma=P["enc_spatial_transformer.norm_out.gamma"], xhat=ctx["xhat_ns"],
                    rstd=ctx["rstd_ns"], dx_f32=d2, dx_bf16=dxb, dgamma=G["enc_spatial_transformer.norm_out.gamma"])
@@ -443,6 +448,8 @@ class CTViTEngine:
                                              self.spatial_w[i], b, T, False, ctx["bias"], ctx["bias_t"], dbias,
                                              tab=ctx["cpb_tab"], dtab=dtab)
             ctx["saved_s"][i] = None
+            if self.on_grads_ready is not None:
+                self.on_grads_ready(f"enc_spatial_transformer.layers.{i}.")
         self._cpb_backward(P, G, dbias, ctx["cpb_h"], dtab=dtab)
         # patch embedding: x = LN_D(xhat_p Wp'^T + bp')
         ops.ln_bwd(M, D, g_f32=dres, gamma=P["to_patch_emb.3.weight"], xhat=ctx["xhat3"], rstd=ctx["rstd3"], dx_bf16=dxb,

@@ -35,6 +35,29 @@ def _dist_env():
     return world, rank, local
 
 
+def merge_ranges(ranges):
+    """Sorted union of half-open [lo, hi) ranges (touching ranges are joined)."""
+    out = []
+    for a, b in sorted(ranges):
+        if out and a <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], b))
+        else:
+            out.append((a, b))
+    return out
+
+
+def complement_ranges(merged, numel):
+    """[0, numel) minus a sorted, disjoint list of ranges."""
+    out, pos = [], 0
+    for a, b in merged:
+        if a > pos:
+            out.append((pos, a))
+        pos = max(pos, b)
+    if pos < numel:
+        out.append((pos, numel))
+    return out
+
+
 def rest_slices(names, offsets, numel, name):
     """[lo, hi) ranges of a flat arena (tensor `names[i]` starts at `offsets[i]`) that are NOT covered by tensor `name`:
     what remains to be all-reduced after `name` went out early."""
@@ -102,6 +125,57 @@ class ParamArena:
         self.step = int(sd["step"])
         self.m.copy_(sd["exp_avg"])
         self.v.copy_(sd["exp_avg_sq"])
+
+
+class GradBucketer:
+    """Gradient all-reduce overlapped with the backward pass (reverse-forward order, like DDP's buckets) over the flat arena:
+      * the arena lays the ndim >= 2 tensors out first, in module order: the tensors of one transformer layer are contiguous and
+        consecutive layers adjacent, so "layer i is done" extends a pending [lo, hi) range downwards;
+      * a pending range goes on the wire (async all-reduce on the process group's own stream: it starts once the kernels enqueued
+        so far are done and overlaps everything enqueued after it) as soon as it holds >= bucket_bytes;
+      * whatever was never announced (1-D tensors, heads, patch embedding ...) is reduced by finish() as the complement."""
+
+    def __init__(self, arena, bucket_bytes=48 << 20, group=None):
+        self.arena, self.bucket_bytes, self.group = arena, bucket_bytes, group
+        self.pending, self.done, self.works = [], [], []
+        self.launches = 0
+
+    def _span(self, i):
+        o = self.arena.offsets[i]
+        return o, o + (self.arena.params[i].numel() + 3) // 4 * 4
+
+    def _launch(self, lo, hi):
+        self.works.append(dist.all_reduce(self.arena.g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.done.append((lo, hi))
+        self.launches += 1
+
+    def tensor_ready(self, name):
+        """one (large) tensor is final: put it on the wire right away (the 604 MB visual projection)"""
+        self._launch(*self._span(self.arena.names.index(name)))
+
+    def prefix_ready(self, prefix):
+        spans = [self._span(i) for i, (n, p) in enumerate(zip(self.arena.names, self.arena.params)) if n.startswith(prefix) and p.ndim >= 2]
+        if not spans:
+            return
+        self.pending = merge_ranges(self.pending + [(min(a for a, _ in spans), max(b for _, b in spans))])
+        keep = []
+        for a, b in self.pending:
+            if (b - a) * 4 >= self.bucket_bytes:
+                self._launch(a, b)
+            else:
+                keep.append((a, b))
+        self.pending = keep
+
+    def finish(self):
+        """Reduce every arena range that is not on the wire yet, then wait for all collectives of this step."""
+        for a, b in self.pending:
+            self._launch(a, b)
+        self.pending = []
+        for a, b in complement_ranges(merge_ranges(self.done), self.arena.numel):
+            self._launch(a, b)
+        for w in self.works:
+            w.wait()
+        self.works, self.done = [], []
 
 
 class CTClipTrainer(nn.Module):
@@ -177,13 +251,10 @@ class CTClipTrainer(nn.Module):
 
         from .dist_utils import gather_latents as gather
         clip.dp_all_gather = gather
-        self._early = None
-
-        def early(name):
-            # NCCL runs on the process group's own stream: the collective starts once the kernels enqueued so far are done
-            # and overlaps everything enqueued after it (the whole image/text tower backward)
-            self._early = (name, dist.all_reduce(self.arena.grad_views[name], op=dist.ReduceOp.SUM, async_op=True))
-        clip.dp_early_reduce = early
+        self.bucketer = GradBucketer(self.arena)
+        clip.dp_early_reduce = self.bucketer.tensor_ready
+        clip.dp_grad_ready = self.bucketer.prefix_ready
+        clip.visual_transformer.engine.on_grads_ready = lambda prefix: self.bucketer.prefix_ready("visual_transformer." + prefix)
         clip.visual_transformer.ema_all_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     @property
@@ -235,14 +306,7 @@ class CTClipTrainer(nn.Module):
         loss = self.CTClip(text_tokens, video, return_loss=True, device=self.device)
         loss.backward()
         if self.world > 1:
-            if self._early is not None:      # the visual projection's gradient is already on the wire: reduce the rest
-                name, work = self._early
-                self._early = None
-                for lo, hi in rest_slices(self.arena.names, self.arena.offsets, self.arena.numel, name):
-                    dist.all_reduce(self.arena.g[lo:hi], op=dist.ReduceOp.SUM)
-                work.wait()
-            else:
-                dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM)
+            self.bucketer.finish()
         ev = getattr(self, "_ckpt_event", None)
         if ev is not None:       # an asynchronous checkpoint copy may still be reading the parameters
             torch.cuda.current_stream().wait_event(ev)

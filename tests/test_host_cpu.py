@@ -160,6 +160,51 @@ def _bucket_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _bucketer_worker(rank, world, port, ret):
+    """GradBucketer: layers announced in reverse order + early tensor + complement == ONE all-reduce of the whole arena"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ct_clip_b200.trainer import GradBucketer, ParamArena
+    g = torch.Generator().manual_seed(5)
+    shapes = [("head.weight", (6, 10)), ("big.weight", (40, 50)), ("temperature", ())]
+    for i in range(4):
+        shapes += [(f"tower.layers.{i}.w1", (16, 16)), (f"tower.layers.{i}.b1", (16,)), (f"tower.layers.{i}.w2", (16, 3, 3))]
+    shapes += [("tower.norm.gamma", (16,)), ("text.emb", (30, 8))]
+    ps = [(n, torch.nn.Parameter(torch.randn(shp, generator=g))) for n, shp in shapes]
+    ar = ParamArena(ps, torch.device("cpu"))
+    ar.g.copy_(torch.randn(ar.numel, generator=torch.Generator().manual_seed(100 + rank)))
+    whole = ar.g.clone()
+    dist.all_reduce(whole, op=dist.ReduceOp.SUM)
+    bk = GradBucketer(ar, bucket_bytes=2 * (16 * 16 + 16 * 9) * 4)       # two layers per bucket
+    bk.tensor_ready("big.weight")
+    bk.prefix_ready("text.")
+    for i in reversed(range(4)):
+        bk.prefix_ready(f"tower.layers.{i}.")
+    launched_before_finish = bk.launches
+    bk.finish()
+    ok = True
+    for n, p in ps:      # padding between tensors is no parameter's gradient: compare tensor by tensor
+        o = ar.offsets[ar.names.index(n)]
+        ok = ok and torch.allclose(ar.g[o:o + p.numel()], whole[o:o + p.numel()])
+    ret[rank] = (ok, launched_before_finish, bk.launches)
+    dist.destroy_process_group()
+
+
+def test_grad_bucketer_matches_single_all_reduce_two_ranks_gloo():
+    from ct_clip_b200.trainer import complement_ranges, merge_ranges
+    assert merge_ranges([(8, 12), (0, 4), (4, 8), (20, 24)]) == [(0, 12), (20, 24)]
+    assert complement_ranges([(0, 12), (20, 24)], 30) == [(12, 20), (24, 30)]
+    assert complement_ranges([], 8) == [(0, 8)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bucketer_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in (0, 1):
+        ok, before, total = ret[r]
+        assert ok
+        assert before >= 3          # early tensor + two 2-layer buckets were on the wire before finish()
+        assert total <= before + 4
+
+
 def test_bucketed_gradient_all_reduce_two_ranks_gloo():
     from ct_clip_b200.trainer import rest_slices
     assert rest_slices(["a", "b", "c"], [0, 16, 20], 28, "a") == [(16, 28)]

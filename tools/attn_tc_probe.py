@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--nseq", type=int, default=192)
     ap.add_argument("--only", default="both")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--bwd-warps", type=int, default=0, help="8 or 16 (default: time both)")
     a = ap.parse_args()
     nseq, H, W, heads, dh = a.nseq, 24, 24, 8, 32
     n, I = H * W, heads * dh
@@ -74,10 +75,13 @@ def main():
         t = timeit(fwd_tc)
         print(f"attn_fwd tc       : {t:.3f} ms  {flops / t / 1e9:.0f} TFLOP/s")
         if not a.fwd_only:
-            t = timeit(bwd_tc)
-            print(f"attn_bwd tc +dtab : {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (incl. delta + table-gradient reduction)")
-            t = timeit(lambda: bwd_tc(False))
-            print(f"attn_bwd tc       : {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (no table gradient / spill)")
+            from ct_clip_b200 import _lib
+            for ew in ([a.bwd_warps] if a.bwd_warps else [8, 16]):
+                _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(ew), "set warps")
+                t = timeit(bwd_tc)
+                print(f"attn_bwd tc +dtab [{ew:2d} warps]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (incl. delta + table-gradient reduction)")
+                t = timeit(lambda: bwd_tc(False))
+                print(f"attn_bwd tc       [{ew:2d} warps]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (no table gradient / spill)")
     if a.only in ("both", "mma"):
         fwd_mma()
         t = timeit(fwd_mma)

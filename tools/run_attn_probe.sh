@@ -9,5 +9,5 @@ ncu --set full --clock-control none --import-source on -k regex:attn_tc_fwd -s 1
 ncu --set full --clock-control none --import-source on -k regex:attn_tc_bwd -s 1 -c 1 -o gpurun_out/${TAG}_ncu_attn_bwd -f \
     python tools/attn_tc_probe.py --reps 1 --only tc > gpurun_out/${TAG}_ncu_bwd.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_fwd.log gpurun_out/${TAG}_ncu_bwd.log
-python -m pytest tests/test_attention_tc_gpu.py tests/test_bert_gpu.py tests/test_gemm_gpu.py tests/test_headline_geometry_gpu.py tests/test_preprocess_gpu.py -q -s 2>&1 | tail -40 > gpurun_out/${TAG}_pytest_new.txt
+python -m pytest tests/test_attention_tc_gpu.py tests/test_bert_gpu.py tests/test_gemm_gpu.py tests/test_headline_geometry_gpu.py tests/test_preprocess_gpu.py tests/test_retrieval_gpu.py tests/test_kernels_gpu.py -q -s 2>&1 | tail -40 > gpurun_out/${TAG}_pytest_new.txt
 tail -25 gpurun_out/${TAG}_pytest_new.txt
