@@ -338,7 +338,11 @@ def run_b200(args):
     T = args.frames // g.temporal_patch
     cfgd = dict(P=g.patch_voxels, N=T * g.S, S=g.S, T=T, depth=args.depth)
     fwd_flops, step_flops = flops_per_volume(cfgd)
+    if world > 1:      # leave the NCCL communicator cleanly on every rank (NCCL warns about leaked process groups otherwise)
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     vols = args.batch * world * args.steps
     h2d = sum(x.numel() * x.element_size() for x in host[0])
@@ -372,9 +376,11 @@ def run_b200(args):
     if stage_rows is not None:
         out["stages"] = [dict(stage=r[0], launches=r[1], ms=round(r[2], 3), bound=r[3], achieved=round(r[4], 1), unit=r[5],
                               frac=round(r[6], 3)) for r in stage_rows[:16]]
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU leg runs on rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline_guarded(args)
     _emit(_OUT_FD, out)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _pin_threads(cores):

@@ -113,6 +113,7 @@ SIGNATURES = {
     "ctclip_cpb_inputs": [P, I32, I32, P],
     "ctclip_cpb_expand": [P, I32, I32, I32, P, P, P],
     "ctclip_cpb_reduce": [P, I32, I32, I32, P, P],
+    "ctclip_cpb_reduce_t": [P, I32, I32, I32, P, P],
     "ctclip_cpb_expand_frag": [P, I32, I32, I32, P, P, P],
     "ctclip_geglu_bwd": [P, I64, P, I64, I64, I32, P, P],
     "ctclip_l2norm_rows_bf16": [P, P, I32, I32, P],

@@ -325,17 +325,27 @@ struct TcBwdParams {
   __nv_bfloat16* dk; long long ld_dk;
   __nv_bfloat16* dv; long long ld_dv;
   __nv_bfloat16* ds_spill;   // [num_seqs*heads][n keys][n queries] or null
+  float* dbias_t;            // alternative to the spill: fp32 [heads][n keys][n queries], accumulated with red.global.add.v4.f32 (L2-resident)
 };
 
 constexpr int TCB_QD_SLOTS = 4;
-constexpr int TCB_QD_BYTES = 4096 + 4096 + 64 * 16;   // Q chunk, dO chunk, per-query records {lse, delta, ci}
+// Q chunk, dO chunk, then EITHER the per-query records {lse, delta, 4*ci} (1 KB) OR the two "augmented k-step" tiles (2 KB each)
+constexpr int TCB_QD_BYTES = 4096 + 4096 + 4096;
 constexpr int TCB_COL_DV = 256, TCB_COL_DK = 288, TCB_COL_DQ = 320;
 constexpr uint32_t SW128 = 2;
 
 // EW = number of softmax-backward warps (8 or 16): warp w owns TMEM lanes 32*(w & 3).. and the (w >> 2)-th slice of CW = 256 / EW
 // query columns of every half-block. 16 warps (4 per scheduler) hide the LDS -> LDS -> MUFU latency chain of the element loop
 // that 8 warps (2 per scheduler, 38 % issue utilisation in profiles/r2c) leave exposed.
-template <int W, int EW>
+// AUG: the per-QUERY terms of the element loop are folded into the tensor-core products by one extra k-step each:
+//   S'^T  = K_blk Q_c^T  + ONES [-lse_i / (scale log2e)]^T      dP'^T = V_blk dO_c^T + ONES [-delta_i]^T
+// (ONES: [128 keys][16] with three leading 1.0; the query vectors are split into three bf16 terms so that the fp32 accumulator
+// receives them to ~2^-24; both tiles in the no-swizzle K-major layout, 8-row x 16-byte core matrices). The element loop then is
+//   p = exp2(S' * scale log2e + table'),   dS = p * dP'
+// without the per-column {lse, delta, table offset} record: its broadcast LDS.128 cost FOUR shared-memory wavefronts per element
+// and made the kernel shared-memory bound (profiles/r2d: LSU wavefronts 53 % + tensor-core operand reads 18 % of the pipe); the
+// table offset of a column is now arithmetic (16 consecutive queries wrap at most once around the grid width).
+template <int W, int EW, bool AUG>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tk, const __grid_constant__ CUtensorMap tv, const TcBwdParams p) {
@@ -346,7 +356,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint8_t* sKV = smem;                                   // 2 slots x (K block 8 KB + V block 8 KB)
   uint8_t* sDS = sKV + 2 * 16384;                        // 2 buffers x [2 query groups][128 keys][128 B]
   uint8_t* sQD = sDS + 2 * 32768;                        // 4 slots x TCB_QD_BYTES
-  float* sTab = reinterpret_cast<float*>(sQD + TCB_QD_SLOTS * TCB_QD_BYTES);
+  uint8_t* sOnes = sQD + TCB_QD_SLOTS * TCB_QD_BYTES;    // [128][16] bf16, no-swizzle K-major (AUG)
+  float* sTab = reinterpret_cast<float*>(sOnes + 4096);
   const int tab_elems = ((2 * p.H - 1) * STR + 31) & ~31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTab + tab_elems);
   uint64_t* kv_full = bars + 0;     // [2]
@@ -396,6 +407,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == EW + 1) {
     tmem_alloc(holder, 512);
     tmem_relinquish();
+  }
+  if (AUG) {
+    // zero the augmented tiles of every slot (their unused k columns must stay zero) and build ONES
+    for (int i = tid; i < TCB_QD_SLOTS * 256; i += NTHREADS)
+      *reinterpret_cast<uint4*>(sQD + (i >> 8) * TCB_QD_BYTES + 8192 + (i & 255) * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 256; i += NTHREADS) {   // 16 groups x (k 0-7 core matrix, k 8-15 core matrix) x 8 rows
+      const bool first_half = ((i >> 3) & 1) == 0;
+      *reinterpret_cast<uint4*>(sOnes + i * 16) = first_half ? make_uint4(0x3F803F80u, 0x00003F80u, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
   }
   // NOTE: the table of head h is only valid for items of head h: a CTA walks items blockIdx.x + k*gridDim.x, so with
   // gridDim.x % heads == 0 (enforced by the launcher) every item of this CTA has the same head.
@@ -475,6 +496,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             tc_fence_after();
             const uint32_t scol = lane_base + st * 128 + cq * CW;       // this warp's S^T columns; dP^T sits 64 columns further
             const float4* rec = reinterpret_cast<const float4*>(sQD + slot * TCB_QD_BYTES + 8192) + cq * CW;
+            (void)rec;
             // groups of 16 queries: the TMEM loads of group g+1 are in flight while group g is computed
             uint32_t sv[NG][16], dp[NG][16];
             tmem_ld_32x16(scol, sv[0]);
@@ -487,17 +509,47 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                 tmem_ld_32x16(scol + 64 + (gi + 1) * 16, dp[gi + 1]);
               }
               uint32_t pk[8], dk_[8];
+              float dsf[16];
+              // AUG: table offsets of the 16 queries i0 .. i0+15 = c0 + e (+ STR - W once the grid row wraps at e = w0)
+              const int i0 = qc * 64 + cq * CW + gi * 16;
+              const int qrow = i0 / W, qcol = i0 - qrow * W;
+              const float* tA = reinterpret_cast<const float*>(tpb) + qrow * STR + qcol;
+              const float* tB = tA + (STR - W);
+              const int w0 = W - qcol;
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
-                const float4 r0 = rec[gi * 16 + e], r1 = rec[gi * 16 + e + 1];   // {lse_i, delta_i, 4*ci}: broadcast LDS.128
-                const float t0 = *reinterpret_cast<const float*>(tpb + __float_as_int(r0.z));
-                const float t1 = *reinterpret_cast<const float*>(tpb + __float_as_int(r1.z));
-                const float x0 = fmaf(__uint_as_float(sv[gi][e]), sc2, t0) - r0.x;
-                const float x1 = fmaf(__uint_as_float(sv[gi][e + 1]), sc2, t1) - r1.x;
-                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                const float d0 = p0 * (__uint_as_float(dp[gi][e]) - r0.y), d1 = p1 * (__uint_as_float(dp[gi][e + 1]) - r1.y);
+                float x0, x1, d0, d1, p0, p1;
+                if constexpr (AUG) {
+                  const float t0 = (e < w0 ? tA : tB)[e], t1 = (e + 1 < w0 ? tA : tB)[e + 1];
+                  x0 = fmaf(__uint_as_float(sv[gi][e]), sc2, t0);
+                  x1 = fmaf(__uint_as_float(sv[gi][e + 1]), sc2, t1);
+                  p0 = ex2_approx(x0);
+                  p1 = ex2_approx(x1);
+                  d0 = p0 * __uint_as_float(dp[gi][e]);
+                  d1 = p1 * __uint_as_float(dp[gi][e + 1]);
+                } else {
+                  const float4 r0 = rec[gi * 16 + e], r1 = rec[gi * 16 + e + 1];   // {lse_i, delta_i, 4*ci}: broadcast LDS.128
+                  const float t0 = *reinterpret_cast<const float*>(tpb + __float_as_int(r0.z));
+                  const float t1 = *reinterpret_cast<const float*>(tpb + __float_as_int(r1.z));
+                  x0 = fmaf(__uint_as_float(sv[gi][e]), sc2, t0) - r0.x;
+                  x1 = fmaf(__uint_as_float(sv[gi][e + 1]), sc2, t1) - r1.x;
+                  p0 = ex2_approx(x0);
+                  p1 = ex2_approx(x1);
+                  d0 = p0 * (__uint_as_float(dp[gi][e]) - r0.y);
+                  d1 = p1 * (__uint_as_float(dp[gi][e + 1]) - r1.y);
+                }
                 pk[e / 2] = pack_bf16x2(p0, p1);
                 dk_[e / 2] = pack_bf16x2(d0, d1);
+                dsf[e] = d0;
+                dsf[e + 1] = d1;
+              }
+              if (p.dbias_t != nullptr) {   // table gradient: fp32 reductions straight into the L2-resident [h][key][query] table
+                float* dst = p.dbias_t + ((long long)(item % p.heads) * n + key) * n + qc * 64 + cq * CW + gi * 16;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k4), "f"(dsf[4 * k4]), "f"(dsf[4 * k4 + 1]),
+                               "f"(dsf[4 * k4 + 2]), "f"(dsf[4 * k4 + 3])
+                               : "memory");
               }
               tmem_st_32x8(scol + gi * 8, pk);                          // P^T over this warp's own (already consumed) S^T columns
 #pragma unroll
@@ -548,6 +600,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     // ===================== producer (whole warp: lane 0 drives TMA, all lanes write the per-query records) =====================
     long long g = 0;
     int u = 0;
+    const float inv_sc2 = 1.0f / sc2;
+    (void)inv_sc2;
     for (int il = 0; il < my_items; il++) {
       const int item = (int)blockIdx.x + il * (int)gridDim.x;
       const int hd = item % p.heads;
@@ -575,8 +629,24 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           for (int h2 = 0; h2 < 2; h2++) {
             const int i = qc * 64 + h2 * 32 + lane;          // < n (n % 64 == 0)
             const long long idx = (row0 + i) * p.heads + hd;
-            rec[h2 * 32 + lane] = make_float4(__ldg(p.lse + idx), __ldg(p.delta + idx), __int_as_float(4 * ((i / W) * STR + (i % W))), 0.f);
+            if constexpr (AUG) {
+              auto split3 = [](float v) {                    // v ~ hi + mid + lo, three bf16 terms (k columns 0..2 of the tile)
+                const __nv_bfloat16 hi = __float2bfloat16(v);
+                const float r1 = v - __bfloat162float(hi);
+                const __nv_bfloat16 mid = __float2bfloat16(r1);
+                const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+                return make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                                  (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+              };
+              const int row = h2 * 32 + lane;
+              const uint32_t off = (row >> 3) * 256 + (row & 7) * 16;          // k 0-7 core matrix of the row's 8-row group
+              *reinterpret_cast<uint4*>(sl + 8192 + off) = split3(-__ldg(p.lse + idx) * inv_sc2);
+              *reinterpret_cast<uint4*>(sl + 8192 + 2048 + off) = split3(-__ldg(p.delta + idx));
+            } else {
+              rec[h2 * 32 + lane] = make_float4(__ldg(p.lse + idx), __ldg(p.delta + idx), __int_as_float(4 * ((i / W) * STR + (i % W))), 0.f);
+            }
           }
+          if constexpr (AUG) fence_proxy_async_smem();       // generic-proxy tile writes -> tcgen05.mma operand reads
           mbar_arrive(&qd_full[slot]);
         }
       }
@@ -592,6 +662,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const uint32_t kv_lo_k = umma_desc_lo(smem_u32(sKV), 16), kv_lo_mn = umma_desc_lo(smem_u32(sKV), 512);
       const uint32_t qd_lo_k = umma_desc_lo(smem_u32(sQD), 16), qd_lo_mn = umma_desc_lo(smem_u32(sQD), 512);
       const uint32_t ds_lo_k = umma_desc_lo(smem_u32(sDS), 16), ds_lo_mn = umma_desc_lo(smem_u32(sDS), 16384);
+      // augmented k-step tiles: no swizzle, K-major, LBO = 128 B (k 8-15 core matrix), SBO = 256 B (next 8 rows)
+      constexpr uint32_t hi_ns = umma_desc_hi(256, 0);
+      const uint32_t ones_lo = umma_desc_lo(smem_u32(sOnes), 128), qd_lo_ns = umma_desc_lo(smem_u32(sQD), 128);
+      (void)ones_lo;
+      (void)qd_lo_ns;
       // incrementally advanced state of the look-ahead S issue (s*) and of the consumer side (no divisions in this thread)
       int s_qc = 0, s_slot = 0, s_st = 0;
       uint32_t s_ub = 0, s_qpar = 0, s_round = 0;     // key-block counter, qd ring parity, (f >> 1) of the look-ahead block
@@ -602,12 +677,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tc_fence_after();
         const uint32_t kA = kv_lo_k + ks * (16384 >> 4), vA = kA + (8192 >> 4);
         const uint32_t qB = qd_lo_k + s_slot * (TCB_QD_BYTES >> 4), dB = qB + (4096 >> 4);
+        const uint32_t eB = qd_lo_ns + s_slot * (TCB_QD_BYTES >> 4) + (8192 >> 4);     // (-lse/sc2) tile; the (-delta) tile 2 KB further
+        (void)eB;
         const uint32_t d0 = tmem_base + s_st * 128;
         if (leader) {
           umma_bf16(d0, umma_desc_join(kA, hi64), umma_desc_join(qB, hi64), idesc_s, 0u);
           umma_bf16(d0, umma_desc_join(kA + 2, hi64), umma_desc_join(qB + 2, hi64), idesc_s, 1u);
+          if constexpr (AUG) umma_bf16(d0, umma_desc_join(ones_lo, hi_ns), umma_desc_join(eB, hi_ns), idesc_s, 1u);
           umma_bf16(d0 + 64, umma_desc_join(vA, hi64), umma_desc_join(dB, hi64), idesc_s, 0u);
           umma_bf16(d0 + 64, umma_desc_join(vA + 2, hi64), umma_desc_join(dB + 2, hi64), idesc_s, 1u);
+          if constexpr (AUG) umma_bf16(d0 + 64, umma_desc_join(ones_lo, hi_ns), umma_desc_join(eB + (2048 >> 4), hi_ns), idesc_s, 1u);
           umma_commit(&s_full[s_st]);
         }
         __syncwarp();
@@ -798,9 +877,9 @@ int ctb_attn_fwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
   return launch_tc_fwd<64, 32>(a, stream);
 }
 
-static int g_tc_bwd_warps = 16;
+static int g_tc_bwd_warps = 8, g_tc_bwd_aug = 0;
 
-template <int EW>
+template <int EW, bool AUG>
 static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {
   const long long rows = (long long)a->num_seqs * a->n;
   CUtensorMap tq, tdo, tk, tv;
@@ -824,10 +903,11 @@ static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.ld_dk = a->ld_dk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.ld_dv = a->ld_dv;
   p.ds_spill = (a->dcpb_table != nullptr) ? reinterpret_cast<__nv_bfloat16*>(a->ds_scratch) : nullptr;
+  p.dbias_t = a->dbias;      // (with cpb_table set) fp32 [heads, n keys, n queries], accumulated by reductions; see ctclip_cpb_reduce_t
   const int tab_elems = ((2 * a->grid_h - 1) * TcGeom<24>::STR + 31) & ~31;
-  const size_t smem = 1024 + 2 * 16384 + 2 * 32768 + (size_t)TCB_QD_SLOTS * TCB_QD_BYTES + (size_t)tab_elems * 4 + 20 * 8 + 8 + 24 * 4 + 64;
+  const size_t smem = 1024 + 2 * 16384 + 2 * 32768 + (size_t)TCB_QD_SLOTS * TCB_QD_BYTES + 4096 + (size_t)tab_elems * 4 + 20 * 8 + 8 + 24 * 4 + 64;
   CTB_CHECK_ARG(smem <= 227 * 1024, "attn_bwd(tc): %zu B of shared memory needed", smem);
-  auto kern = attn_tc_bwd_kernel<24, EW>;
+  auto kern = attn_tc_bwd_kernel<24, EW, AUG>;
   CTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent grid: a multiple of `heads` CTAs so that every item a CTA walks (blockIdx.x + k*gridDim.x) has the same head
   const int items = a->num_seqs * a->heads;
@@ -856,13 +936,17 @@ int ctb_attn_bwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
   CTB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0 && a->ld_dq % 8 == 0 && a->ld_dk % 8 == 0 &&
                     a->ld_dv % 8 == 0, "attn_bwd(tc): rows must be 16B aligned");
   CTB_CHECK_ARG(a->dcpb_table == nullptr || a->ds_scratch != nullptr, "attn_bwd(tc): dcpb_table needs ds_scratch");
-  CTB_CHECK_ARG(a->dbias == nullptr, "attn_bwd(tc): the table path produces dcpb_table, not dbias");
-  return (g_tc_bwd_warps == 8) ? launch_tc_bwd<8>(a, stream) : launch_tc_bwd<16>(a, stream);
+  CTB_CHECK_ARG(a->dbias == nullptr || a->dcpb_table == nullptr, "attn_bwd(tc): give dcpb_table (+ ds_scratch) OR dbias (transposed fp32 table)");
+  if (g_tc_bwd_aug) return (g_tc_bwd_warps == 8) ? launch_tc_bwd<8, true>(a, stream) : launch_tc_bwd<16, true>(a, stream);
+  return (g_tc_bwd_warps == 8) ? launch_tc_bwd<8, false>(a, stream) : launch_tc_bwd<16, false>(a, stream);
 }
 
-// Measurement knob (tools/attn_tc_probe.py): number of softmax-backward warps of the tcgen05 backward kernel, 8 or 16.
+// Measurement knob (tools/attn_tc_probe.py): number of softmax-backward warps of the tcgen05 backward kernel (8 or 16); +100 selects
+// the variant with the per-query terms folded into the tensor-core products (AUG).
 extern "C" int ctclip_debug_set_attn_bwd_warps(int32_t warps) {
-  CTB_CHECK_ARG(warps == 8 || warps == 16, "attn bwd warps must be 8 or 16");
-  g_tc_bwd_warps = warps;
+  const int w = warps % 100;
+  CTB_CHECK_ARG((w == 8 || w == 16) && (warps == w || warps == 100 + w), "attn bwd variant must be 8, 16, 108 or 116");
+  g_tc_bwd_warps = w;
+  g_tc_bwd_aug = warps >= 100;
   return CTCLIP_OK;
 }

@@ -140,7 +140,9 @@ __global__ void cpb_expand_frag_kernel(const float* __restrict__ table, int head
   }
 }
 // dtable[r][hd] = sum over (i,j) with rel(i,j) == r of dbias[hd][i][j]
-__global__ void cpb_reduce_kernel(const float* __restrict__ dbias, int heads, int h, int w, float* __restrict__ dtable) {
+// mirror = 1: the input is the TRANSPOSED table dbias_t[hd][j][i] (what the tcgen05 backward accumulates) and the result is
+// ADDED to dtable: element (row a, col b) of the input is d bias[b][a], whose offset is rel(b, a) = R - 1 - rel(a, b).
+__global__ void cpb_reduce_kernel(const float* __restrict__ dbias, int heads, int h, int w, float* __restrict__ dtable, int mirror) {
   const int r = blockIdx.x;
   const int n = h * w;
   const int dy = r / (2 * w - 1) - (h - 1), dx = r % (2 * w - 1) - (w - 1);
@@ -161,7 +163,10 @@ __global__ void cpb_reduce_kernel(const float* __restrict__ dbias, int heads, in
       if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) dtable[(long long)r * heads + hd] = red[0];
+    if (threadIdx.x == 0) {
+      if (mirror) dtable[(long long)((2 * h - 1) * (2 * w - 1) - 1 - r) * heads + hd] += red[0];
+      else dtable[(long long)r * heads + hd] = red[0];
+    }
     __syncthreads();
   }
 }
@@ -633,7 +638,14 @@ extern "C" int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t
 extern "C" int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(dbias && dtable && heads > 0 && h > 0 && w > 0, "cpb_reduce: bad args");
-  cpb_reduce_kernel<<<(2 * h - 1) * (2 * w - 1), 256, 0, stream>>>(dbias, heads, h, w, dtable);
+  cpb_reduce_kernel<<<(2 * h - 1) * (2 * w - 1), 256, 0, stream>>>(dbias, heads, h, w, dtable, 0);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+extern "C" int ctclip_cpb_reduce_t(const float* dbias_t, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(dbias_t && dtable && heads > 0 && h > 0 && w > 0, "cpb_reduce_t: bad args");
+  cpb_reduce_kernel<<<(2 * h - 1) * (2 * w - 1), 256, 0, stream>>>(dbias_t, heads, h, w, dtable, 1);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

@@ -242,6 +242,11 @@ def cpb_reduce(dbias, heads, h, w, dtable):
     call("ctclip_cpb_reduce", dbias.data_ptr(), heads, h, w, dtable.data_ptr(), _stream())
 
 
+def cpb_reduce_t(dbias_t, heads, h, w, dtable):
+    """transposed fp32 table gradient [heads, n(j), n(i)] (tcgen05 backward, red.add path) -> dtable += (mirrored offsets)"""
+    call("ctclip_cpb_reduce_t", dbias_t.data_ptr(), heads, h, w, dtable.data_ptr(), _stream())
+
+
 def geglu_bwd(dg, h, *, M, n_pairs, colsum_out=None, ld_dg=None, ld_h=None):
     call("ctclip_geglu_bwd", dg.data_ptr(), ld_dg if ld_dg is not None else dg.stride(0), h.data_ptr(),
          ld_h if ld_h is not None else h.stride(0), M, n_pairs, _ptr(colsum_out), _stream(),

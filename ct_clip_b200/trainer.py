@@ -307,6 +307,9 @@ class CTClipTrainer(nn.Module):
         loss.backward()
         if self.world > 1:
             self.bucketer.finish()
+        probe = getattr(self, "_grad_probe", None)
+        if probe is not None:    # tests (tests/dp_check_multigpu.py): the reduced gradient arena, before clipping / Adam
+            probe(self.arena)
         ev = getattr(self, "_ckpt_event", None)
         if ev is not None:       # an asynchronous checkpoint copy may still be reading the parameters
             torch.cuda.current_stream().wait_event(ev)

@@ -228,7 +228,9 @@ typedef struct {
    *   qk_bound   device scalar >= max_d |q_scale_d * k_scale_d| (NULL: 1): with unit-norm q_hat/q_scale, k_hat/k_scale it bounds
    *              |q_hat . k_hat|, which lets the kernels use a fixed softmax reference instead of an online maximum;
    *   dcpb_table backward: fp32 [(2*grid_h-1)*(2*grid_w-1), heads], ACCUMULATED gradient w.r.t. cpb_table (replaces dbias;
-   *              needs ds_scratch, bf16 [num_seqs*heads, n, n]).
+   *              needs ds_scratch, bf16 [num_seqs*heads, n, n]: d logits are spilled and reduced over the sequences);
+   *   OR dbias   (with cpb_table set) fp32 [heads, n, n] holding the TRANSPOSED gradient d bias[h, i, j] at [h][j][i], accumulated
+   *              with red.global.add.v4.f32 (stays in L2); ctclip_cpb_reduce_t turns it into the table gradient.
    * ctclip_attn_tc_supported() tells whether a geometry can take this path. */
   const float* cpb_table;
   int32_t grid_h, grid_w;
@@ -282,6 +284,9 @@ int ctclip_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int ctclip_cpb_inputs(float* X, int32_t h, int32_t w, void* stream);
 int ctclip_cpb_expand(const float* table, int32_t heads, int32_t h, int32_t w, void* bias, void* bias_t, void* stream);
 int ctclip_cpb_reduce(const float* dbias, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream);
+/* the same reduction for the TRANSPOSED table dbias_t fp32 [heads, n(j), n(i)] = d bias[h, i, j] that the tcgen05 backward accumulates
+ * when ctclip_attn_args.dbias is given together with cpb_table; the result is ADDED to dtable. */
+int ctclip_cpb_reduce_t(const float* dbias_t, int32_t heads, int32_t h, int32_t w, float* dtable, void* stream);
 /* fragment-ordered copies of bias * log2(e) and of its transpose (see ctclip_attn_args.bias_frag) */
 int ctclip_cpb_expand_frag(const float* table, int32_t heads, int32_t h, int32_t w, void* bias_frag, void* bias_t_frag,
                            void* stream);

@@ -40,6 +40,8 @@ def main():
                        results_folder="/tmp/dpcheck")
     dev = tr.device
     sl = slice(rank * b, (rank + 1) * b)
+    grads_dp = {}
+    tr._grad_probe = lambda ar: grads_dp.update({n: ar.grad_views[n].detach().clone() for n in ar.names})
     loss = tr.step_on_batch(hu[sl].to(dev), _Tokens(ids[sl].to(dev), mask[sl].to(dev)))
     torch.cuda.synchronize()
     after_dp = {k: v.detach().clone() for k, v in tr.CTClip.named_parameters()}
@@ -52,8 +54,23 @@ def main():
         tr1 = CTClipTrainer(build(), num_train_steps=1, batch_size=world * b, train_dataset=ds, num_workers=0, lr=1e-3,
                             save_model_every=0, results_folder="/tmp/dpcheck1")
         tr1.world, tr1.CTClip.dp_world = 1, 1
+        grads_1 = {}
+        tr1._grad_probe = lambda ar: grads_1.update({n: ar.grad_views[n].detach().clone() for n in ar.names})
         loss1 = tr1.step_on_batch(hu.to(dev), _Tokens(ids.to(dev), mask.to(dev)))
         torch.cuda.synchronize()
+        # raw gradients (after the all-reduce, before clipping and Adam): a wrong scale or sign is visible here, unlike after
+        # Adam's first step, which moves every element by ~lr whatever the gradient
+        gmax = max(v.abs().max().item() for v in grads_1.values() if v.numel() > 0)
+        gworst, gname = 0.0, ""
+        for k, v in grads_1.items():
+            if v.numel() == 0 or v.abs().max().item() < 1e-5 * gmax:
+                continue
+            e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-20)).item()
+            if e > gworst:
+                gworst, gname = e, k
+        t_dp, t_1 = grads_dp["temperature"].item(), grads_1["temperature"].item()
+        print(f"dp_check world={world}: worst relative-RMS gradient difference {gworst:.3e} ({gname}); d temperature dp {t_dp:.6e} vs "
+              f"single {t_1:.6e}")
         worst = 0.0
         for k, v in tr1.CTClip.named_parameters():
             if v.numel() == 0:      # null_kv (heads, 0, dim_head)
@@ -65,6 +82,7 @@ def main():
               f"{worst:.3e} (lr 1e-3); code-book EMA max diff {emb_d:.3e}")
         # Adam's first step moves every element by ~lr*sign(g): sign flips of near-zero gradients are the only differences
         ok = abs(loss_dp - loss1.item()) < 2e-3 * abs(loss1.item()) and worst <= 2.1e-3 and emb_d < 1e-2
+        ok = ok and gworst < 3e-2 and abs(t_dp - t_1) < 3e-2 * abs(t_1) + 1e-6 * gmax
         print("DP_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()

@@ -31,7 +31,7 @@ def _inputs(nseq, H, W, heads=8, dh=32, seed=0):
     return q, k, kv, tab, d_o, qs, ks
 
 
-@pytest.mark.parametrize("bwd_warps", [16, 8])
+@pytest.mark.parametrize("bwd_warps", [8, 16, 108, 116])
 @pytest.mark.parametrize("nseq,H,W", [(2, 24, 24), (3, 8, 24), (2, 16, 24), (1, 32, 24), (1, 32, 32), (20, 24, 24)])
 def test_attention_tc_fwd_bwd(nseq, H, W, bwd_warps):
     from ct_clip_b200 import _lib, ops
@@ -88,7 +88,14 @@ def test_attention_tc_fwd_bwd(nseq, H, W, bwd_warps):
     ops.attn_bwd(q, k, v, o, lse, d_o, delta, dq2, dkv, dkv[:, I:], ldq=I, ldk=I, ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I,
                  ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(H, W), **geom)
     assert torch.equal(dq2, dq)
-    _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(16), "restore default")
+    # table gradient through fp32 reductions into the transposed [h][j][i] table + mirrored binning
+    dbt = torch.zeros(heads, n, n, device=DEV)
+    ops.attn_bwd(q, k, v, o, lse, d_o, delta, dq2, dkv, dkv[:, I:], ldq=I, ldk=I, ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I,
+                 ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(H, W), dbias=dbt, **geom)
+    dtab2 = torch.zeros_like(tab)
+    ops.cpb_reduce_t(dbt, heads, H, W, dtab2)
+    assert rms_err(dtab2, tabr.grad) < 1e-2
+    _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(8), "restore default")
 
 
 def test_attention_tc_matches_mma_sync_path():

@@ -76,12 +76,16 @@ def main():
         print(f"attn_fwd tc       : {t:.3f} ms  {flops / t / 1e9:.0f} TFLOP/s")
         if not a.fwd_only:
             from ct_clip_b200 import _lib
-            for ew in ([a.bwd_warps] if a.bwd_warps else [8, 16]):
+            for ew in ([a.bwd_warps] if a.bwd_warps else [8, 16, 108, 116]):
                 _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(ew), "set warps")
                 t = timeit(bwd_tc)
-                print(f"attn_bwd tc +dtab [{ew:2d} warps]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (incl. delta + table-gradient reduction)")
+                print(f"attn_bwd tc +dtab [variant {ew:3d}]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (incl. delta + table-gradient reduction)")
+                dbt = torch.zeros(heads, n, n, device="cuda")
+                t = timeit(lambda: ops.attn_bwd(q, k, v, o, lse, d_o, delta, dq, dkv, dkv[:, I:], ldq=I, ldk=I, ldv=2 * I, ldo=I, ld_dq=I,
+                                                ld_dk=2 * I, ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(H, W), dbias=dbt, **geom))
+                print(f"attn_bwd tc +red  [variant {ew:3d}]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (table gradient by fp32 red.add into the L2-resident table)")
                 t = timeit(lambda: bwd_tc(False))
-                print(f"attn_bwd tc       [{ew:2d} warps]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (no table gradient / spill)")
+                print(f"attn_bwd tc       [variant {ew:3d}]: {t:.3f} ms  {2.5 * flops / t / 1e9:.0f} TFLOP/s (no table gradient / spill)")
     if a.only in ("both", "mma"):
         fwd_mma()
         t = timeit(fwd_mma)

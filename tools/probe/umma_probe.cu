@@ -493,6 +493,89 @@ static int run_diag(int mode) {
   return maxerr < 2e-3 ? 0 : 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ns16: K = 16 operands in the NO-SWIZZLE K-major canonical layout (8-row x 16-byte core matrices; LBO = 128 B between the two
+// K halves, SBO = 256 B between 8-row groups), written with plain st.shared: the "augmented k-step" tiles of the backward
+// kernel (A = ones, B = (-lse/sc2) split into three bf16 terms).  D[128, 64] (+)= A[128,16] B[64,16]^T, accumulating onto a
+// first SW64 MMA so that the accumulate path is the one the kernel uses.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) probe_ns16(const float* A, const float* B, float* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;            // 16 groups x 256 B
+  uint8_t* sB = smem + 4096;     // 8 groups x 256 B
+  uint64_t* bar = (uint64_t*)(smem + 8192);
+  uint32_t* holder = (uint32_t*)(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(holder, 64);
+    tmem_relinquish();
+  }
+  auto put = [](uint8_t* tile, int row, const float* src) {   // 16 values of one row -> two 16-byte core-matrix rows
+    for (int kh = 0; kh < 2; kh++) {
+      uint32_t w[4];
+      for (int j = 0; j < 4; j++) w[j] = pack_bf16x2(src[kh * 8 + 2 * j], src[kh * 8 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(tile + (row >> 3) * 256 + kh * 128 + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  };
+  put(sA, tid, A + tid * 16);
+  if (tid < 64) put(sB, tid, B + tid * 16);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *holder;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc(1, 0, 0, 128, 64);
+    const uint64_t ad = umma_smem_desc_sw(smem_u32(sA), 128, 256, 0);
+    const uint64_t bd = umma_smem_desc_sw(smem_u32(sB), 128, 256, 0);
+    umma_bf16(tm, ad, bd, idesc, 0);
+    umma_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after();
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; j++) out[tid * 64 + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 64);
+}
+static int run_ns16() {
+  std::vector<float> A(128 * 16), B(64 * 16);
+  uint32_t s = 31337u;
+  for (auto& x : A) x = frand(s);
+  for (auto& x : B) x = frand(s);
+  float *dA, *dB, *dO;
+  CK(cudaMalloc(&dA, A.size() * 4));
+  CK(cudaMalloc(&dB, B.size() * 4));
+  CK(cudaMalloc(&dO, 128 * 64 * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  const int smem = 1024 + 8192 + 64;
+  CK(cudaFuncSetAttribute(probe_ns16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_ns16<<<1, 128, smem>>>(dA, dB, dO);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> O(128 * 64);
+  CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  for (int m = 0; m < 128; m++)
+    for (int n = 0; n < 64; n++) {
+      float r = 0;
+      for (int k = 0; k < 16; k++) r += bf(A[m * 16 + k]) * bf(B[n * 16 + k]);
+      maxerr = fmax(maxerr, fabs(r - O[m * 64 + n]));
+    }
+  printf("probe ns16 (no-swizzle K-major, K = 16): max abs err %.3e -> %s\n", maxerr, maxerr < 1e-3 ? "PASS" : "FAIL");
+  return maxerr < 1e-3 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   const char* which = argc > 1 ? argv[1] : "all";
   int rc = 0;
@@ -501,6 +584,7 @@ int main(int argc, char** argv) {
   else if (!strcmp(which, "mna")) rc = run_mna();
   else if (!strcmp(which, "red")) rc = run_red();
   else if (!strcmp(which, "diag")) rc = run_diag(argc > 2 ? atoi(argv[2]) : 0);
+  else if (!strcmp(which, "ns16")) rc = run_ns16();
   else printf("usage: umma_probe ss64 N | ts KK pcol0 pcol1 ocol | mna | red\n");
   return rc;
 }
