@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=240)
     ap.add_argument("--text-len", type=int, default=128)
     ap.add_argument("--bert-layers", type=int, default=12)
+    ap.add_argument("--config", default="train", choices=["train", "zero_shot"],
+                    help="train: BASELINE configs[1] contrastive step (the headline); zero_shot: configs[3], 18 x 2 prompt bank x N volumes")
+    ap.add_argument("--volumes", type=int, default=1304, help="zero_shot: number of synthetic volumes (reference validation set: 1304)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-stage roofline pass (one extra untimed step)")
     ap.add_argument("--cpu-sample-volumes", type=int, default=2)
@@ -466,6 +469,83 @@ def _mem_available_gb():
     return 0.0
 
 
+def run_zero_shot(args):
+    """BASELINE configs[3] (scripts/run_zero_shot.py / zero_shot.py:106-171): the 36-prompt text bank is encoded once, every volume
+    goes through the image tower once. `value`: volumes resident in HBM; `e2e`: CTClipInference.infer() on host batches (pinned
+    memory, the H2D copy of every batch and the D2H read-back of its (b, 18) probabilities inside the timed region)."""
+    import numpy as np
+
+    from ct_clip_b200 import _lib
+    from ct_clip_b200.inference import CTClipInference, prompts
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    clip = build_model(args, device).eval()
+    n_prompts = len(prompts())
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(5, 30522, (n_prompts, args.text_len), generator=g)
+    lens = torch.randint(8, 16, (n_prompts,), generator=g)
+    mask = (torch.arange(args.text_len)[None, :] < lens[:, None]).long()
+    ids[:, 0] = 2
+    ids = ids * mask
+    bsz = args.batch
+    pool = [(torch.randn(bsz, 1, args.frames, args.image, args.image, generator=g) * 450.0 - 300.0).round_().clamp_(-1000, 1000)
+            .to(torch.int16).pin_memory() for _ in range(2)]          # 2 x 885 MB: alternating batches > L2
+
+    class Pool(torch.utils.data.Dataset):
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            return pool[(i // bsz) & 1][i % bsz], "", np.zeros(18, dtype=np.float32), f"vol{i}"
+    n_vol = (args.volumes + bsz - 1) // bsz * bsz
+    inf = CTClipInference(clip, dataset=Pool(n_vol), prompt_tokens=dict(input_ids=ids, attention_mask=mask), batch_size=bsz,
+                          results_folder="/tmp/ctclip_zero_shot")
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    # ---- device-resident: text bank once + image tower per batch
+    dev_pool = [p.to(device) for p in pool]
+    from ct_clip_b200 import ops
+    with torch.no_grad():
+        for w in range(max(3, args.warmup)):
+            clip.encode_image_latents(dev_pool[w & 1])
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        text_lat = clip.encode_text_latents(inf._bank())
+        for b in range(n_vol // bsz):
+            img = clip.encode_image_latents(dev_pool[b & 1])
+            probs = torch.empty(bsz, 18, device=device)
+            ops.zero_shot_probs(img, text_lat, clip.temperature, probs)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - l0
+    sampler.window(t_wall0, time.time())
+    clocks = sampler.stop()
+    # ---- end to end through the public API (DataLoader over pinned host volumes -> H2D -> infer -> probabilities on the host)
+    inf.infer()                                  # warm-up pass over the pool (untimed)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    pred = inf.infer()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    out = {"metric": "CT volumes/sec zero-shot inference (18 pathologies x 2 prompts), 480x480x240", "value": n_vol / (ms * 1e-3),
+           "unit": "volumes/s", "n_gpus": 1, "steps": n_vol // bsz, "warmup": max(3, args.warmup), "ms_per_step": ms / (n_vol // bsz),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"BASELINE configs[3]: 36-prompt text bank x {n_vol} synthetic {args.image}x{args.image}x{args.frames} int16 volumes, "
+                                  f"CTViT dim512 depth{args.depth}+{args.depth}, batches of {bsz}", "parallelism": "dp1",
+                      "l2": "two alternating 885 MB input batches (> 126 MB L2)"},
+           "e2e": {"value": n_vol / dt, "unit": "volumes/s", "h2d_bytes_per_step": int(pool[0].numel() * 2), "d2h_bytes_per_step": bsz * 18 * 4,
+                   "note": "wall clock around CTClipInference.infer(): DataLoader collation of pinned volumes + H2D + image tower + D2H"},
+           "gpu_launches": launches // max(1, n_vol // bsz), "clocks": clocks, "probs_shape": list(pred.shape)}
+    _emit(_OUT_FD, out)
+
+
 def cpu_baseline_guarded(args):
     """cpu_baseline leg of the GPU arm: the reference arm in a CHILD process (the eager CPU autograd of 2 whole volumes at
     12+12 layers keeps ~45 GB of activations: an out-of-memory kill or a slow host must not take the bench line with it).
@@ -566,5 +646,7 @@ if __name__ == "__main__":
     _OUT_FD = _quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "zero_shot":
+        run_zero_shot(a)
     else:
         run_b200(a)

@@ -101,6 +101,7 @@ SIGNATURES = {
     "ctclip_peg_fwd": [C.POINTER(PegArgs), P],
     "ctclip_peg_bwd_data": [C.POINTER(PegArgs), P],
     "ctclip_peg_bwd_weight": [C.POINTER(PegArgs), P],
+    "ctclip_debug_set_peg_variant": [I32],
     "ctclip_attn_fwd": [C.POINTER(AttnArgs), P],
     "ctclip_attn_bwd": [C.POINTER(AttnArgs), P],
     "ctclip_attn_tc_supported": [I32, I32, I32, I32],

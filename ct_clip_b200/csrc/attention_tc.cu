@@ -563,9 +563,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
               __syncwarp();
               const uint8_t* tile_w = sDS + buf * 32768 + grp * 16384 + (q * 32) * 128;
               __nv_bfloat16* sp = p.ds_spill + ((long long)item * n + kb * 128 + q * 32) * n + qc * 64;
+              // a 16-byte shared load is served per quarter-warp: the 8 lanes of a quarter take rows CPR apart, so that their
+              // swizzled chunks (ch ^ (row & 7)) cover all eight 16-byte bank groups (no conflict; ncu r2e showed 2-way before)
+              const int sp_row = ((lane & 7) / CPR) * CPR + ((lane >> 3) % CPR) + 8 * ((lane >> 3) / CPR);
 #pragma unroll
               for (int j = 0; j < CPR; j++) {
-                const int rr = j * (32 / CPR) + lane / CPR, ch = cq * CPR + lane % CPR;
+                const int rr = j * (32 / CPR) + sp_row, ch = cq * CPR + lane % CPR;
                 const uint4 val = *reinterpret_cast<const uint4*>(tile_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
                 __stcs(reinterpret_cast<uint4*>(sp + (long long)rr * n + ch * 8), val);
               }
@@ -877,7 +880,7 @@ int ctb_attn_fwd_tc(const ctclip_attn_args* a, cudaStream_t stream) {
   return launch_tc_fwd<64, 32>(a, stream);
 }
 
-static int g_tc_bwd_warps = 8, g_tc_bwd_aug = 0;
+static int g_tc_bwd_warps = 8, g_tc_bwd_aug = 1;
 
 template <int EW, bool AUG>
 static int launch_tc_bwd(const ctclip_attn_args* a, cudaStream_t stream) {

@@ -69,6 +69,32 @@ int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, con
   return CTCLIP_OK;
 }
 
+int encode_tmap_nd(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return CTCLIP_ERR_DRIVER;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; i++) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) st[i] = strides_bytes[i];
+  }
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed: CUresult=%d (dims %llu %llu %llu.. box %u %u %u..)", rank, (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1],
+              rank > 2 ? box[2] : 0);
+    return CTCLIP_ERR_DRIVER;
+  }
+  return CTCLIP_OK;
+}
+
 }  // namespace ctb
 
 extern "C" int ctclip_version(void) { return CTCLIP_B200_VERSION; }

@@ -45,6 +45,10 @@ int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, con
                    uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner,
                    uint32_t box_outer, CUtensorMapSwizzle swz);
 
+// rank <= 5 tiled tensor map, dims[0] = contiguous dimension, strides_bytes[i] = byte stride of dims[i+1] (rank-1 entries)
+int encode_tmap_nd(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace ctb

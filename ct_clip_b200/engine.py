@@ -100,6 +100,9 @@ class CTViTEngine:
         import os
         tc = ops.attn_tc_supported(g.S, g.H, g.W, g.dim_head) if os.environ.get("CTCLIP_ATTN_TC", "1") != "0" else 0
         self.tc_fwd, self.tc_bwd = bool(tc & 1), bool(tc & 2)
+        # table gradient of the tcgen05 backward: False = bf16 spill + reduction over the sequences, True = fp32 red.global.add into
+        # an L2-resident transposed [heads, S, S] table (one binning pass per step)
+        self.tc_dbias_red = os.environ.get("CTCLIP_ATTN_DBIAS_RED", "0") == "1"
         # data parallelism: callable(prefix) invoked when every gradient of the parameters under `prefix` is final (the trainer
         # starts their all-reduce while the rest of the backward is still running)
         self.on_grads_ready = None
@@ -387,7 +390,11 @@ class CTViTEngine:
         dqh = torch.empty(M, I, **bf)
         dkv = torch.empty(M, 2 * I, **bf)       # [dk_hat | dv]
         delta = torch.empty(M, g.heads, device=dev)
-        if dtab is not None:      # tcgen05 / TMEM kernel: one pass, table gradient accumulated into dtab
+        if dtab is not None and self.tc_dbias_red:      # tcgen05 / TMEM kernel; d bias accumulated by fp32 reductions into dtab = [h][j][i]
+            ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
+                         ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(g.H, g.W),
+                         dbias=dtab, **self._attn_geom(b, T, temporal))
+        elif dtab is not None:      # tcgen05 / TMEM kernel: one pass, d logits spilled (bf16) + reduced over the sequences into dtab
             ops.attn_bwd(sv.qh, sv.kh, sv.kv_raw[:, I:], sv.o, sv.lse, d_o, delta, dqh, dkv, dkv[:, I:], ldq=I, ldk=I,
                          ldv=2 * I, ldo=I, ld_dq=I, ld_dk=2 * I, ld_dv=2 * I, total_rows=M, cpb_table=tab, grid_hw=(g.H, g.W),
                          dcpb_table=dtab, ds_scratch=self._ds_scratch(b, T), **self._attn_geom(b, T, temporal))
@@ -439,7 +446,9 @@ class CTViTEngine:
                    rstd=ctx["rstd_ns"], dx_f32=d2, dx_bf16=dxb, dgamma=G["enc_spatial_transformer.norm_out.gamma"])
         dres = d2
         dbias = dtab = None
-        if self.tc_bwd:
+        if self.tc_bwd and self.tc_dbias_red:
+            dtab = torch.zeros(g.heads, g.S, g.S, device=dev)        # TRANSPOSED d bias [h][j][i], L2-resident (10.6 MB at S = 576)
+        elif self.tc_bwd:
             dtab = torch.zeros(self.cpb_x.shape[0], g.heads, device=dev)
         else:
             dbias = torch.zeros(g.heads, g.S, g.S, device=dev)
@@ -450,6 +459,9 @@ class CTViTEngine:
             ctx["saved_s"][i] = None
             if self.on_grads_ready is not None:
                 self.on_grads_ready(f"enc_spatial_transformer.layers.{i}.")
+        if self.tc_bwd and self.tc_dbias_red:
+            dbt, dtab = dtab, torch.zeros(self.cpb_x.shape[0], g.heads, device=dev)
+            ops.cpb_reduce_t(dbt, g.heads, g.H, g.W, dtab)
         self._cpb_backward(P, G, dbias, ctx["cpb_h"], dtab=dtab)
         # patch embedding: x = LN_D(xhat_p Wp'^T + bp')
         ops.ln_bwd(M, D, g_f32=dres, gamma=P["to_patch_emb.3.weight"], xhat=ctx["xhat3"], rstd=ctx["rstd3"], dx_bf16=dxb,

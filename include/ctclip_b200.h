@@ -180,6 +180,9 @@ typedef struct {
 int ctclip_peg_fwd(const ctclip_peg_args* args, void* stream);
 int ctclip_peg_bwd_data(const ctclip_peg_args* args, void* stream);
 int ctclip_peg_bwd_weight(const ctclip_peg_args* args, void* stream);
+/* measurement / test knob (tools/peg_probe.py, tests): 0 = plane-streaming kernels (csrc/peg_stream.cu) whenever the token grid
+ * allows them (default), 1 = always the general kernels of csrc/peg.cu */
+int ctclip_debug_set_peg_variant(int32_t variant);
 
 /* ------------------------------------------------------------------------------------------
  * Attention core (attention.py:156-178; also BERT self-attention), dim_head 32 or 64. q/k are the l2-normalised, scaled projections

@@ -62,12 +62,16 @@ def main():
         # Adam's first step, which moves every element by ~lr whatever the gradient
         gmax = max(v.abs().max().item() for v in grads_1.values() if v.numel() > 0)
         gworst, gname = 0.0, ""
+        errs = []
         for k, v in grads_1.items():
             if v.numel() == 0 or v.abs().max().item() < 1e-5 * gmax:
                 continue
             e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-20)).item()
+            errs.append((e, k, v.pow(2).mean().sqrt().item(), grads_dp[k].pow(2).mean().sqrt().item()))
             if e > gworst:
                 gworst, gname = e, k
+        for e, k, r1, rdp in sorted(errs, reverse=True)[:8]:
+            print(f"   grad diff {e:.3e}  rms single {r1:.3e}  rms dp {rdp:.3e}  {k}")
         t_dp, t_1 = grads_dp["temperature"].item(), grads_1["temperature"].item()
         print(f"dp_check world={world}: worst relative-RMS gradient difference {gworst:.3e} ({gname}); d temperature dp {t_dp:.6e} vs "
               f"single {t_1:.6e}")
@@ -81,8 +85,10 @@ def main():
         print(f"dp_check world={world}: loss dp {loss_dp:.6f} vs single {loss1.item():.6f}; max |param diff| after one step "
               f"{worst:.3e} (lr 1e-3); code-book EMA max diff {emb_d:.3e}")
         # Adam's first step moves every element by ~lr*sign(g): sign flips of near-zero gradients are the only differences
-        ok = abs(loss_dp - loss1.item()) < 2e-3 * abs(loss1.item()) and worst <= 2.1e-3 and emb_d < 1e-2
-        ok = ok and gworst < 3e-2 and abs(t_dp - t_1) < 3e-2 * abs(t_1) + 1e-6 * gmax
+        gates = {"loss": abs(loss_dp - loss1.item()) < 2e-3 * abs(loss1.item()), "params": worst <= 2.1e-3, "ema": emb_d < 1e-2,
+                 "grads": gworst < 3e-2, "temperature": abs(t_dp - t_1) < 3e-2 * abs(t_1) + 1e-6 * gmax}
+        print("dp_check gates:", gates, "gmax", gmax)
+        ok = all(gates.values())
         print("DP_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()

@@ -95,7 +95,7 @@ def test_attention_tc_fwd_bwd(nseq, H, W, bwd_warps):
     dtab2 = torch.zeros_like(tab)
     ops.cpb_reduce_t(dbt, heads, H, W, dtab2)
     assert rms_err(dtab2, tabr.grad) < 1e-2
-    _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(8), "restore default")
+    _lib.check(_lib.lib().ctclip_debug_set_attn_bwd_warps(108), "restore default")
 
 
 def test_attention_tc_matches_mma_sync_path():

@@ -58,7 +58,8 @@ def test_layernorm_fwd_bwd(D):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("exact", [True, False])
 @pytest.mark.parametrize("temporal,T,H,W", [(False, 4, 4, 4), (True, 4, 4, 4), (False, 5, 3, 6), (True, 5, 3, 6), (True, 6, 4, 4),
-                                            (False, 3, 10, 24), (True, 6, 10, 24)])
+                                            (False, 3, 10, 24), (True, 6, 10, 24), (False, 7, 12, 20), (True, 8, 8, 8),
+                                            (False, 26, 24, 24), (True, 24, 24, 24)])
 def test_peg_fwd_bwd(temporal, T, H, W, exact):
     """exact=True: fp32 stencil kernels (the default path) against the fp32 oracle (1e-5). exact=False: the opt-in bf16
     tensor-core kernels (csrc/peg_mma.cu), checked
@@ -66,6 +67,9 @@ def test_peg_fwd_bwd(temporal, T, H, W, exact):
     (b) against the fp32 oracle within the bf16 tolerance of north_star (1e-2)."""
     from ct_clip_b200 import ops
     from oracle import ctclip_oracle as O
+    # which kernels run (exact=True): spatial grids with W <= 24 and temporal grids with T == H == W take the plane-streaming
+    # kernels (csrc/peg_stream.cu; the 24^3 cases cut the CTA ranges mid-column: priming steps, several columns per CTA),
+    # the other temporal grids the general kernels of csrc/peg.cu; test_peg_kernel_families_agree pins the two against each other
     b, D = 2, 512
     x = _randn(b, T, H, W, D, seed=7)            # canonical layout
     w = 0.2 * _randn(D, 1, 3, 3, 3, seed=8)
@@ -110,6 +114,36 @@ def test_peg_fwd_bwd(temporal, T, H, W, exact):
         assert rel_err(dx, xf.grad + dy.cpu()) < 1e-2
         assert rel_err(dw, wf.grad.view(D, 27)) < 1e-2
         assert rel_err(db, bf_.grad) < 1e-2
+
+
+@pytest.mark.parametrize("temporal,T,H,W", [(False, 24, 24, 24), (True, 24, 24, 24), (False, 9, 13, 22), (True, 12, 12, 12)])
+def test_peg_kernel_families_agree(temporal, T, H, W):
+    """plane-streaming kernels (default) vs the general kernels on the same inputs: forward, data gradient (+ bf16 copy), weight
+    and bias gradients; b = 3 so that CTA ranges start and end mid-column in both families."""
+    from ct_clip_b200 import _lib, ops
+    b, D = 3, 512
+    x = _randn(b * T * H * W, D, seed=11)
+    dy = _randn(b * T * H * W, D, seed=12)
+    w = 0.2 * _randn(D, 27, seed=13)
+    bias = 0.1 * _randn(D, seed=14)
+    kw = dict(B=b, T=T, H=H, W=W, D=D, temporal=temporal)
+    res = {}
+    try:
+        for variant in (0, 1):
+            _lib.check(_lib.lib().ctclip_debug_set_peg_variant(variant), "variant")
+            y, dx = torch.empty_like(x), torch.empty_like(x)
+            dxb = torch.empty(x.shape, dtype=torch.bfloat16, device=DEV)
+            dw, db = torch.zeros(D, 27, device=DEV), torch.zeros(D, device=DEV)
+            ops.peg_fwd(x, y, w, bias, **kw)
+            ops.peg_bwd_data(dy, dx, w, dx_bf16=dxb, **kw)
+            ops.peg_bwd_weight(x, dy, dw, db, **kw)
+            ops.peg_bwd_weight(x, dy, dw, db, **kw)            # gradients ACCUMULATE
+            torch.cuda.synchronize()
+            res[variant] = (y, dx, dxb.float(), dw, db)
+    finally:
+        _lib.check(_lib.lib().ctclip_debug_set_peg_variant(0), "restore default")
+    for a, r, tol in zip(res[0], res[1], (1e-5, 1e-5, 1e-2, 1e-4, 1e-4)):
+        assert rel_err(a, r) < tol, (rel_err(a, r), tol)
 
 
 # ------------------------------------------------------------------------------------------------
