@@ -1193,12 +1193,16 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 
 // Backward of  x_hat = x / max(||x||, eps) * scale  per (row, head):  given d(x_hat) and raw x:
 //   u = scale * dxh;  dx = (u - xn * (xn . u)) / ||x||  with xn = x/||x||;   dscale[d] += dxh[d] * xn[d]
+// HEADS > 0: compile-time head count (8 on the CTViT path, 12 would be BERT-like); 0: run-time. The item index is 32-bit
+// (the 64-bit division + modulo per 48-byte item used to dominate the instruction count of this kernel: 44 % of HBM).
+template <int HEADS>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ dxh, long long ld_dxh,
                                                         const __nv_bfloat16* __restrict__ xraw, long long ld_x,
                                                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ dx,
-                                                        long long ld_dx, float* __restrict__ dscale, long long rows,
-                                                        int heads) {
+                                                        long long ld_dx, float* __restrict__ dscale, unsigned n_items,
+                                                        int heads_rt) {
   constexpr int DH = 32;
+  const unsigned heads = HEADS > 0 ? (unsigned)HEADS : (unsigned)heads_rt;
   __shared__ float sds[DH];
   if (threadIdx.x < DH) sds[threadIdx.x] = 0.f;
   __syncthreads();
@@ -1206,12 +1210,13 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
   float sc[8], dsc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) { sc[i] = scale[part * 8 + i]; dsc[i] = 0.f; }
-  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); idx < rows * heads;
-       idx += (long long)gridDim.x * (blockDim.x >> 2)) {
-    const long long row = idx / heads;
-    const int head = (int)(idx % heads);
-    const uint4 ug = *reinterpret_cast<const uint4*>(dxh + row * ld_dxh + head * DH + part * 8);
-    const uint4 ux = *reinterpret_cast<const uint4*>(xraw + row * ld_x + head * DH + part * 8);
+  const unsigned stride = gridDim.x * (blockDim.x >> 2);
+  for (unsigned idx = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); idx < n_items; idx += stride) {
+    const unsigned row = idx / heads;
+    const unsigned head = idx - row * heads;
+    const long long col = (long long)head * DH + part * 8;
+    const uint4 ug = *reinterpret_cast<const uint4*>(dxh + (long long)row * ld_dxh + col);
+    const uint4 ux = *reinterpret_cast<const uint4*>(xraw + (long long)row * ld_x + col);
     const uint32_t* pg = reinterpret_cast<const uint32_t*>(&ug);
     const uint32_t* px = reinterpret_cast<const uint32_t*>(&ux);
     float gg[8], xx[8];
@@ -1239,7 +1244,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int i = 0; i < 4; i++)
       po[i] = pack_bf16x2((gg[2 * i] - xx[2 * i] * dot) * inv, (gg[2 * i + 1] - xx[2 * i + 1] * dot) * inv);
-    *reinterpret_cast<uint4*>(dx + row * ld_dx + head * DH + part * 8) = out;
+    *reinterpret_cast<uint4*>(dx + (long long)row * ld_dx + col) = out;
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) atomicAdd(&sds[part * 8 + i], dsc[i]);
@@ -1417,12 +1422,19 @@ extern "C" int ctclip_l2norm_bwd(const void* dxh, int64_t ld_dxh, const void* xr
   CTB_CHECK_ARG(dim_head == 32, "l2norm_bwd: dim_head must be 32");
   CTB_CHECK_ARG(dxh && xraw && scale && dx && dscale && rows > 0 && heads > 0, "l2norm_bwd: bad args");
   CTB_CHECK_ARG(ld_dxh % 8 == 0 && ld_x % 8 == 0 && ld_dx % 8 == 0, "l2norm_bwd: rows must be 16B aligned");
+  CTB_CHECK_ARG(rows * heads < (1ll << 31), "l2norm_bwd: rows*heads must fit 31 bits");
   long long ctas = (rows * heads + 63) / 64;
   const long long cap = (long long)num_sms() * 8;
   if (ctas > cap) ctas = cap;
-  l2norm_bwd_kernel<<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,
-                                                  reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,
-                                                  reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, rows, heads);
+  const unsigned n_items = (unsigned)(rows * heads);
+#define L2N_LAUNCH(H)                                                                                                   \
+  l2norm_bwd_kernel<H><<<(int)ctas, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dxh), ld_dxh,              \
+                                                     reinterpret_cast<const __nv_bfloat16*>(xraw), ld_x, scale,         \
+                                                     reinterpret_cast<__nv_bfloat16*>(dx), ld_dx, dscale, n_items, heads)
+  if (heads == 8) L2N_LAUNCH(8);
+  else if (heads == 12) L2N_LAUNCH(12);
+  else L2N_LAUNCH(0);
+#undef L2N_LAUNCH
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

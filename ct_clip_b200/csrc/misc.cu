@@ -197,8 +197,10 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const float2 xv = unpack_bf16x2(ph[i]);  // (value, gate)
-        const float dval = dgv[i] * gelu_erf(xv.y);
-        const float dgate = dgv[i] * xv.x * gelu_erf_grad(xv.y);
+        float ge, dge;
+        gelu_erf_fast_both(xv.y, ge, dge);
+        const float dval = dgv[i] * ge;
+        const float dgate = dgv[i] * xv.x * dge;
         ph[i] = pack_bf16x2(dval, dgate);
         cs[2 * i] += dval;
         cs[2 * i + 1] += dgate;
@@ -460,7 +462,10 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(__nv_bfloat16* __restrict
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const float2 d = unpack_bf16x2(pd[i]), x = unpack_bf16x2(pp[i]);
-        const float a = d.x * gelu_erf_grad(x.x), b = d.y * gelu_erf_grad(x.y);
+        float g0, g1, dg0, dg1;
+        gelu_erf_fast_both(x.x, g0, dg0);
+        gelu_erf_fast_both(x.y, g1, dg1);
+        const float a = d.x * dg0, b = d.y * dg1;
         pd[i] = pack_bf16x2(a, b);
         cs[2 * i] += a;
         cs[2 * i + 1] += b;

@@ -347,6 +347,25 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float h = 0.5f * ax;
   return fmaf(-h, poly * e, fmaf(0.5f, x, h));
 }
+// gelu(x) and d/dx gelu(x) from ONE rcp.approx + ONE ex2.approx (same erf approximation as gelu_erf_fast, |abs error| <= 1.5e-7):
+//   e = exp(-x^2/2), q = poly(t) e / 2  ->  cdf = x >= 0 ? 1 - q : q,  gelu = x cdf,  gelu' = cdf + x e / sqrt(2 pi).
+// The backward kernels used erff twice + __expf per element (~70 instructions) and were issue-bound, not HBM-bound.
+__device__ __forceinline__ void gelu_erf_fast_both(float x, float& g, float& dg) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));
+  const float q = 0.5f * poly * e;
+  const float cdf = x >= 0.f ? 1.0f - q : q;
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 // d/dx gelu(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

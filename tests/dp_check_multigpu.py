@@ -66,12 +66,17 @@ def main():
         for k, v in grads_1.items():
             if v.numel() == 0 or v.abs().max().item() < 1e-5 * gmax:
                 continue
-            e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-20)).item()
+            # relative RMS difference; tensors whose gradient is analytically zero (the key bias of a softmax attention: 1.6e-6
+            # of rounding noise at a global scale of 0.11) are measured against 1e-4 of the global gradient scale instead
+            e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-4 * gmax)).item()
             errs.append((e, k, v.pow(2).mean().sqrt().item(), grads_dp[k].pow(2).mean().sqrt().item()))
             if e > gworst:
                 gworst, gname = e, k
-        for e, k, r1, rdp in sorted(errs, reverse=True)[:8]:
-            print(f"   grad diff {e:.3e}  rms single {r1:.3e}  rms dp {rdp:.3e}  {k}")
+        lines = [f"   grad diff {e:.3e}  rms single {r1:.3e}  rms dp {rdp:.3e}  {k}" for e, k, r1, rdp in sorted(errs, reverse=True)]
+        print("\n".join(lines[:8]))
+        report = os.environ.get("DP_CHECK_REPORT")
+        if report:      # full per-tensor list for a post-mortem
+            Path(report).write_text("\n".join(lines) + "\n")
         t_dp, t_1 = grads_dp["temperature"].item(), grads_1["temperature"].item()
         print(f"dp_check world={world}: worst relative-RMS gradient difference {gworst:.3e} ({gname}); d temperature dp {t_dp:.6e} vs "
               f"single {t_1:.6e}")
