@@ -198,7 +198,7 @@ extern "C" int ctclip_patchify(const ctclip_patchify_args* a, void* stream_) {
   const size_t smem = sizeof(float) * (4 * Wt + (size_t)a->p1 * a->W);
   // measured on B200 at configs[1] (tools/small_probe.py): 1596 us (v2) -> 672 us (v3), outputs equal to one bf16 ulp (the
   // per-patch moments are reduced with shared-memory atomics in both). CTCLIP_PATCHIFY_V3=0 selects the v2 kernel.
-  const int v3 = getenv("CTCLIP_PATCHIFY_V3") ? atoi(getenv("CTCLIP_PATCHIFY_V3")) : 1;
+  static const int v3 = getenv("CTCLIP_PATCHIFY_V3") ? atoi(getenv("CTCLIP_PATCHIFY_V3")) : 1;   // debug knob, read once
   const bool v3_ok = v3 && a->W / 2 <= 256 && (a->p1 * a->p2) / 2 <= 7 * 32;
   if (v3_ok) {
     if (a->dtype == 1) patchify3_kernel<true><<<grid, 256, smem, stream>>>(*a);

@@ -236,6 +236,7 @@ class CTViT(nn.Module):
         if self._force_indices is not None:
             ectx["idx"] = self._force_indices.to(device=video.device, dtype=torch.int32).reshape(-1).contiguous()
         ectx["P"] = P
+        self._last_indices = ectx["idx"].view(ectx["b"], ectx["T"], self.engine.g.H, self.engine.g.W)   # code-book ids of this pass
         return ectx
 
     def _finish_quantize(self, ectx):

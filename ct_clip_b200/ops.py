@@ -62,7 +62,7 @@ def _gemm_bytes(M, N, K, epilogue, norm_cols, has_c):
     return ops_b + out
 
 
-def wgrad_splits(k_red: int, out_tiles: int, sms: int = 148) -> int:
+def wgrad_splits(k_red: int, out_tiles: int) -> int:
     """Split-K factor for a weight-gradient GEMM: 0 = let the library choose (it minimises waves x k-blocks per unit for
     the tile shape it actually launches; a fixed '4 waves' guess left the 2816x512 gradient at 2.08 waves = 3 wave times)."""
     return 0
