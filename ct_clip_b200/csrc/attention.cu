@@ -1207,6 +1207,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
   if (threadIdx.x < DH) sds[threadIdx.x] = 0.f;
   __syncthreads();
   const int part = threadIdx.x & 3;
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);   // the four lanes of this item (the tail of the item loop diverges per quad)
   float sc[8], dsc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) { sc[i] = scale[part * 8 + i]; dsc[i] = 0.f; }
@@ -1228,7 +1229,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
       xx[2 * i] = b.x; xx[2 * i + 1] = b.y;
       ss += b.x * b.x + b.y * b.y;
     }
-    ss = quad_sum(ss);
+    ss += __shfl_xor_sync(qmask, ss, 1);
+    ss += __shfl_xor_sync(qmask, ss, 2);
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     float dot = 0.f;
 #pragma unroll
@@ -1238,7 +1240,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const __nv_bfloat16* __
       gg[i] *= sc[i];               // u
       dot += gg[i] * xx[i];
     }
-    dot = quad_sum(dot);
+    dot += __shfl_xor_sync(qmask, dot, 1);
+    dot += __shfl_xor_sync(qmask, dot, 2);
     uint4 out;
     uint32_t* po = reinterpret_cast<uint32_t*>(&out);
 #pragma unroll

@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* __r
   for (int i = 0; i < 8; i++) cs[i] = 0.f;
   const bool ok = cg * 4 < n_pairs;
   if (ok) {
+    // HBM-bound at ~70 % of the copy bandwidth whatever the arithmetic: neither the rcp/ex2 form of gelu / gelu' (instead of two
+    // erff + expf) nor two rows in flight per thread changed the time (profiles/r2_stages_history.md)
     for (long long m = m0 + rl; m < m1; m += 4) {
       const uint2 ud = *reinterpret_cast<const uint2*>(dg + m * ld_dg + cg * 4);
       uint4 uh = *reinterpret_cast<const uint4*>(h + m * ld_h + cg * 8);

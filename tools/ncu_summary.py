@@ -17,6 +17,10 @@ WANT = [("gpu__time_duration.sum", "time"), ("launch__registers_per_thread", "re
         ("lts__t_sector_hit_rate.pct", "l2hit%"), ("l1tex__t_sector_hit_rate.pct", "l1hit%"),
         ("lts__t_bytes.sum", "l2_bytes"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_lsu_wavefronts%"),
+        ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_tensor_operand_wavefronts%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu(sfu)%"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe%"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long_sb"),
         ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short_sb"),
         ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_barrier"),
