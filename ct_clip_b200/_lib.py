@@ -133,6 +133,7 @@ SIGNATURES = {
     "ctclip_prep_batched": [P, I32, I32, P],
     "ctclip_unprep_wgrad": [P, I64, P, I64, I32, P, P, I32, P, P, P, P, P, P],
     "ctclip_clip_loss": [C.POINTER(LossArgs), P],
+    "ctclip_latent_exchange": [P, P, I32, I32, I32, I32, P, P, C.c_uint32, P],
     "ctclip_clip_sims": [P, I32, P, I32, I32, P, P, P],
     "ctclip_grad_sumsq": [P, I64, P, P],
     "ctclip_adam_step": [P, P, P, P, I64, F32, F32, F32, F32, I32, F32, P, F32, F32, I64, P],

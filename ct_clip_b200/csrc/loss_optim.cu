@@ -205,6 +205,52 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 using namespace ctb;
 
+// ------------------------------------------------------------------------------------------------
+// Data-parallel latent exchange over NVLink peer memory (replaces cat + NCCL all-gather + two copies in front of the loss:
+// the north_star's "all-gather of image/text embeddings before the similarity matmul"). Every rank owns a gather buffer
+// [2 parities][text | image][world*b][L] fp32 and a flag block [2][world] in symmetric memory that all peers have mapped.
+// CTA r of rank k PUSHES rank k's b rows into peer r's buffer (16-byte P2P stores), fences system-wide, releases
+// flag[parity][k] = seq in peer r's flag block, then waits until peer r's rows have landed in its OWN buffer
+// (flag[parity][r] == seq, ld.acquire.sys). When the kernel retires, the local buffer holds the global batch.
+// Two parities: a rank can run at most one step ahead of a peer (it cannot pass the wait of step s+1 before the peer has
+// published s+1, which the peer does after its own step-s kernels), so buffers of step s are never overwritten while read.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) latent_exchange_kernel(const float* __restrict__ t_raw, const float* __restrict__ i_raw, int b,
+                                                             int L, int rank, int world, const unsigned long long* __restrict__ peer_bufs,
+                                                             const unsigned long long* __restrict__ peer_flags, unsigned seq) {
+  const int r = blockIdx.x;   // peer served by this CTA
+  const int par = (int)(seq & 1u);
+  const size_t half = (size_t)world * b * L;
+  float* base = reinterpret_cast<float*>(peer_bufs[r]) + (size_t)par * 2 * half + (size_t)rank * b * L;
+  float4* dt = reinterpret_cast<float4*>(base);
+  float4* di = reinterpret_cast<float4*>(base + half);
+  const float4* st = reinterpret_cast<const float4*>(t_raw);
+  const float4* si = reinterpret_cast<const float4*>(i_raw);
+  const int n4 = b * L / 4;
+  for (int k = threadIdx.x; k < n4; k += blockDim.x) {
+    dt[k] = st[k];
+    di[k] = si[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* pf = reinterpret_cast<unsigned*>(peer_flags[r]) + par * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf), "r"(seq) : "memory");
+    const unsigned* lf = reinterpret_cast<const unsigned*>(peer_flags[rank]) + par * world + r;
+    unsigned v = 0;
+    unsigned long long spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(lf) : "memory");
+      if (v == seq) break;
+      if (++spins > (1ull << 28)) {   // a peer that never arrives must not hang the box
+        printf("ctclip: latent exchange watchdog: rank %d waited for rank %d, step %u (flag %u)\n", rank, r, seq, v);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
 extern "C" int ctclip_clip_loss(const ctclip_loss_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CTB_CHECK_ARG(a && a->t_raw && a->i_raw && a->temperature && a->t_hat && a->i_hat && a->inv_norm && a->sim,
@@ -265,6 +311,19 @@ extern "C" int ctclip_adam_step(float* p, const float* g, float* m, float* v, in
   if (ctas > cap) ctas = cap;
   adam_kernel<<<(int)ctas, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), max_norm, sumsq,
                                             grad_scale, 1.f - lr * weight_decay, weight_decay > 0.f ? (long long)n_decay : 0LL);
+  CTB_LAUNCH_CHECK();
+  return CTCLIP_OK;
+}
+
+extern "C" int ctclip_latent_exchange(const float* t_raw, const float* i_raw, int32_t b, int32_t L, int32_t rank, int32_t world,
+                                      const uint64_t* peer_bufs, const uint64_t* peer_flags, uint32_t seq, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CTB_CHECK_ARG(t_raw && i_raw && peer_bufs && peer_flags, "latent_exchange: null pointer");
+  CTB_CHECK_ARG(b > 0 && L > 0 && (b * (long long)L) % 4 == 0, "latent_exchange: b*L must be a multiple of 4");
+  CTB_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world && seq > 0, "latent_exchange: bad rank / world / step");
+  latent_exchange_kernel<<<world, 256, 0, stream>>>(t_raw, i_raw, b, L, rank, world,
+                                                   reinterpret_cast<const unsigned long long*>(peer_bufs),
+                                                   reinterpret_cast<const unsigned long long*>(peer_flags), seq);
   CTB_LAUNCH_CHECK();
   return CTCLIP_OK;
 }

@@ -353,6 +353,12 @@ def clip_loss(t_raw, i_raw, temperature, *, B, L, t_hat, i_hat, inv_norm, sim, l
     call("ctclip_clip_loss", C.byref(a), _stream())
 
 
+def latent_exchange(t_raw, i_raw, *, b, L, rank, world, peer_bufs, peer_flags, step):
+    """one kernel: push this rank's raw latents into every peer's gather buffer over NVLink, release / acquire the step flags"""
+    call("ctclip_latent_exchange", t_raw.data_ptr(), i_raw.data_ptr(), b, L, rank, world, peer_bufs.data_ptr(),
+         peer_flags.data_ptr(), step, _stream())
+
+
 def clip_sims(t_hat, Bt, i_hat, Bi, L, temperature, out):
     call("ctclip_clip_sims", t_hat.data_ptr(), Bt, i_hat.data_ptr(), Bi, L, temperature.data_ptr(), out.data_ptr(),
          _stream())

@@ -17,6 +17,7 @@ B200-first differences (all documented in DESIGN.md):
 from __future__ import annotations
 
 import os
+import warnings
 from pathlib import Path
 
 import torch
@@ -249,8 +250,32 @@ class CTClipTrainer(nn.Module):
                 dist.broadcast(b, src=0)
         clip.mark_weights_dirty()
 
-        from .dist_utils import gather_latents as gather
+        from .dist_utils import PeerLatentExchange, gather_latents as gather
         clip.dp_all_gather = gather
+        self.latent_exchange = None
+        if os.environ.get("CTCLIP_DP_EXCHANGE", "p2p") != "nccl":
+            # one kernel over NVLink peer memory; the mapping is set up at the first step. Every rank takes the same branch: a
+            # failure of the (collective) setup is agreed on with an all-reduce before the fallback to NCCL is chosen.
+            xch = PeerLatentExchange(self.device)
+
+            def exchange(t_raw, i_raw, _x=xch):
+                if self.latent_exchange is False:
+                    return gather(t_raw, i_raw)
+                if _x.key is None:
+                    ok = torch.ones(1, device=self.device)
+                    try:
+                        _x._setup(*t_raw.shape)
+                    except Exception as e:      # noqa: BLE001  (no P2P / no symmetric memory on this box)
+                        ok.zero_()
+                        warnings.warn(f"peer-memory latent exchange unavailable ({e!r}); using the NCCL all-gather")
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if ok.item() < 1:
+                        self.latent_exchange, _x.key = False, None
+                        return gather(t_raw, i_raw)
+                    self.latent_exchange = _x
+                return _x(t_raw, i_raw)
+
+            clip.dp_all_gather = exchange
         self.bucketer = GradBucketer(self.arena)
         clip.dp_early_reduce = self.bucketer.tensor_ready
         clip.dp_grad_ready = self.bucketer.prefix_ready

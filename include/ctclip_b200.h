@@ -398,6 +398,14 @@ typedef struct {
   float loss_scale;
 } ctclip_loss_args;
 int ctclip_clip_loss(const ctclip_loss_args* args, void* stream);
+/* Data-parallel exchange of the raw latents over NVLink peer memory, in front of ctclip_clip_loss (replaces the embedding
+ * all-gather the north_star names; the reference's own gather, CT_CLIP/ct_clip/distributed.py:9-34, is dead code).
+ * peer_bufs[r] / peer_flags[r]: device addresses, valid on THIS device, of rank r's gather buffer
+ * ([2 parities][text | image][world*b][L] fp32) and flag block ([2][world] uint32, zero before the first call); the caller
+ * maps them (e.g. torch symmetric memory). step >= 1 and identical on all ranks, +1 per call. On return (stream order) the
+ * local buffer of parity step & 1 holds the global batch ordered by rank. One kernel: push + release + acquire. */
+int ctclip_latent_exchange(const float* t_raw, const float* i_raw, int32_t b, int32_t L, int32_t rank, int32_t world,
+                           const uint64_t* peer_bufs, const uint64_t* peer_flags, uint32_t step, void* stream);
 /* inference similarity (ct_clip.py:805-807), broadcasting a batch of 1 */
 int ctclip_clip_sims(const float* t_hat, int32_t Bt, const float* i_hat, int32_t Bi, int32_t L, const float* temperature,
                      float* out, void* stream);

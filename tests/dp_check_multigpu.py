@@ -67,8 +67,8 @@ def main():
             if v.numel() == 0 or v.abs().max().item() < 1e-5 * gmax:
                 continue
             # relative RMS difference; tensors whose gradient is analytically zero (the key bias of a softmax attention: 1.6e-6
-            # of rounding noise at a global scale of 0.11) are measured against 1e-4 of the global gradient scale instead
-            e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-4 * gmax)).item()
+            # of rounding noise at a global scale of 0.11) are measured against 1e-3 of the global gradient scale instead
+            e = ((grads_dp[k] - v).pow(2).mean().sqrt() / v.pow(2).mean().sqrt().clamp_min(1e-3 * gmax)).item()
             errs.append((e, k, v.pow(2).mean().sqrt().item(), grads_dp[k].pow(2).mean().sqrt().item()))
             if e > gworst:
                 gworst, gname = e, k
@@ -95,6 +95,34 @@ def main():
         print("dp_check gates:", gates, "gmax", gmax)
         ok = all(gates.values())
         print("DP_CHECK", "PASS" if ok else "FAIL")
+    dist.barrier()
+    # ---- the peer-memory latent exchange (one kernel, NVLink P2P stores + release/acquire flags) against NCCL's all-gather,
+    # many back-to-back steps with different data and a deliberately skewed rank, so that a protocol bug (stale parity buffer,
+    # flag reuse) cannot hide behind timing
+    from ct_clip_b200.dist_utils import gather_latents
+    xch = tr.latent_exchange
+    ok_x = True
+    if xch:
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        for it in range(300):
+            t = torch.randn(b, 512, device=dev, generator=g)
+            i = torch.randn(b, 512, device=dev, generator=g)
+            if it % 7 == rank:          # skew: this rank arrives late
+                torch.cuda._sleep(2_000_000)
+            tg, ig = xch(t, i)
+            tg, ig = tg.clone(), ig.clone()
+            tn, inn = gather_latents(t, i)
+            ok_x = ok_x and torch.equal(tg, tn) and torch.equal(ig, inn)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"dp_check world={world}: peer-memory latent exchange == NCCL all-gather over 300 skewed steps: {ok_x}")
+    elif rank == 0:
+        print(f"dp_check world={world}: peer-memory latent exchange NOT active (NCCL path): {xch!r}")
+    okt = torch.tensor([1.0 if (ok and ok_x) else 0.0], device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    ok = okt.item() > 0
+    if rank == 0:
+        print("DP_CHECK_ALL", "PASS" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
