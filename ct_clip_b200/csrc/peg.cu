@@ -464,12 +464,6 @@ __global__ void __launch_bounds__(PEG_THREADS, 1) peg_wgrad4_kernel(ctclip_peg_a
 
 }  // namespace ctb
 
-namespace ctb {   // tensor-core path (peg_mma.cu)
-bool peg_mma_supported(const ctclip_peg_args* a, bool wgrad);
-int peg_mma_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream);
-int peg_mma_launch_wgrad(const ctclip_peg_args* a, cudaStream_t stream);
-}
-
 namespace ctb {   // plane-streaming path (peg_stream.cu): the default whenever the token grid allows it
 bool peg_stream_supported(const ctclip_peg_args* a, bool wgrad);
 int peg_stream_launch_conv(int mode, const ctclip_peg_args* a, cudaStream_t stream);
@@ -540,7 +534,6 @@ extern "C" int ctclip_peg_fwd(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_fwd")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_fwd: null y/weight");
-  if (peg_mma_supported(a, false)) return peg_mma_launch_conv(0, a, stream);
   if (peg_stream_supported(a, false)) return peg_stream_launch_conv(0, a, stream);
   return peg_launch_conv(0, a, stream);
 }
@@ -550,7 +543,6 @@ extern "C" int ctclip_peg_bwd_data(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_data")) return rc;
   CTB_CHECK_ARG(a->y && a->weight, "peg_bwd_data: null y/weight");
-  if (peg_mma_supported(a, false)) return peg_mma_launch_conv(1, a, stream);
   if (peg_stream_supported(a, false)) return peg_stream_launch_conv(1, a, stream);
   return peg_launch_conv(1, a, stream);
 }
@@ -560,7 +552,6 @@ extern "C" int ctclip_peg_bwd_weight(const ctclip_peg_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = peg_check(a, "peg_bwd_weight")) return rc;
   CTB_CHECK_ARG(a->dy && a->dweight, "peg_bwd_weight: null dy/dweight");
-  if (peg_mma_supported(a, true)) return peg_mma_launch_wgrad(a, stream);
   if (peg_stream_supported(a, true)) return peg_stream_launch_wgrad(a, stream);
   return peg_launch_wgrad(a, stream);
 }

@@ -67,23 +67,70 @@ class CTClipInference(nn.Module):
             tok = dict(input_ids=enc.input_ids, attention_mask=enc.attention_mask)
         return _Tokens(tok["input_ids"].to(self.device), tok["attention_mask"].to(self.device))
 
+    def _host_batches(self):
+        """(pinned volume batch, release(), rest of the batch) with the collation of batch k+1 running in a background thread while the
+        GPU works on batch k: the volumes are stacked straight into one of three reusable PINNED buffers (one memcpy; the default
+        collate builds a pageable tensor, whose host-to-device copy is synchronous), and a buffer is only reused after the event
+        recorded behind its H2D copy has fired."""
+        import queue
+        import threading
+        q = queue.Queue(maxsize=1)
+        bufs, events = [None] * 3, [None] * 3
+
+        def work():
+            try:
+                it = iter(torch.utils.data.DataLoader(self.ds, num_workers=self.dl.num_workers, batch_size=self.dl.batch_size,
+                                                      shuffle=False, collate_fn=lambda items: items))
+                for k, items in enumerate(it):
+                    vols = [torch.as_tensor(x[0]) for x in items]
+                    slot = k % 3
+                    if events[slot] is not None:
+                        events[slot].synchronize()
+                    shape = (len(vols),) + tuple(vols[0].shape)
+                    if bufs[slot] is None or bufs[slot].shape[1:] != shape[1:] or bufs[slot].dtype != vols[0].dtype or bufs[slot].shape[0] < shape[0]:
+                        bufs[slot] = torch.empty(shape, dtype=vols[0].dtype).pin_memory()
+                    dst = bufs[slot][:len(vols)]
+                    torch.stack(vols, out=dst)
+                    rest = [[x[j] for x in items] for j in range(1, len(items[0]))]
+                    q.put((slot, dst, rest))
+                q.put(None)
+            except BaseException as e:      # noqa: BLE001  (re-raised in the consumer)
+                q.put(e)
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            slot, dst, rest = item
+
+            def copied(slot=slot):
+                events[slot] = torch.cuda.Event()
+                events[slot].record()
+            yield dst, copied, rest
+        th.join()
+
     @torch.no_grad()
     def infer(self, log_fn=lambda logs: None):
         self.CTClip.eval()
         from . import ops
         text_lat = self.CTClip.encode_text_latents(self._bank())              # (36, L), once
         predicted, real, names = [], [], []
-        for batch in self.dl:
-            vol = batch[0].to(self.device, non_blocking=True)
+        for host_vol, copied, rest in self._host_batches():
+            vol = host_vol.to(self.device, non_blocking=True)
+            copied()
             img_lat = self.CTClip.encode_image_latents(vol)                     # (b, L), one image pass per volume
             probs = torch.empty(vol.shape[0], len(PATHOLOGIES), device=self.device)
             ops.zero_shot_probs(img_lat, text_lat, self.CTClip.temperature, probs)   # sims * exp(T) + pair softmax (zero_shot.py:140-143)
-            predicted.append(probs.cpu().numpy())
-            if len(batch) > 2:
-                real.append(np.asarray(batch[2]).reshape(vol.shape[0], -1))
-            if len(batch) > 3:
-                names += list(batch[3]) if not isinstance(batch[3], str) else [batch[3]]
-        predicted = np.concatenate(predicted, axis=0)
+            predicted.append(probs)                                             # read back once, after the last batch
+            if len(rest) > 1:
+                real.append(np.asarray([np.asarray(r) for r in rest[1]]).reshape(vol.shape[0], -1))
+            if len(rest) > 2:
+                names += [str(n) for n in rest[2]]
+        predicted = torch.cat(predicted, dim=0).cpu().numpy()
         np.savez(self.results_folder / "predicted_weights.npz", data=predicted)    # zero_shot.py:152-165
         if real:
             np.savez(self.results_folder / "labels_weights.npz", data=np.concatenate(real, axis=0))

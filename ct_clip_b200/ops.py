@@ -108,10 +108,7 @@ def patchify(video, xhat, *, B, Cc, F, H, W, pt, p1, p2, eps=1e-5, ld_out=None):
 
 
 def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_bf16=None, dy=None, dweight=None,
-              dbias=None, lines=4, canon_table=None, mma=False):
-    """mma=True opts in to the bf16 tensor-core formulation (ctclip_peg_args.lines = -2); default = exact fp32 stencil."""
-    if mma:
-        lines = -2
+              dbias=None, lines=4, canon_table=None):
     a = PegArgs()
     a.x, a.dy, a.y, a.y_bf16 = x.data_ptr(), _ptr(dy), _ptr(y), _ptr(y_bf16)
     a.weight, a.bias, a.dweight, a.dbias = _ptr(weight), _ptr(bias), _ptr(dweight), _ptr(dbias)
@@ -121,7 +118,7 @@ def _peg_args(x, *, B, T, H, W, D, temporal, weight=None, bias=None, y=None, y_b
 
 
 def _peg_tag(kw):
-    return ("temporal" if kw.get("temporal") else "spatial") + (" mma" if kw.get("mma") else "")
+    return "temporal" if kw.get("temporal") else "spatial"
 
 
 def peg_fwd(x, y, weight, bias, **kw):

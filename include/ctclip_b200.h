@@ -154,8 +154,8 @@ int ctclip_patchify(const ctclip_patchify_args* args, void* stream);
  * PEG: causal depthwise 3x3x3 conv + residual on the canonical fp32 token stream [B,T,H,W,D].
  * attention.py:63-84 + the residual at :324. temporal = 1 reproduces the reference's reshape of
  * the (b,h,w,t)-ordered tokens as (b,T,H,W) (SURVEY trap T1).
- * Default arithmetic: exact fp32 (packed FFMA2 stencil, csrc/peg.cu); lines = -2 selects the bf16 m16n8k16 formulation
- * with block-diagonal weights (csrc/peg_mma.cu), kept as a measured alternative.
+ * Exact fp32 arithmetic (packed FFMA2): the plane-streaming TMA kernels of csrc/peg_stream.cu whenever the token grid allows
+ * them (W <= 24, D % 32 == 0, temporal only for T == H == W), the general stencil of csrc/peg.cu otherwise.
  *   ctclip_peg_fwd        : y = x + conv(x) + bias          (y_bf16 optional bf16 copy)
  *   ctclip_peg_bwd_data   : y = x + conv^T(x)  with x = upstream gradient
  *   ctclip_peg_bwd_weight : dweight[D,27] += ..., dbias[D] += ...  (x = forward input, dy = upstream)
@@ -171,9 +171,7 @@ typedef struct {
   float* dbias;
   int32_t B, T, H, W, D;
   int32_t temporal;
-  int32_t lines;       /* -2: opt in to the bf16 tensor-core formulation (csrc/peg_mma.cu: conv operands rounded to bf16 like
-                          the reference's autocast; measured slower than the default on B200); anything else: exact fp32
-                          packed-FFMA2 stencil kernels (csrc/peg.cu) */
+  int32_t lines;       /* reserved (was: selector of a bf16 tensor-core formulation that measured slower and was removed) */
   const int32_t* canon_table; /* optional, temporal only: canon_table[f] = canonical token of conv-grid index
                                  f = (a0*H + a1)*W + a2, i.e. ((f % T)*H + f / (T*W))*W + (f / T) % W */
 } ctclip_peg_args;
