@@ -311,9 +311,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 // the item; both are drained by the softmax warps one block later, while the tensor pipe already works on the next block.
 // Operands stream through TMA rings that run across item boundaries (K/V block ring of 2, Q/dO chunk ring of 4 -- each
 // chunk is re-read once per key block from L2), so there is no per-item prologue bubble.
-// The gradient of the position-bias table needs sum over sequences of dS: the bf16 dS^T tiles are spilled (the kernel is
-// exp/issue bound, the writes ride along) and attn_dtab_reduce_kernel sums them over the sequences straight into the
-// (2H-1)(2W-1) table bins -- the [heads, n, n] dbias tensor of the mma.sync path never exists.
+// The gradient of the position-bias table needs sum over sequences of dS: the bf16 dS^T tiles are spilled (read back from the
+// shared tile so that every global store covers full 32-byte sectors) and attn_dtab_reduce_kernel sums them over the
+// sequences straight into the (2H-1)(2W-1) table bins -- the [heads, n, n] dbias tensor of the mma.sync path never exists.
+// The kernel is bound by shared-memory wavefronts (ncu: LSU 39 % + tensor-core operand fetch 26 %), not by the tensor pipe
+// (17 %) or the SFU (22 %): profiles/r2_ncu_attn_bwd.txt.
 // ------------------------------------------------------------------------------------------------------------------
 struct TcBwdParams {
   int n, heads, H, num_seqs;

@@ -248,8 +248,9 @@ int ctclip_attn_bwd(const ctclip_attn_args* args, void* stream);
 int ctclip_attn_tc_supported(int32_t n, int32_t grid_h, int32_t grid_w, int32_t dim_head);
 /* out[0] = max_d |q_scale[d] * k_scale[d]|  (attention.py:131-132 parameters): the qk_bound of ctclip_attn_args */
 int ctclip_qk_bound(const float* q_scale, const float* k_scale, int32_t dim_head, float* out, void* stream);
-/* measurement knob (tools/attn_tc_probe.py, not used by the product path): softmax-backward warps of the tcgen05 backward kernel,
- * 8 or 16 (default 16) */
+/* measurement knob (tools/attn_tc_probe.py, tests; not used by the product path): variant of the tcgen05 backward kernel.
+ * 8 / 16 = element-wise warps with per-query records in shared memory; 108 / 116 = the same with lse and delta folded into the
+ * MMAs as two extra k-steps (108 is the default) */
 int ctclip_debug_set_attn_bwd_warps(int32_t warps);
 
 /* Backward of x_hat = x/max(||x||,1e-12)*scale per (row, head) (attention.py:152-154):
