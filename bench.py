@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--depth", type=int, default=12, help="spatial_depth = temporal_depth (configs[1]: 12; reference scripts: 4)")
     ap.add_argument("--batch", type=int, default=8, help="volumes per GPU")
+    ap.add_argument("--dim", type=int, default=512, help="CTViT width (configs[1]: 512; configs[4]: 768 with --image 512 --frames 320 --depth 24)")
     ap.add_argument("--image", type=int, default=480)
     ap.add_argument("--frames", type=int, default=240)
     ap.add_argument("--text-len", type=int, default=128)
@@ -151,7 +152,7 @@ def write_stage_table(path, rows, step_ms):
 
 def flops_per_volume(cfgd):
     """SURVEY 8(d) algorithmic FLOPs of one forward pass per volume (and the x3 step estimate)."""
-    D, I, F, P, C, L = 512, 256, 1365, cfgd["P"], 8192, 512
+    D, I, F, P, C, L = cfgd.get("D", 512), 256, int(cfgd.get("D", 512) * 4 * 2 / 3), cfgd["P"], 8192, 512
     N, S, T = cfgd["N"], cfgd["S"], cfgd["T"]
     layer_s = 54 * N * D + 8 * N * D * I + 4 * N * S * I + 6 * N * D * F
     layer_t = 54 * N * D + 8 * N * D * I + 4 * N * T * I + 6 * N * D * F
@@ -164,12 +165,12 @@ def build_model(args, device):
 
     from ct_clip_b200 import CTCLIP, CTViT
     torch.manual_seed(0)
-    vit = CTViT(dim=512, codebook_size=8192, image_size=args.image, patch_size=args.image // 24 if args.image % 24 == 0 else 16,
+    vit = CTViT(dim=args.dim, codebook_size=8192, image_size=args.image, patch_size=args.image // 24 if args.image % 24 == 0 else 16,
                 temporal_patch_size=args.frames // 24 if args.frames % 24 == 0 else 8, spatial_depth=args.depth,
                 temporal_depth=args.depth, dim_head=32, heads=8)
     bert = BertModel(BertConfig(num_hidden_layers=args.bert_layers, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
     h, w = vit.patch_height_width
-    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=h * w * 512, dim_latent=512)
+    clip = CTCLIP(image_encoder=vit, text_encoder=bert, dim_text=768, dim_image=h * w * args.dim, dim_latent=512)
     return clip.to(device)
 
 
@@ -339,7 +340,7 @@ def run_b200(args):
     vit = clip.visual_transformer
     g = vit.geom
     T = args.frames // g.temporal_patch
-    cfgd = dict(P=g.patch_voxels, N=T * g.S, S=g.S, T=T, depth=args.depth)
+    cfgd = dict(P=g.patch_voxels, N=T * g.S, S=g.S, T=T, depth=args.depth, D=args.dim)
     fwd_flops, step_flops = flops_per_volume(cfgd)
     if world > 1:      # leave the NCCL communicator cleanly on every rank (NCCL warns about leaked process groups otherwise)
         dist.barrier()
@@ -354,7 +355,7 @@ def run_b200(args):
         "value": vols / (ms * 1e-3), "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: CTViT dim512 depth{args.depth}+{args.depth}, {args.image}x{args.image}x{args.frames} "
+        "config": {"workload": f"BASELINE configs[{1 if args.dim == 512 else 4}]: CTViT dim{args.dim} depth{args.depth}+{args.depth}, {args.image}x{args.image}x{args.frames} "
                                f"int16 volumes, patch ({g.patch_hw[0]},{g.patch_hw[1]},{g.temporal_patch}), {args.text_len}-token text, "
                                f"BERT-base({args.bert_layers}L, random init), bs{args.batch}/GPU",
                    "global_batch": args.batch * world, "parallelism": f"dp{world}",

@@ -42,8 +42,14 @@ CFG5_SMALL = dict(dim=768, codebook_size=1024, image_size=64, patch_size=16, tem
                   temporal_depth=1, dim_head=32, heads=8)
 
 
-@pytest.mark.parametrize("kw,frames", [(CFG1_VIT, 32), (CFG5_SMALL, 48)], ids=["cfg1", "cfg5_small"])
-def test_contrastive_step_matches_oracle(kw, frames):
+# gradient gates = measured on B200 (round 2) x ~1.6: the relative RMS error of a gradient grows with the number of layers its signal
+# crosses (bf16 storage of every saved activation, like the reference under bf16 autocast): 4+4 layers: median 3.1e-2, p90 3.8e-2,
+# worst 4.8e-2 (q_scale / k_scale of the deepest layers); 1+1 layers at dim 768: median 1.5e-2, p90 1.8e-2, worst 2.6e-2
+GRAD_GATES = {"cfg1": dict(worst=8e-2, p90=6e-2, median=4.5e-2), "cfg5_small": dict(worst=5e-2, p90=3.5e-2, median=2.5e-2)}
+
+
+@pytest.mark.parametrize("kw,frames,gate", [(CFG1_VIT, 32, "cfg1"), (CFG5_SMALL, 48, "cfg5_small")], ids=["cfg1", "cfg5_small"])
+def test_contrastive_step_matches_oracle(kw, frames, gate):
     from oracle import ctclip_oracle as O
     clip, sd, cfg = build_clip(kw)
     hu, ids, mask = O.synth_inputs(2, frames, 64, 32)
@@ -72,15 +78,16 @@ def test_contrastive_step_matches_oracle(kw, frames):
         e = rms_err(p.grad, ref)
         cos = torch.nn.functional.cosine_similarity(p.grad.detach().float().cpu().reshape(1, -1), ref.reshape(1, -1)).item()
         report[name] = e
-        # every gradient must point the same way (cos >= 0.995) and agree to 1e-1 relative RMS; the bulk agrees to 3e-2
-        if e > 1e-1 or cos < 0.995:
+        # every gradient must point the same way (cos >= 0.995) and stay under the measured worst case of this depth
+        if e > GRAD_GATES[gate]["worst"] or cos < 0.995:
             bad.append((name, e, cos))
     worst = sorted(report.items(), key=lambda kv: -kv[1])[:12]
     print("worst gradient rms errors:", worst)
     errs = sorted(report.values())
     print("median / p90 gradient rms error:", errs[len(errs) // 2], errs[int(0.9 * len(errs))])
     assert not bad, bad
-    assert errs[len(errs) // 2] < 5e-2, errs[len(errs) // 2]
+    assert errs[len(errs) // 2] < GRAD_GATES[gate]["median"], errs[len(errs) // 2]
+    assert errs[int(0.9 * len(errs))] < GRAD_GATES[gate]["p90"], errs[int(0.9 * len(errs))]
     # ---- code-book EMA side effect of the training-mode forward
     emb = clip.visual_transformer.vq._codebook.embed[0]
     cs = clip.visual_transformer.vq._codebook.cluster_size[0]
