@@ -351,7 +351,7 @@ def run_b200(args):
     vols = args.batch * world * args.steps
     h2d = sum(x.numel() * x.element_size() for x in host[0])
     out = {
-        "metric": "CT volumes/sec contrastive step @ 480x480x240, bs8/GPU",
+        "metric": f"CT volumes/sec contrastive step @ {args.image}x{args.image}x{args.frames}, bs{args.batch}/GPU",
         "value": vols / (ms * 1e-3), "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
