@@ -249,7 +249,9 @@ class CTViTEngine:
         o = torch.empty(M, I, **bf)
         lse = torch.empty(M, g.heads, device=dev) if save else None
         v = kv_raw[:, I:]
-        if tab is not None and self.tc_fwd and not temporal and (self.tc_bwd or not save):     # tcgen05 / TMEM kernel, bias from the table
+        if tab is not None and self.tc_fwd and not temporal:     # tcgen05 / TMEM kernel, bias from the table
+            # (also when only the FORWARD kernel takes the grid, e.g. 32 x 32: both families store lse = log2 sum 2^logit per
+            # (row, head), so the mma.sync backward runs on the tcgen05 forward's outputs)
             ops.attn_fwd(qh, kh, v, o, lse, ldq=I, ldk=I, ldv=2 * I, ldo=I, cpb_table=tab, grid_hw=(g.H, g.W), qk_bound=lw.qkb,
                          **self._attn_geom(b, T, temporal))
         else:

@@ -117,3 +117,45 @@ def test_contrastive_step_headline_geometry():
     others = {k: v for k, v in report.items() if k != "temperature"}
     assert max(others.values()) < 6e-2, worst
     assert errs[int(0.9 * len(errs))] < 3e-2 and errs[len(errs) // 2] < 2e-2, (errs[len(errs) // 2], errs[int(0.9 * len(errs))])
+
+
+GRID32_VIT = dict(dim=512, codebook_size=1024, image_size=256, patch_size=8, temporal_patch_size=4, spatial_depth=1,
+                  temporal_depth=1, dim_head=32, heads=8)
+
+
+def test_contrastive_step_grid32_tc_forward_with_mma_backward():
+    """32 x 32 token grid (S = 1024, the spatial grid of BASELINE configs[4]): the tcgen05 FORWARD kernel takes it, the tcgen05
+    backward does not (its dQ accumulators cover 768 queries of TMEM), so the training step pairs the tcgen05 forward (bias from
+    the fp32 table, lse against the fixed reference) with the mma.sync backward (bf16 fragment-ordered bias). Loss and every
+    gradient against the oracle."""
+    from oracle import ctclip_oracle as O
+    clip, sd, cfg = build_clip(GRID32_VIT, bert_layers=1)
+    eng = clip.visual_transformer.engine
+    assert eng.tc_fwd and not eng.tc_bwd, (eng.tc_fwd, eng.tc_bwd)
+    hu, ids, mask = O.synth_inputs(2, 8, 256, 32)
+    video = hu.float() / 1000.0
+    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.ctclip_forward(sdp, cfg, ids, mask, video, training=True)
+    out["loss"].backward()
+    clip.train()
+    clip.visual_transformer._force_indices = out["indices"]
+    loss = clip(_Tok(ids.cuda(), mask.cuda()), hu.cuda(), device="cuda", return_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - out["loss"].item()) < 1e-2 * abs(out["loss"].item()), (loss.item(), out["loss"].item())
+    gmax = max(v.grad.abs().max().item() for v in sdp.values() if v.is_floating_point() and v.grad is not None)
+    report = {}
+    for name, p in clip.named_parameters():
+        ref = sdp[name].grad
+        if ref is None or ref.numel() == 0 or ref.abs().max().item() < 1e-6 * gmax:
+            continue
+        assert p.grad is not None, f"missing gradient for {name}"
+        report[name] = rms_err(p.grad, ref)
+    errs = sorted(report.values())
+    worst = sorted(report.items(), key=lambda kv: -kv[1])[:6]
+    print("grid 32x32: median / p90 / max gradient rms error:", errs[len(errs) // 2], errs[int(0.9 * len(errs))], errs[-1], worst)
+    t_err = (clip.temperature.grad.float().cpu() - sdp["temperature"].grad).abs().item()
+    assert t_err < 1e-3 * gmax, (t_err, gmax)
+    others = {k: v for k, v in report.items() if k != "temperature"}
+    assert max(others.values()) < 6e-2, worst
+    assert errs[int(0.9 * len(errs))] < 3e-2 and errs[len(errs) // 2] < 2e-2, (errs[len(errs) // 2], errs[int(0.9 * len(errs))])
