@@ -1,2 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_headline_geometry_gpu.py tests/test_ctvit_gpu.py -q -s 2>&1 | grep -E "grid 32|median|passed|failed|Error|assert" | cut -c1-600
+mkdir -p gpurun_out
+timeout 420 python bench.py --dim 768 --image 512 --frames 320 --depth 24 --batch 2 --steps 3 --warmup 3 --no-cpu-baseline \
+  > gpurun_out/r2x_bench_cfg4_b2.json 2> gpurun_out/r2x_bench_cfg4_b2.err
+echo "rc=$?"; head -c 300 gpurun_out/r2x_bench_cfg4_b2.json; echo
