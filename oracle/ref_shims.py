@@ -120,3 +120,22 @@ def load_reference():
     del tm
     _loaded = ref
     return ref
+
+
+def load_reference_dataset_class():
+    """The unmodified reference dataset class (scripts/data.py: CTReportDataset) with a nibabel stub whose `load` the caller
+    replaces: used to pin oracle.ctclip_oracle.ct_preprocess against data.py:92-162 (nii_img_to_tensor)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    import importlib.util
+    if "nibabel" not in sys.modules:
+        _stub("nibabel", load=lambda *a, **k: (_ for _ in ()).throw(RuntimeError("nibabel stub")))
+    if "tqdm" not in sys.modules:
+        try:
+            import tqdm  # noqa: F401
+        except ImportError:
+            _stub("tqdm", tqdm=lambda x, **k: x)
+    spec = importlib.util.spec_from_file_location("_reference_scripts_data", str(REFERENCE_ROOT / "scripts" / "data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

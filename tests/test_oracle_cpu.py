@@ -177,3 +177,64 @@ def test_oracle_bert_dropout_sites_match_transformers_train_mode():
     assert calls == order, calls
     valid = mask.bool()
     assert (hf[valid] - ref[valid]).abs().max().item() < 1e-4
+
+
+def _preprocess_case():
+    """A seeded stored-value volume (H, W, D order of a NIfTI array) that exercises resampling in all three axes, the HU clip on
+    both sides, a centre crop in-plane and padding in depth."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    raw = np.round(rng.normal(900.0, 700.0, size=(300, 280, 60))).clip(0, 4000)
+    return raw, dict(slope=1.0, intercept=-1024.0, xy=1.3, z=2.0)
+
+
+def _digest(t):
+    """shape, statistics and 512 sampled voxels (fixed positions): robust against last-bit differences of F.interpolate between
+    CPU instruction sets, which a hash of all 55 M voxels would not be."""
+    import numpy as np
+    a = t.detach().cpu().contiguous().numpy().astype(np.float64)
+    pos = np.random.default_rng(5).integers(0, a.size, size=512)
+    return dict(shape=list(a.shape), mean=float(a.mean()), std=float(a.std()), min=float(a.min()), max=float(a.max()),
+                frac_padding=float((a == -1.0).mean()), sample_positions_seed=5, samples=[float(v) for v in a.reshape(-1)[pos]])
+
+
+def _digest_close(d, want):
+    assert d["shape"] == want["shape"]
+    for k in ("mean", "std", "frac_padding"):
+        assert abs(d[k] - want[k]) < 1e-6, (k, d[k], want[k])
+    assert d["min"] == want["min"] and d["max"] == want["max"]
+    assert max(abs(x - y) for x, y in zip(d["samples"], want["samples"])) < 1e-6
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference checkout not mounted (GPU box)")
+def test_ct_preprocess_matches_reference_dataset_live():
+    """oracle.ct_preprocess against the UNMODIFIED CTReportDataset.nii_img_to_tensor (scripts/data.py:92-162),
+    bit for bit, with nibabel.load stubbed by an in-memory array and a one-row metadata frame."""
+    import pandas as pd
+    mod = ref_shims.load_reference_dataset_class()
+    raw, m = _preprocess_case()
+
+    class _Img:
+        def get_fdata(self):
+            return raw.astype("float64")
+    mod.nib.load = lambda path: _Img()
+    ds = object.__new__(mod.CTReportDataset)
+    df = pd.DataFrame({"VolumeName": ["case.nii.gz"], "RescaleSlope": [m["slope"]], "RescaleIntercept": [m["intercept"]],
+                       "XYSpacing": [f"[{m['xy']}, {m['xy']}]"], "ZSpacing": [m["z"]]})
+    ref = ds.nii_img_to_tensor("/data/case.nii.gz", df)
+    got = O.ct_preprocess(raw, m["slope"], m["intercept"], m["xy"], m["z"])
+    assert tuple(ref.shape) == tuple(got.shape) == (1, 240, 480, 480)
+    assert torch.equal(ref, got)
+    # the committed digest (tests/golden/preprocess_digest.json) was produced by such a reference run
+    import json
+    from pathlib import Path
+    _digest_close(_digest(ref), json.loads((Path(__file__).parent / "golden" / "preprocess_digest.json").read_text()))
+
+
+def test_ct_preprocess_matches_committed_reference_digest():
+    """Same case without the reference checkout (GPU box): the oracle must reproduce the digest of the reference's output."""
+    import json
+    from pathlib import Path
+    raw, m = _preprocess_case()
+    got = O.ct_preprocess(raw, m["slope"], m["intercept"], m["xy"], m["z"])
+    _digest_close(_digest(got), json.loads((Path(__file__).parent / "golden" / "preprocess_digest.json").read_text()))
